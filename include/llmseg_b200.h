@@ -1,0 +1,130 @@
+/* llmseg_b200 — C ABI of the B200-native LLM-Seg forward path.
+ *
+ * The reference (wangjunchi/LLMSeg) has no FFI / plugin layer: its hot path is pure PyTorch
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds instead of the ATen ops that
+ * `LISAForCausalLM.model_forward` (reference model/LISA.py:225-414) issues; each entry point cites
+ * the reference call site it replaces.  The binding used by this repo is ctypes
+ * (llmseg_b200/_lib.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 or a negative LLMSEG_E* code; text via llmseg_last_error()
+ *   - all pointers are DEVICE pointers unless the name says host; bf16 = 2-byte bfloat16
+ *   - nothing allocates or frees caller memory; work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*) and is asynchronous
+ *   - thread-safe for distinct streams; no global mutable state
+ *   - sm_100 only: any other device returns LLMSEG_EARCH (there is no CPU / other-arch fallback)
+ */
+#ifndef LLMSEG_B200_H_
+#define LLMSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLMSEG_OK 0
+#define LLMSEG_ESHAPE (-1)  /* unsupported / inconsistent shape */
+#define LLMSEG_EALIGN (-2)  /* pointer or stride not 16-byte aligned */
+#define LLMSEG_EARCH (-3)   /* device is not sm_100 */
+#define LLMSEG_ECUDA (-4)   /* CUDA runtime / driver error */
+#define LLMSEG_EARG (-5)    /* null pointer or bad enum */
+
+/* activation applied in the GEMM epilogue (after bias, before residual) */
+#define LLMSEG_ACT_NONE 0
+#define LLMSEG_ACT_GELU 1       /* erf GELU   — SAM MLPBlock, reference common.py:13-26          */
+#define LLMSEG_ACT_QUICK_GELU 2 /* x*sigmoid(1.702x) — CLIP ViT-L/14 MLP (transformers CLIPMLP)  */
+#define LLMSEG_ACT_RELU 3       /* selector MLPs, reference model/transformer.py:13-26           */
+
+#define LLMSEG_GEMM_PLAIN 0
+#define LLMSEG_GEMM_SWIGLU 1 /* W rows interleaved (gate0,up0,gate1,up1,..); C[:, j] = silu(g_j)*u_j */
+#define LLMSEG_GEMM_QKV 2    /* split columns into per-head Q, K and transposed V buffers          */
+
+const char* llmseg_last_error(void);
+int llmseg_version(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py) */
+uint64_t llmseg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * C = epilogue(A · Wᵀ)         tcgen05 / TMEM / TMA GEMM, bf16 in, fp32 accumulate, bf16 out.
+ * Replaces every nn.Linear / 1×1-conv / patch-embed conv on the path:
+ *   SAM  qkv / proj / MLP            reference image_encoder.py:223-224,238-258; common.py:21-26
+ *   SAM  patch-embed + pos, neck     image_encoder.py:111-113,418-426,92-108
+ *   CLIP / LLaMA linears             clip_encoder.py:53-57, llava_llama.py:93-102 (transformers)
+ *   mm_projector, text_hidden_fcs    llava_arch.py:35,95; LISA.py:56-65,317-318
+ * Rounding follows the bf16 reference: bf16(acc+bias) → bf16(act) → bf16(+residual).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int M, N, K;          /* K % 8 == 0 (pad with zeros otherwise)                              */
+  const void* A;        /* bf16 [M, lda]                                                       */
+  int lda;
+  const void* W;        /* bf16 [N, ldw]  (nn.Linear weight layout)                            */
+  int ldw;
+  void* C;              /* bf16 [*, ldc]  (PLAIN / SWIGLU)                                     */
+  int ldc;
+  const void* bias;     /* bf16 [N] or NULL                                                    */
+  const void* residual; /* bf16 [*, ldr] or NULL; row = out_row % res_mod (res_mod 0: no mod)  */
+  int ldr;
+  int res_mod;
+  int act;
+  int mode;
+  const int32_t* out_row_map; /* [M] or NULL: C/residual row of GEMM row r; negative = dropped */
+  /* LLMSEG_GEMM_QKV: N = 3*heads*head_dim, columns ordered (which, head, d).  GEMM row r is
+   * token s = r % seq_in of sequence b = r / seq_in.
+   *   q, k : bf16 [(b*heads+h), seq_pad, head_dim]
+   *   vt   : bf16 [(b*heads+h), head_dim, seq_pad]          (transposed for the PV tensor-core tile)
+   * rope_cos/sin: bf16 [>=seq_in, head_dim/2] rotate-half RoPE applied to q and k (LLaMA) or NULL */
+  void* q;
+  void* k;
+  void* vt;
+  int heads, head_dim, seq_in, seq_pad;
+  const void* rope_cos;
+  const void* rope_sin;
+} llmseg_gemm_params;
+int llmseg_gemm(const llmseg_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused attention  softmax(scale·QKᵀ + bias + mask)·V   (flash-style, tcgen05/TMEM, TMA-fed).
+ *   SAM windowed / global with decomposed rel-pos   image_encoder.py:244-257,354-392
+ *   CLIP ViT-L/14 self-attention                      (transformers CLIPAttention, eager)
+ *   LLaMA causal self-attention (+ right padding)     (transformers LlamaAttention, eager)
+ * q,k,vt are the buffers written by LLMSEG_GEMM_QKV.  out is token-major bf16
+ * [batch*seq, heads*head_dim] (ldo elements per row) ready for the output projection.
+ * rel_h/rel_w: bf16 [2*grid-1, head_dim] tables with seq == grid*grid, or NULL.
+ * kv_len: int32 [batch] number of valid (non right-padded) keys, or NULL for all.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* vt;
+  void* out;
+  int ldo;
+  int batch, heads, head_dim, seq, seq_pad;
+  float scale;
+  int causal;
+  const int32_t* kv_len;
+  const void* rel_h;
+  const void* rel_w;
+  int grid;
+} llmseg_attn_params;
+int llmseg_attention(const llmseg_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row norms (HBM-bound, one warp per row, 16-byte vector loads, warp-shuffle reductions).
+ * out[r] = norm(in[src_row_map ? src_row_map[r] : r]); a negative source row writes zeros
+ * (the SAM 64→70 window padding is zeros *after* LayerNorm, image_encoder.py:179-185,281).
+ *   layernorm : SAM norm1/norm2 (eps 1e-6), LayerNorm2d on NHWC rows (common.py:31-43),
+ *               CLIP LayerNorms (eps 1e-5), selector LayerNorms (transformer.py:240-250)
+ *   rmsnorm   : LLaMA RMSNorm, fp32 variance, eps 1e-6 (transformers LlamaRMSNorm)
+ * ------------------------------------------------------------------------------------------ */
+int llmseg_layernorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
+                     const void* beta, int rows_out, int dim, float eps,
+                     const int32_t* src_row_map, void* stream);
+int llmseg_rmsnorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
+                   int rows, int dim, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMSEG_B200_H_ */

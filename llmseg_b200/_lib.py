@@ -1,0 +1,89 @@
+"""ctypes binding of libllmseg_b200.so (the C ABI in include/llmseg_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing, or a call returns a negative
+LLMSEG_E* code (e.g. LLMSEG_EARCH on a non-sm_100 device), a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libllmseg_b200.so"
+
+c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("A", c_void_p), ("lda", c_int),
+        ("W", c_void_p), ("ldw", c_int),
+        ("C", c_void_p), ("ldc", c_int),
+        ("bias", c_void_p),
+        ("residual", c_void_p), ("ldr", c_int), ("res_mod", c_int),
+        ("act", c_int), ("mode", c_int),
+        ("out_row_map", c_void_p),
+        ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
+        ("heads", c_int), ("head_dim", c_int), ("seq_in", c_int), ("seq_pad", c_int),
+        ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
+        ("out", c_void_p), ("ldo", c_int),
+        ("batch", c_int), ("heads", c_int), ("head_dim", c_int), ("seq", c_int), ("seq_pad", c_int),
+        ("scale", c_float), ("causal", c_int),
+        ("kv_len", c_void_p),
+        ("rel_h", c_void_p), ("rel_w", c_void_p), ("grid", c_int),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    lib.llmseg_last_error.restype = C.c_char_p
+    lib.llmseg_version.restype = c_int
+    lib.llmseg_launch_count.restype = C.c_uint64
+    for name in SYMBOLS:
+        getattr(lib, name)  # raises AttributeError if the .so is stale
+    lib.llmseg_gemm.argtypes = [C.POINTER(GemmParams), c_void_p]
+    lib.llmseg_attention.argtypes = [C.POINTER(AttnParams), c_void_p]
+    lib.llmseg_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                     c_int, c_float, c_void_p, c_void_p]
+    lib.llmseg_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                   c_float, c_void_p]
+
+
+# every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
+SYMBOLS = [
+    "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
+    "llmseg_gemm", "llmseg_attention", "llmseg_layernorm", "llmseg_rmsnorm",
+]
+
+
+def lib():
+    """Load (once) and return the CDLL; raise loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m llmseg_b200.build` "
+                "(llmseg_b200 has no CPU or PyTorch fallback path)")
+        l = C.CDLL(str(LIB_PATH))
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().llmseg_last_error().decode(errors="replace")
+        raise RuntimeError(f"llmseg_b200 {what} failed ({code}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().llmseg_launch_count())

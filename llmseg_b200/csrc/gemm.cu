@@ -1,0 +1,514 @@
+// llmseg_b200 — persistent warp-specialised tcgen05 GEMM  C = epilogue(A · Wᵀ)  for sm_100a.
+//
+//   warp 0 (1 lane)  TMA producer: A[128×64] and W[BN×64] bf16 tiles, 128B-swizzled, mbarrier ring
+//   warp 1 (1 lane)  MMA issuer:   tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 ×4 per stage,
+//                                  fp32 accumulators in TMEM, double-buffered (2×BN columns)
+//   warp 2           TMEM allocator
+//   warps 4..7       epilogue: tcgen05.ld 32 lanes × 32 columns → bias / act / residual / layout → HBM
+//
+// The epilogue variants replace the reference's separate elementwise passes:
+//   PLAIN   bias + {GELU, quick-GELU, ReLU} + residual (+ row scatter for window un-partition,
+//           reference image_encoder.py:291-318, and broadcast residual for pos_embed, :111-113)
+//   SWIGLU  LLaMA MLP  silu(gate)·up  with gate/up rows interleaved in W
+//   QKV     split into per-head Q, K, Vᵀ (reference image_encoder.py:238-242) with optional
+//           rotate-half RoPE on q,k (transformers LlamaAttention.apply_rotary_pos_emb)
+#include <atomic>
+
+#include "common.cuh"
+
+namespace llmseg {
+extern std::atomic<uint64_t> g_launches;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmDev {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  bf16* C;
+  int ldc;
+  const bf16* bias;
+  const bf16* residual;
+  int ldr;
+  int res_mod;
+  int act;
+  const int* out_row_map;
+  bf16* q;
+  bf16* k;
+  bf16* vt;
+  int heads, head_dim, seq_in, seq_pad;
+  const bf16* rope_cos;
+  const bf16* rope_sin;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == LLMSEG_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  if (act == LLMSEG_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+  if (act == LLMSEG_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+__device__ __forceinline__ uint4 ldg16(const bf16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// ---- epilogue: 32 fp32 accumulator columns of one row, PLAIN mode ----------------------------
+__device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, int out_row, int n0) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int col = n0 + j;
+    if (col >= p.N) break;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
+    if (p.bias) {
+      uint4 b = ldg16(p.bias + col);
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = unpack_bf16(bw[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = bf16_round(v[e]);
+    if (p.act != LLMSEG_ACT_NONE) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = bf16_round(apply_act(v[e], p.act));
+    }
+    if (p.residual) {
+      const int rr = p.res_mod > 0 ? out_row % p.res_mod : out_row;
+      uint4 b = ldg16(p.residual + (size_t)rr * p.ldr + col);
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = unpack_bf16(bw[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p.C + (size_t)out_row * p.ldc + col) = o;
+  }
+}
+
+// ---- SWIGLU: columns (2j, 2j+1) = (gate_j, up_j) ---------------------------------------------
+__device__ __forceinline__ void epi_swiglu(const GemmDev& p, const uint32_t* r, int out_row, int n0) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 16) {
+    const int col = n0 + j;
+    if (col >= p.N) break;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = bf16_round(__uint_as_float(r[j + 2 * e]));
+      const float u = bf16_round(__uint_as_float(r[j + 2 * e + 1]));
+      const float a = bf16_round(g / (1.0f + __expf(-g)));
+      o[e] = a * u;
+    }
+    uint4 w;
+    w.x = pack_bf16(o[0], o[1]);
+    w.y = pack_bf16(o[2], o[3]);
+    w.z = pack_bf16(o[4], o[5]);
+    w.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(p.C + (size_t)out_row * p.ldc + (col >> 1)) = w;
+  }
+}
+
+// ---- QKV split (no RoPE): 8-column groups never straddle a head (head_dim % 8 == 0) ----------
+__device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int row, int n0) {
+  const int b = row / p.seq_in;
+  const int s = row - b * p.seq_in;
+  const int hd = p.head_dim;
+  const int hw = p.heads * hd;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int col = n0 + j;
+    if (col >= p.N) break;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
+    if (p.bias) {
+      uint4 bb = ldg16(p.bias + col);
+      const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = unpack_bf16(bw[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+    const int which = col / hw;
+    const int rem = col - which * hw;
+    const int h = rem / hd;
+    const int d = rem - h * hd;
+    const size_t bh = (size_t)b * p.heads + h;
+    if (which < 2) {
+      bf16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq_pad + s) * hd + d;
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      o.z = pack_bf16(v[4], v[5]);
+      o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+      bf16* dst = p.vt + (bh * hd + d) * p.seq_pad + s;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[(size_t)e * p.seq_pad] = __float2bfloat16_rn(v[e]);
+    }
+  }
+}
+
+// ---- QKV split with rotate-half RoPE, head_dim == 128: lo/hi are columns [d0,d0+32) and
+//      [d0+64,d0+96) of the same head; d0 in {0,32}.  cos/sin tables are bf16 [seq, 64]. --------
+__device__ __forceinline__ void epi_qkv_rope(const GemmDev& p, const uint32_t* lo, const uint32_t* hi,
+                                             int row, int col_lo) {
+  const int b = row / p.seq_in;
+  const int s = row - b * p.seq_in;
+  const int hw = p.heads * 128;
+  const int which = col_lo / hw;
+  const int rem = col_lo - which * hw;
+  const int h = rem >> 7;
+  const int d0 = rem & 127;  // 0 or 32
+  const size_t bh = (size_t)b * p.heads + h;
+  if (which == 2) {
+    bf16* dst = p.vt + (bh * 128 + d0) * p.seq_pad + s;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      dst[(size_t)e * p.seq_pad] = __float2bfloat16_rn(__uint_as_float(lo[e]));
+      dst[(size_t)(e + 64) * p.seq_pad] = __float2bfloat16_rn(__uint_as_float(hi[e]));
+    }
+    return;
+  }
+  bf16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq_pad + s) * 128 + d0;
+  const bf16* cs = p.rope_cos + (size_t)s * 64 + d0;
+  const bf16* sn = p.rope_sin + (size_t)s * 64 + d0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 cw = ldg16(cs + j), sw = ldg16(sn + j);
+    const uint32_t c4[4] = {cw.x, cw.y, cw.z, cw.w};
+    const uint32_t s4[4] = {sw.x, sw.y, sw.z, sw.w};
+    float ol[8], oh[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 c = unpack_bf16(c4[e]);
+      const float2 sn2 = unpack_bf16(s4[e]);
+      const float cc[2] = {c.x, c.y}, ss[2] = {sn2.x, sn2.y};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const float x1 = bf16_round(__uint_as_float(lo[j + 2 * e + t]));
+        const float x2 = bf16_round(__uint_as_float(hi[j + 2 * e + t]));
+        // q*cos + rotate_half(q)*sin with bf16 rounding of each product, as the bf16 reference does
+        ol[2 * e + t] = bf16_round(x1 * cc[t]) + bf16_round(-x2 * ss[t]);
+        oh[2 * e + t] = bf16_round(x2 * cc[t]) + bf16_round(x1 * ss[t]);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(ol[0], ol[1]);
+    o.y = pack_bf16(ol[2], ol[3]);
+    o.z = pack_bf16(ol[4], ol[5]);
+    o.w = pack_bf16(ol[6], ol[7]);
+    *reinterpret_cast<uint4*>(dst + j) = o;
+    o.x = pack_bf16(oh[0], oh[1]);
+    o.y = pack_bf16(oh[2], oh[3]);
+    o.z = pack_bf16(oh[4], oh[5]);
+    o.w = pack_bf16(oh[6], oh[7]);
+    *reinterpret_cast<uint4*>(dst + 64 + j) = o;
+  }
+}
+
+template <int BN, int MODE, bool ROPE>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmDev p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_tiles;
+        const int n_blk = tile / p.num_m_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 1024, UMMA_SW128);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      int out_row = row;
+      if (MODE != LLMSEG_GEMM_QKV && p.out_row_map != nullptr && row < p.M)
+        out_row = p.out_row_map[row];
+      const bool live = row < p.M && out_row >= 0;
+      if (MODE == LLMSEG_GEMM_QKV && ROPE) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 128; ++c) {
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t lo[32], hi[32];
+            tmem_ld32(taddr + c * 128 + half * 32, lo);
+            tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
+            tmem_ld_wait();
+            const int col = n_blk * BN + c * 128 + half * 32;
+            if (live && col < p.N) epi_qkv_rope(p, lo, hi, row, col);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (live && n0 < p.N) {
+            if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0);
+            else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
+            else epi_qkv(p, r, row, n0);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int MODE, bool ROPE>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int grid,
+           cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, MODE, ROPE>;
+  static bool attr_done = false;  // idempotent; a race only repeats the call
+  if (!attr_done) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<BN>::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, 256, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+}  // namespace llmseg
+
+using namespace llmseg;
+
+extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LLMSEG_REQUIRE(p != nullptr, LLMSEG_EARG, "llmseg_gemm: null params");
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, LLMSEG_ESHAPE, "llmseg_gemm: empty problem %dx%dx%d",
+                 p->M, p->N, p->K);
+  LLMSEG_REQUIRE(p->K % 8 == 0 && p->lda % 8 == 0 && p->ldw % 8 == 0, LLMSEG_ESHAPE,
+                 "llmseg_gemm: K=%d lda=%d ldw=%d must be multiples of 8", p->K, p->lda, p->ldw);
+  LLMSEG_REQUIRE(p->N % 8 == 0, LLMSEG_ESHAPE, "llmseg_gemm: N=%d must be a multiple of 8", p->N);
+  LLMSEG_REQUIRE(p->A && p->W, LLMSEG_EARG, "llmseg_gemm: null A/W");
+  LLMSEG_REQUIRE(p->mode >= 0 && p->mode <= 2, LLMSEG_EARG, "llmseg_gemm: bad mode %d", p->mode);
+  LLMSEG_REQUIRE(p->act >= 0 && p->act <= 3, LLMSEG_EARG, "llmseg_gemm: bad act %d", p->act);
+
+  GemmDev d{};
+  d.M = p->M; d.N = p->N; d.K = p->K;
+  d.C = static_cast<bf16*>(p->C); d.ldc = p->ldc;
+  d.bias = static_cast<const bf16*>(p->bias);
+  d.residual = static_cast<const bf16*>(p->residual); d.ldr = p->ldr; d.res_mod = p->res_mod;
+  d.act = p->act; d.out_row_map = p->out_row_map;
+  d.q = static_cast<bf16*>(p->q); d.k = static_cast<bf16*>(p->k); d.vt = static_cast<bf16*>(p->vt);
+  d.heads = p->heads; d.head_dim = p->head_dim; d.seq_in = p->seq_in; d.seq_pad = p->seq_pad;
+  d.rope_cos = static_cast<const bf16*>(p->rope_cos);
+  d.rope_sin = static_cast<const bf16*>(p->rope_sin);
+
+  bool rope = false;
+  if (p->mode == LLMSEG_GEMM_QKV) {
+    LLMSEG_REQUIRE(p->q && p->k && p->vt, LLMSEG_EARG, "llmseg_gemm(QKV): null q/k/vt");
+    LLMSEG_REQUIRE(p->heads > 0 && p->head_dim % 8 == 0 && p->N == 3 * p->heads * p->head_dim,
+                   LLMSEG_ESHAPE, "llmseg_gemm(QKV): N=%d != 3*%d*%d", p->N, p->heads, p->head_dim);
+    LLMSEG_REQUIRE(p->seq_in > 0 && p->seq_pad >= p->seq_in && p->seq_pad % 8 == 0 &&
+                       p->M % p->seq_in == 0,
+                   LLMSEG_ESHAPE, "llmseg_gemm(QKV): M=%d seq_in=%d seq_pad=%d inconsistent", p->M,
+                   p->seq_in, p->seq_pad);
+    rope = p->rope_cos != nullptr;
+    if (rope)
+      LLMSEG_REQUIRE(p->head_dim == 128 && p->rope_sin != nullptr, LLMSEG_ESHAPE,
+                     "llmseg_gemm(QKV+RoPE): head_dim must be 128 (got %d)", p->head_dim);
+  } else {
+    LLMSEG_REQUIRE(p->C != nullptr, LLMSEG_EARG, "llmseg_gemm: null C");
+    LLMSEG_REQUIRE(p->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0, LLMSEG_EALIGN,
+                   "llmseg_gemm: C / ldc not 16-byte aligned");
+    if (p->residual)
+      LLMSEG_REQUIRE(p->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p->residual) & 15) == 0,
+                     LLMSEG_EALIGN, "llmseg_gemm: residual / ldr not 16-byte aligned");
+    if (p->mode == LLMSEG_GEMM_SWIGLU)
+      LLMSEG_REQUIRE(p->N % 16 == 0, LLMSEG_ESHAPE, "llmseg_gemm(SWIGLU): N=%d %% 16 != 0", p->N);
+  }
+  if (p->bias)
+    LLMSEG_REQUIRE((reinterpret_cast<uintptr_t>(p->bias) & 15) == 0, LLMSEG_EALIGN,
+                   "llmseg_gemm: bias not 16-byte aligned");
+
+  // tile shape: BN=256 when it still fills the machine, else BN=128 for more CTAs
+  const int m_tiles = (p->M + BM - 1) / BM;
+  const int sms = num_sms();
+  int bn = 256;
+  if (p->N < 256 || m_tiles * ((p->N + 255) / 256) < sms) bn = 128;
+  d.num_m_tiles = m_tiles;
+  d.num_n_tiles = (p->N + bn - 1) / bn;
+  d.num_k_blocks = (p->K + BK - 1) / BK;
+  const int tiles = d.num_m_tiles * d.num_n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
+    uint64_t str[1] = {(uint64_t)p->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    if (int e = make_tmap_bf16(&tmA, p->A, 2, dims, str, box, 128)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+    uint64_t str[1] = {(uint64_t)p->ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    if (int e = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, 128)) return e;
+  }
+
+#define LLMSEG_GEMM_DISPATCH(BN_)                                                            \
+  switch (p->mode) {                                                                         \
+    case LLMSEG_GEMM_PLAIN: return launch<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, d, grid, stream); \
+    case LLMSEG_GEMM_SWIGLU: return launch<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, d, grid, stream); \
+    default:                                                                                 \
+      return rope ? launch<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, d, grid, stream)             \
+                  : launch<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, d, grid, stream);           \
+  }
+  if (bn == 256) {
+    LLMSEG_GEMM_DISPATCH(256)
+  } else {
+    LLMSEG_GEMM_DISPATCH(128)
+  }
+#undef LLMSEG_GEMM_DISPATCH
+}
