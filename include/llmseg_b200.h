@@ -91,7 +91,15 @@ int llmseg_gemm(const llmseg_gemm_params* p, void* stream);
  *   LLaMA causal self-attention (+ right padding)     (transformers LlamaAttention, eager)
  * q,k,vt are the buffers written by LLMSEG_GEMM_QKV.  out is token-major bf16
  * [batch*seq, heads*head_dim] (ldo elements per row) ready for the output projection.
- * rel_h/rel_w: bf16 [2*grid-1, head_dim] tables with seq == grid*grid, or NULL.
+ *
+ * Decomposed rel-pos bias rides on the tensor core: the score tile is computed over an extended
+ * reduction dimension  S = [q | qext]·[k | kext]ᵀ  where qext (written by llmseg_relpos_prep) holds
+ * the per-query bias values divided by `scale` and kext is a constant one-hot key-position matrix:
+ *   ext_cols = 32 (14×14 windows): qext[:, kh] = q·rel_h[qh-kh+13], qext[:, 14+kw] = q·rel_w[qw-kw+13];
+ *                                  kext bf16 [256, 32], kext[key, key/14] = kext[key, 14+key%14] = 1
+ *   ext_cols = 64 (64×64 global) : qext[:, kw] = q·rel_w[qw-kw+63];  kext bf16 [128, 64] = [I;I];
+ *                                  the rel_h term is a per-(query, key-row) constant read from
+ *                                  row_bias bf16 [(b*heads+h), seq_pad, 64] (index key/64)
  * kv_len: int32 [batch] number of valid (non right-padded) keys, or NULL for all.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -104,11 +112,23 @@ typedef struct {
   float scale;
   int causal;
   const int32_t* kv_len;
-  const void* rel_h;
-  const void* rel_w;
-  int grid;
+  int ext_cols;         /* 0, 32 or 64 */
+  const void* qext;     /* bf16 [(b*heads+h), seq_pad, ext_cols] or NULL */
+  const void* kext;     /* bf16 constant, see above, or NULL            */
+  const void* row_bias; /* bf16 [(b*heads+h), seq_pad, 64] (ext_cols == 64) or NULL */
 } llmseg_attn_params;
 int llmseg_attention(const llmseg_attn_params* p, void* stream);
+
+/* Rel-pos prologue: QR = q · [rel_h; rel_w]ᵀ on the tensor core (same GEMM kernel, gather
+ * epilogue), scattered into qext (and row_bias for the global case) as described above.
+ * Replaces get_rel_pos + the two einsums of add_decomposed_rel_pos (image_encoder.py:321-392);
+ * q is the UNSCALED query, values are rounded to bf16 like the reference's einsum outputs.
+ *   q      bf16 [bh, seq_pad, head_dim]      rel_hw bf16 [n_pad >= 2*(2*grid-1), head_dim]
+ *          (rows 0..2g-2 = rel_pos_h, rows 2g-1..4g-3 = rel_pos_w, rest zero; n_pad % 8 == 0)
+ *   seq == grid*grid; grid == 14 -> ext_cols 32, row_bias NULL; grid == 64 -> ext_cols 64 + row_bias */
+int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int seq, int seq_pad,
+                       int head_dim, int grid, float inv_scale, void* qext, int ext_cols,
+                       void* row_bias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row norms (HBM-bound, one warp per row, 16-byte vector loads, warp-shuffle reductions).

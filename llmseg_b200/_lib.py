@@ -37,7 +37,7 @@ class AttnParams(C.Structure):
         ("batch", c_int), ("heads", c_int), ("head_dim", c_int), ("seq", c_int), ("seq_pad", c_int),
         ("scale", c_float), ("causal", c_int),
         ("kv_len", c_void_p),
-        ("rel_h", c_void_p), ("rel_w", c_void_p), ("grid", c_int),
+        ("ext_cols", c_int), ("qext", c_void_p), ("kext", c_void_p), ("row_bias", c_void_p),
     ]
 
 
@@ -52,6 +52,8 @@ def _declare(lib):
         getattr(lib, name)  # raises AttributeError if the .so is stale
     lib.llmseg_gemm.argtypes = [C.POINTER(GemmParams), c_void_p]
     lib.llmseg_attention.argtypes = [C.POINTER(AttnParams), c_void_p]
+    lib.llmseg_relpos_prep.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_float, c_void_p, c_int, c_void_p, c_void_p]
     lib.llmseg_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                      c_int, c_float, c_void_p, c_void_p]
     lib.llmseg_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
@@ -61,7 +63,7 @@ def _declare(lib):
 # every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
-    "llmseg_gemm", "llmseg_attention", "llmseg_layernorm", "llmseg_rmsnorm",
+    "llmseg_gemm", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm",
 ]
 
 

@@ -1,5 +1,436 @@
+// llmseg_b200 — fused flash-style attention for sm_100a:  O = softmax(scale·[q|qext]·[k|kext]ᵀ + mask)·V
+//
+// One CTA = one (batch·head, 128-query tile); 192 threads, two CTAs co-resident per SM so one
+// CTA's softmax overlaps the other's tensor-core work.
+//   warp 0      TMA producer: Q tile once, then K tile and Vᵀ tile per 128-key step (single buffers
+//               with separate full/empty barriers: K(j+1) streams in under softmax(j)+PV(j))
+//   warp 1      TMEM allocator + MMA issuer (one lane):
+//                 S(128×128 fp32, TMEM cols 0..127)   = Q·Kᵀ   tcgen05.mma SS, K-major operands
+//                 O(128×HD  fp32, TMEM cols 128..)   += P·V    tcgen05.mma TS: P is read from TMEM
+//   warps 2..5  softmax: thread = query row (tcgen05.ld 32x32b).  Two passes over S in TMEM
+//               (row max, then exp2 → bf16 P written back over the first 64 columns of S), lazy
+//               rescale of O (only when the running max grew by > 2^8), final O/l → HBM.
+// S never reaches shared or global memory; HBM traffic is Q, K, V, O only.
+//
+// Decomposed rel-pos (reference image_encoder.py:354-392) enters through the extended reduction
+// columns qext/kext (see include/llmseg_b200.h): windows use 32 extra columns (rel_h and rel_w),
+// global attention 64 extra columns (rel_w) plus a per-(row, 64-key block) additive constant (rel_h).
+#include <atomic>
+
 #include "common.cuh"
-extern "C" int llmseg_attention(const llmseg_attn_params* p, void* stream) {
-  (void)p; (void)stream;
-  return llmseg::set_error(LLMSEG_ESHAPE, "llmseg_attention: not implemented yet");
+
+namespace llmseg {
+extern std::atomic<uint64_t> g_launches;
+namespace {
+
+constexpr int BM = 128;  // queries per CTA
+constexpr int BN = 128;  // keys per step
+constexpr float LOG2E = 1.4426950408889634f;
+
+template <int HD, int EXT>
+struct ACfg {
+  static constexpr int Q0_BYTES = 128 * 128;                                     // [128 x 64] SW128
+  static constexpr int Q1_BYTES = HD == 80 ? 128 * 32 : (HD == 128 ? 128 * 128 : 0);
+  static constexpr int QX_BYTES = EXT == 1 ? 128 * 64 : (EXT == 2 ? 128 * 128 : 0);
+  static constexpr int E_BYTES = EXT ? 16384 : 0;  // EXT1: 2 tiles x [128 x 32]; EXT2: [128 x 64]
+  static constexpr int V_CHUNK = HD * 128;         // [HD x 64 keys] SW128
+  static constexpr int OFF_Q0 = 0;
+  static constexpr int OFF_Q1 = OFF_Q0 + Q0_BYTES;
+  static constexpr int OFF_QX = OFF_Q1 + Q1_BYTES;
+  static constexpr int OFF_E = OFF_QX + QX_BYTES;
+  static constexpr int OFF_K0 = OFF_E + E_BYTES;
+  static constexpr int OFF_K1 = OFF_K0 + Q0_BYTES;
+  static constexpr int OFF_V = OFF_K1 + Q1_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * V_CHUNK;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int Q_TX = Q0_BYTES + Q1_BYTES + QX_BYTES + E_BYTES;
+  static constexpr int K_TX = Q0_BYTES + Q1_BYTES;
+  static constexpr int V_TX = 2 * V_CHUNK;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int O_COL = 128;
+};
+
+struct AttnDev {
+  bf16* out;
+  int ldo;
+  int heads, seq, seq_pad;
+  float c1;  // scale * log2(e)
+  int causal;
+  const int* kv_len;
+  const bf16* row_bias;  // [(bh), seq_pad, 64] or null
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD, int EXT>
+__global__ void __launch_bounds__(192, 2)
+attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+            const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
+            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
+            const __grid_constant__ CUtensorMap tmE, const AttnDev p) {
+  using C = ACfg<HD, EXT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;
+  uint64_t* v_empty = bars + 4;
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_p = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+
+  int kv_limit = p.seq;
+  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
+  int kv_hi = kv_limit;
+  if (p.causal) kv_hi = min(kv_hi, q0 + BM);
+  const int n_tiles = (kv_hi + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQa);
+    tma_prefetch_desc(&tmKa);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_p, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, C::Q_TX);
+      tma_load_3d(smem + C::OFF_Q0, &tmQa, bar_q, 0, q0, bh);
+      if (HD == 80) tma_load_3d(smem + C::OFF_Q1, &tmQb, bar_q, 64, q0, bh);
+      if (HD == 128) tma_load_3d(smem + C::OFF_Q1, &tmQa, bar_q, 64, q0, bh);
+      if (EXT == 1) {
+        tma_load_3d(smem + C::OFF_QX, &tmQx, bar_q, 0, q0, bh);
+        tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
+        tma_load_2d(smem + C::OFF_E + 8192, &tmE, bar_q, 0, 128);
+      }
+      if (EXT == 2) {
+        tma_load_3d(smem + C::OFF_QX, &tmQx, bar_q, 0, q0, bh);
+        tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = j & 1;
+        const int key0 = j * BN;
+        mbar_wait(k_empty, ph ^ 1);
+        mbar_expect_tx(k_full, C::K_TX);
+        tma_load_3d(smem + C::OFF_K0, &tmKa, k_full, 0, key0, bh);
+        if (HD == 80) tma_load_3d(smem + C::OFF_K1, &tmKb, k_full, 64, key0, bh);
+        if (HD == 128) tma_load_3d(smem + C::OFF_K1, &tmKa, k_full, 64, key0, bh);
+        mbar_wait(v_empty, ph ^ 1);
+        mbar_expect_tx(v_full, C::V_TX);
+        tma_load_3d(smem + C::OFF_V, &tmV, v_full, key0, 0, bh);
+        tma_load_3d(smem + C::OFF_V + C::V_CHUNK, &tmV, v_full, key0 + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+      const uint32_t sQ0 = smem_u32(smem + C::OFF_Q0), sQ1 = smem_u32(smem + C::OFF_Q1);
+      const uint32_t sQX = smem_u32(smem + C::OFF_QX), sE = smem_u32(smem + C::OFF_E);
+      const uint32_t sK0 = smem_u32(smem + C::OFF_K0), sK1 = smem_u32(smem + C::OFF_K1);
+      const uint32_t sV = smem_u32(smem + C::OFF_V);
+      const uint32_t tS = tmem_base, tO = tmem_base + C::O_COL;
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(k_full, ph);
+        tc_fence_after();
+        // ---- S = [q|qext]·[k|kext]ᵀ ----
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, umma_smem_desc(sQ0 + k * 32, 1024, UMMA_SW128),
+                  umma_smem_desc(sK0 + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
+        if (HD == 80)
+          umma_ss(tS, umma_smem_desc(sQ1, 256, UMMA_SW32), umma_smem_desc(sK1, 256, UMMA_SW32),
+                  idesc_s, 1);
+        if (HD == 128) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_smem_desc(sQ1 + k * 32, 1024, UMMA_SW128),
+                    umma_smem_desc(sK1 + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+        }
+        if (EXT == 1) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_ss(tS, umma_smem_desc(sQX + k * 32, 512, UMMA_SW64),
+                    umma_smem_desc(sE + j * 8192 + k * 32, 512, UMMA_SW64), idesc_s, 1);
+        }
+        if (EXT == 2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_smem_desc(sQX + k * 32, 1024, UMMA_SW128),
+                    umma_smem_desc(sE + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+        }
+        umma_commit(k_empty);
+        umma_commit(bar_s);
+        // ---- O += P·V ----
+        mbar_wait(bar_p, ph);
+        mbar_wait(v_full, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tO, tS + k * 8,
+                  umma_smem_desc(sV + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128),
+                  idesc_o, (j | k) != 0);
+        umma_commit(v_empty);
+      }
+      umma_commit(bar_s);  // final: all PV done
+    }
+  } else {
+    // ================================ softmax / correction / epilogue ================================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + row_in_tile;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t tO = t_row + C::O_COL;
+    const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;  // key valid iff key < lim
+    const bf16* rb = nullptr;
+    if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
+    const float c1 = p.c1;
+    float m = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const int key0 = j * BN;
+      float add0 = 0.f, add1 = 0.f;
+      if (EXT == 2) {
+        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(rb + 2 * j);
+        add0 = __low2float(v2) * LOG2E;
+        add1 = __high2float(v2) * LOG2E;
+      }
+      const bool need_mask = (key0 + BN > kv_limit) || (p.causal && key0 + BN - 1 > q0);
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+
+      // ---- pass 1: row max ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const float add = c < 2 ? add0 : add1;
+        if (need_mask) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float t = fmaf(__uint_as_float(r[e]), c1, add);
+            mx = fmaxf(mx, (key0 + c * 32 + e < lim) ? t : -INFINITY);
+          }
+        } else {
+          float mc = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
+          // c1 > 0: max commutes with the affine map
+          mx = fmaxf(mx, fmaf(mc, c1, add));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+
+      // ---- lazy O rescale ----
+      if (j == 0) {
+        m = m_new;
+      } else if (__any_sync(0xffffffffu, m_new > m + 8.0f)) {
+        float f = ex2(m - m_new);
+        if (m_new == -INFINITY) f = 1.f;
+#pragma unroll 1
+        for (int c = 0; c < HD / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(tO + c * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
+          tmem_st16(tO + c * 16, r);
+        }
+        l *= f;
+        m = m_new;
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+
+      // ---- pass 2: P = exp2(t - m), written as packed bf16 over S columns [0,64) ----
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const float add = (c < 2 ? add0 : add1) - m_use;
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float t0 = fmaf(__uint_as_float(r[e]), c1, add);
+          float t1 = fmaf(__uint_as_float(r[e + 1]), c1, add);
+          if (need_mask) {
+            if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
+            if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+          }
+          const float p0 = ex2(t0), p1 = ex2(t1);
+          lsum += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(t_row + c * 16, pk);
+      }
+      l += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+
+    // ---- epilogue: O / l → bf16 → out[b*seq + q_row, h*HD + d] ----
+    if (n_tiles > 0) {
+      mbar_wait(bar_s, n_tiles & 1);
+      tc_fence_after();
+    }
+    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+    const int h = bh - b * p.heads;
+    bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t r[16];
+      if (n_tiles > 0) {
+        tmem_ld16(tO + c * 16, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0;
+      }
+      if (q_row < p.seq) {
+        uint4 o0, o1;
+        o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        o0.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        o0.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        o1.x = pack_bf16(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+        o1.y = pack_bf16(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+        o1.z = pack_bf16(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+        o1.w = pack_bf16(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 16) = o0;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int HD, int EXT>
+int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
+  using C = ACfg<HD, EXT>;
+  const int BH = p->batch * p->heads;
+  CUtensorMap tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE;
+  {
+    uint64_t dims[3] = {(uint64_t)HD, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)HD * 2, (uint64_t)p->seq_pad * HD * 2};
+    uint32_t boxa[3] = {64, 128, 1};
+    if (int e = make_tmap_bf16(&tmQa, p->q, 3, dims, str, boxa, 128)) return e;
+    if (int e = make_tmap_bf16(&tmKa, p->k, 3, dims, str, boxa, 128)) return e;
+    tmQb = tmQa;
+    tmKb = tmKa;
+    if (HD == 80) {
+      uint32_t boxb[3] = {16, 128, 1};
+      if (int e = make_tmap_bf16(&tmQb, p->q, 3, dims, str, boxb, 32)) return e;
+      if (int e = make_tmap_bf16(&tmKb, p->k, 3, dims, str, boxb, 32)) return e;
+    }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p->seq_pad, (uint64_t)HD, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)p->seq_pad * 2, (uint64_t)p->seq_pad * HD * 2};
+    uint32_t box[3] = {64, (uint32_t)HD, 1};
+    if (int e = make_tmap_bf16(&tmV, p->vt, 3, dims, str, box, 128)) return e;
+  }
+  tmQx = tmQa;
+  tmE = tmQa;
+  if (EXT) {
+    const int xc = EXT == 1 ? 32 : 64;
+    uint64_t dims[3] = {(uint64_t)xc, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)xc * 2, (uint64_t)p->seq_pad * xc * 2};
+    uint32_t box[3] = {(uint32_t)xc, 128, 1};
+    if (int e = make_tmap_bf16(&tmQx, p->qext, 3, dims, str, box, xc * 2)) return e;
+    uint64_t edims[2] = {(uint64_t)xc, (uint64_t)(EXT == 1 ? 256 : 128)};
+    uint64_t estr[1] = {(uint64_t)xc * 2};
+    uint32_t ebox[2] = {(uint32_t)xc, 128};
+    if (int e = make_tmap_bf16(&tmE, p->kext, 2, edims, estr, ebox, xc * 2)) return e;
+  }
+  AttnDev d{};
+  d.out = static_cast<bf16*>(p->out);
+  d.ldo = p->ldo;
+  d.heads = p->heads;
+  d.seq = p->seq;
+  d.seq_pad = p->seq_pad;
+  d.c1 = p->scale * LOG2E;
+  d.causal = p->causal;
+  d.kv_len = p->kv_len;
+  d.row_bias = static_cast<const bf16*>(p->row_bias);
+
+  auto kern = attn_kernel<HD, EXT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid((p->seq + BM - 1) / BM, BH);
+  kern<<<grid, 192, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // namespace
+}  // namespace llmseg
+
+using namespace llmseg;
+
+extern "C" int llmseg_attention(const llmseg_attn_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LLMSEG_REQUIRE(p != nullptr, LLMSEG_EARG, "llmseg_attention: null params");
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(p->q && p->k && p->vt && p->out, LLMSEG_EARG, "llmseg_attention: null q/k/vt/out");
+  LLMSEG_REQUIRE(p->batch > 0 && p->heads > 0 && p->seq > 0 && p->seq_pad >= p->seq &&
+                     p->seq_pad % 8 == 0,
+                 LLMSEG_ESHAPE, "llmseg_attention: batch=%d heads=%d seq=%d seq_pad=%d", p->batch,
+                 p->heads, p->seq, p->seq_pad);
+  LLMSEG_REQUIRE(p->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0, LLMSEG_EALIGN,
+                 "llmseg_attention: out / ldo not 16-byte aligned");
+  LLMSEG_REQUIRE(p->scale > 0.f, LLMSEG_EARG, "llmseg_attention: scale must be positive");
+  const int hd = p->head_dim, ext = p->ext_cols;
+  if (ext != 0) {
+    LLMSEG_REQUIRE(hd == 80 && (ext == 32 || ext == 64) && p->qext && p->kext && !p->causal,
+                   LLMSEG_ESHAPE, "llmseg_attention: rel-pos extension needs head_dim 80, ext 32|64");
+    LLMSEG_REQUIRE(ext == 32 ? (p->seq <= 256 && p->row_bias == nullptr)
+                             : (p->row_bias != nullptr && p->seq <= 64 * 64),
+                   LLMSEG_ESHAPE, "llmseg_attention: ext_cols=%d inconsistent with seq=%d / row_bias", ext,
+                   p->seq);
+  }
+  if (hd == 64 && ext == 0) return launch_attn<64, 0>(p, stream);
+  if (hd == 128 && ext == 0) return launch_attn<128, 0>(p, stream);
+  if (hd == 80 && ext == 0) return launch_attn<80, 0>(p, stream);
+  if (hd == 80 && ext == 32) return launch_attn<80, 1>(p, stream);
+  if (hd == 80 && ext == 64) return launch_attn<80, 2>(p, stream);
+  return set_error(LLMSEG_ESHAPE, "llmseg_attention: unsupported head_dim=%d ext_cols=%d", hd, ext);
 }

@@ -42,7 +42,14 @@ struct GemmDev {
   int heads, head_dim, seq_in, seq_pad;
   const bf16* rope_cos;
   const bf16* rope_sin;
+  // RELPOS mode (llmseg_relpos_prep)
+  int rp_grid, rp_seq, rp_seq_pad, rp_ext;
+  float rp_inv_scale;
+  bf16* rp_qext;
+  bf16* rp_rh;
 };
+
+constexpr int MODE_RELPOS = 3;
 
 template <int BN>
 struct Cfg {
@@ -172,6 +179,34 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
       bf16* dst = p.vt + (bh * hd + d) * p.seq_pad + s;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dst[(size_t)e * p.seq_pad] = __float2bfloat16_rn(v[e]);
+    }
+  }
+}
+
+// ---- rel-pos gather: QR[row, i] -> qext / row_bias (see include/llmseg_b200.h) --------------
+__device__ __forceinline__ void epi_relpos(const GemmDev& p, const uint32_t* r, int row, int n0) {
+  const int s = row % p.rp_seq_pad;
+  if (s >= p.rp_seq) return;
+  const int G = p.rp_grid;
+  const int qh = s / G, qw = s - qh * G;
+  const int T = 2 * G - 1;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int col = n0 + e;
+    if (col >= 2 * T) break;
+    const float v = bf16_round(__uint_as_float(r[e]));
+    if (col < T) {
+      const int kh = qh + G - 1 - col;
+      if (kh >= 0 && kh < G) {
+        if (p.rp_rh) p.rp_rh[(size_t)row * 64 + kh] = __float2bfloat16_rn(v);
+        else p.rp_qext[(size_t)row * p.rp_ext + kh] = __float2bfloat16_rn(v * p.rp_inv_scale);
+      }
+    } else {
+      const int kw = qw + G - 1 - (col - T);
+      if (kw >= 0 && kw < G) {
+        const int dst = p.rp_rh ? kw : G + kw;
+        p.rp_qext[(size_t)row * p.rp_ext + dst] = __float2bfloat16_rn(v * p.rp_inv_scale);
+      }
     }
   }
 }
@@ -342,7 +377,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
       int out_row = row;
-      if (MODE != LLMSEG_GEMM_QKV && p.out_row_map != nullptr && row < p.M)
+      if (MODE == LLMSEG_GEMM_PLAIN && p.out_row_map != nullptr && row < p.M)
         out_row = p.out_row_map[row];
       const bool live = row < p.M && out_row >= 0;
       if (MODE == LLMSEG_GEMM_QKV && ROPE) {
@@ -368,6 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (live && n0 < p.N) {
             if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0);
             else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
+            else if (MODE == MODE_RELPOS) epi_relpos(p, r, row, n0);
             else epi_qkv(p, r, row, n0);
           }
         }
@@ -511,4 +547,46 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
     LLMSEG_GEMM_DISPATCH(128)
   }
 #undef LLMSEG_GEMM_DISPATCH
+}
+
+extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int seq,
+                                  int seq_pad, int head_dim, int grid, float inv_scale, void* qext,
+                                  int ext_cols, void* row_bias, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(q && rel_hw && qext, LLMSEG_EARG, "llmseg_relpos_prep: null pointer");
+  LLMSEG_REQUIRE(grid > 0 && seq == grid * grid && seq_pad >= seq && head_dim % 8 == 0 &&
+                     n_pad % 8 == 0 && n_pad >= 2 * (2 * grid - 1),
+                 LLMSEG_ESHAPE, "llmseg_relpos_prep: grid=%d seq=%d seq_pad=%d n_pad=%d", grid, seq,
+                 seq_pad, n_pad);
+  LLMSEG_REQUIRE((row_bias == nullptr && ext_cols == 32 && 2 * grid <= 32) ||
+                     (row_bias != nullptr && ext_cols == 64 && grid <= 64),
+                 LLMSEG_ESHAPE, "llmseg_relpos_prep: ext_cols=%d inconsistent with grid=%d", ext_cols, grid);
+  GemmDev d{};
+  d.M = bh * seq_pad; d.N = n_pad; d.K = head_dim;
+  d.rp_grid = grid; d.rp_seq = seq; d.rp_seq_pad = seq_pad; d.rp_ext = ext_cols;
+  d.rp_inv_scale = inv_scale;
+  d.rp_qext = static_cast<bf16*>(qext);
+  d.rp_rh = static_cast<bf16*>(row_bias);
+  const int sms = num_sms();
+  const int bn = 128;
+  d.num_m_tiles = (d.M + BM - 1) / BM;
+  d.num_n_tiles = (d.N + bn - 1) / bn;
+  d.num_k_blocks = (d.K + BK - 1) / BK;
+  const int tiles = d.num_m_tiles * d.num_n_tiles;
+  const int grid_x = tiles < sms ? tiles : sms;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)head_dim, (uint64_t)d.M};
+    uint64_t str[1] = {(uint64_t)head_dim * 2};
+    uint32_t box[2] = {BK, BM};
+    if (int e = make_tmap_bf16(&tmA, q, 2, dims, str, box, 128)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)head_dim, (uint64_t)n_pad};
+    uint64_t str[1] = {(uint64_t)head_dim * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    if (int e = make_tmap_bf16(&tmB, rel_hw, 2, dims, str, box, 128)) return e;
+  }
+  return launch<128, MODE_RELPOS, false>(tmA, tmB, d, grid_x, stream);
 }

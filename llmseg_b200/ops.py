@@ -89,17 +89,55 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, batch: int,
               heads: int, head_dim: int, seq: int, seq_pad: int, scale: float, causal: bool = False,
-              kv_len: Optional[torch.Tensor] = None, rel_h: Optional[torch.Tensor] = None,
-              rel_w: Optional[torch.Tensor] = None, grid: int = 0) -> torch.Tensor:
-    _req_bf16(q, k, vt, out, rel_h, rel_w)
+              kv_len: Optional[torch.Tensor] = None, qext: Optional[torch.Tensor] = None,
+              kext: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
+              ext_cols: int = 0) -> torch.Tensor:
+    """Fused attention over the q/k/vt buffers of gemm_qkv; out is [batch*seq, heads*head_dim]."""
+    _req_bf16(q, k, vt, out, qext, kext, row_bias)
     p = AttnParams()
     p.q, p.k, p.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     p.out, p.ldo = out.data_ptr(), out.stride(0)
     p.batch, p.heads, p.head_dim, p.seq, p.seq_pad = batch, heads, head_dim, seq, seq_pad
     p.scale, p.causal = float(scale), int(causal)
     p.kv_len = _ptr(kv_len)
-    p.rel_h, p.rel_w, p.grid = _ptr(rel_h), _ptr(rel_w), grid
+    p.ext_cols, p.qext, p.kext, p.row_bias = ext_cols, _ptr(qext), _ptr(kext), _ptr(row_bias)
     check(_lib.lib().llmseg_attention(C.byref(p), _stream()), "attention")
+    return out
+
+
+def relpos_prep(q: torch.Tensor, rel_hw: torch.Tensor, *, bh: int, seq: int, seq_pad: int,
+                head_dim: int, grid: int, inv_scale: float, qext: torch.Tensor,
+                row_bias: Optional[torch.Tensor] = None) -> None:
+    """qext/row_bias <- gathered q·rel_posᵀ (decomposed rel-pos, see include/llmseg_b200.h)."""
+    _req_bf16(q, rel_hw, qext, row_bias)
+    check(_lib.lib().llmseg_relpos_prep(q.data_ptr(), rel_hw.data_ptr(), rel_hw.shape[0], bh, seq,
+                                        seq_pad, head_dim, grid, float(inv_scale), qext.data_ptr(),
+                                        qext.shape[-1], _ptr(row_bias), _stream()), "relpos_prep")
+
+
+def make_kext(grid: int, device) -> torch.Tensor:
+    """Constant one-hot key-position matrix for the rel-pos score extension."""
+    if grid == 14:
+        e = torch.zeros(256, 32)
+        key = torch.arange(196)
+        e[key, key // 14] = 1
+        e[key, 14 + key % 14] = 1
+    elif grid == 64:
+        e = torch.zeros(128, 64)
+        key = torch.arange(128)
+        e[key, key % 64] = 1
+    else:
+        raise ValueError(f"rel-pos extension supports grid 14 (windows) or 64 (global), got {grid}")
+    return e.to(device=device, dtype=torch.bfloat16)
+
+
+def make_rel_hw(rel_h: torch.Tensor, rel_w: torch.Tensor) -> torch.Tensor:
+    """Stack rel_pos_h / rel_pos_w ([2g-1, hd] each) into the zero-padded table relpos_prep reads."""
+    t = rel_h.shape[0]
+    n_pad = (2 * t + 7) // 8 * 8
+    out = torch.zeros(n_pad, rel_h.shape[1], dtype=torch.bfloat16, device=rel_h.device)
+    out[:t] = rel_h
+    out[t:2 * t] = rel_w
     return out
 
 
