@@ -100,11 +100,7 @@ def gold_selector(ref_tr):
     for K, seed in ((32, 11), (64, 12), (7, 13)):
         sd = selector.random_state_dict(seed, hidden=64)
         blocks, fin = _load_selector_ref(ref_tr, sd)
-        g = torch.Generator().manual_seed(seed + 100)
-        emb = torch.randn(1, 256, 64, 64, generator=g)
-        segs = (torch.rand(K, 256, 256, generator=g) > 0.7).float()
-        segs = F.avg_pool2d(segs[None], 3, 1, 1)[0]
-        hidden = torch.randn(1, 64, generator=g)
+        emb, segs, hidden = selector.synthetic_case(seed, K, 64)
         with torch.no_grad():
             text = selector.text_hidden_fc(hidden, sd)
             # --- reference-side computation (LISA.py:350-408) with reference modules
@@ -129,7 +125,8 @@ def gold_selector(ref_tr):
         print(f"[selector K={K}] sim max|d|={e1:.3e} iou max|d|={e2:.3e}")
         assert e1 < 1e-5 and e2 < 1e-5
         torch.save({"seed": seed, "K": K, "hidden_dim": 64, "weights_checksum": checksum(sd),
-                    "emb": emb.half(), "segs": segs.half(), "hidden": hidden, "feat": feat,
+                    "inputs_checksum": float(emb.double().sum() + segs.double().sum() + hidden.double().sum()),
+                    "feat": feat,
                     "pred_similarity": sim_ref, "pred_iou": iou_ref}, GOLD / f"selector_K{K}.pt")
 
 
