@@ -142,7 +142,63 @@ int llmseg_layernorm(const void* in, int ld_in, void* out, int ld_out, const voi
                      const void* beta, int rows_out, int dim, float eps,
                      const int32_t* src_row_map, void* stream);
 int llmseg_rmsnorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
-                   int rows, int dim, float eps, void* stream);
+                   int rows, int dim, float eps, const int32_t* src_row_map, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data movement around the GEMMs (HBM-bound).
+ *   patchify      NCHW bf16 image → [batch*(g*g+cls_rows), k_pad] patch rows, column order
+ *                 (c,py,px) = flattened conv weight, so PatchEmbed / CLIP patch_embedding become
+ *                 one GEMM (image_encoder.py:418-426; transformers CLIPVisionEmbeddings).  With
+ *                 cls_rows=1 each image gets a leading row that is zero except column 3*p*p = 1,
+ *                 which selects a class-embedding column appended to the weight.
+ *   embed_splice  LLaVA `prepare_inputs_labels_for_multimodal` for the inference layout
+ *                 (llava_arch.py:185-245,332-345): token embeddings with the single IMAGE token
+ *                 (-200) replaced by n_img_tokens feature rows; also emits
+ *                 kv_len[n] = n_img_tokens-1 + #true(attention_mask[n]) and the flat row index of
+ *                 the hidden state that predicts [SEG] (LISA.py:254-266), -1 if absent.
+ *   add_rows_bcast out[r] = x[r] + y[row_group ? row_group[r] : r/group]   (single-key cross
+ *                 attention collapses to a broadcast add, transformer.py:264-269)
+ * ------------------------------------------------------------------------------------------ */
+int llmseg_patchify(const void* images, void* out, int batch, int img_size, int patch, int k_pad,
+                    int cls_rows, void* stream);
+int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* attention_mask,
+                        const void* embed_table, const void* image_feats, void* out,
+                        int32_t* kv_len, int32_t* seg_row, int n_seq, int t_text, int n_img_tokens,
+                        int dim, int64_t image_token_id, int64_t seg_token_id, int vocab,
+                        void* stream);
+int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim, int group,
+                          const int32_t* row_group, void* stream);
+/* 3x3 / pad-1 im2col on token-major NHWC bf16: out[(b,y,x), (ky,kx,c)]; turns the SAM neck
+ * conv3x3 (image_encoder.py:100-106) into one GEMM with the weight permuted to [out,(ky,kx,c)]. */
+int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width, int channels,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mask-proposal selector (reference LISA.py:350-408, model/transformer.py:215-341).
+ *   maskpool        fused bilinear upsample 64²→256² + mask pooling in the exact adjoint form
+ *                   (Uᵀw)·E: segs bf16 [n_masks,256,256] are read once; emb is the token-major
+ *                   SAM neck output bf16 [B,4096,256]; mask_image[m] = image of mask m;
+ *                   out bf16 [n_masks,256]; workspace = llmseg_maskpool_workspace(n_masks) bytes.
+ *   small_attention 32-dim heads among <=128 mask tokens (self-attention) or from the single
+ *                   text token to the masks; q rows q_off[b]..q_off[b+1], kv rows kv_off[b]..
+ *   select          sim[b,k] = cos(text_b, feat_k), iou[b,k] = sigmoid(h_iou_k·w2+b2), first
+ *                   argmax per image; outputs fp32 [batch,k_stride] (-inf / 0 padding), int32 [batch]
+ *   losses          align/IoU-regression (loss.py:50-94) → out2 = {kl, mse*50};
+ *                   dice/BCE (loss.py:4-47) → out2 = {dice, bce}; workspace = 2*n_masks floats
+ * ------------------------------------------------------------------------------------------ */
+size_t llmseg_maskpool_workspace(int n_masks);
+int llmseg_maskpool(const void* segs, const void* emb, const int32_t* mask_image, int n_masks,
+                    void* out, void* workspace, void* stream);
+int llmseg_small_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                           void* out, int ldo, const int32_t* q_off, const int32_t* kv_off,
+                           int batch, int heads, int head_dim, int max_kv, void* stream);
+int llmseg_select(const void* feat, const void* text, const void* h_iou, const void* w2,
+                  const void* b2, const int32_t* k_off, int batch, int k_stride, float* sim_out,
+                  float* iou_out, int32_t* best, void* stream);
+int llmseg_align_iou_loss(const float* sim, const float* pred_iou, const float* gt_iou, int K,
+                          float temperature, float* out2, void* stream);
+int llmseg_dice_bce_loss(const float* logits, const float* targets, int n_masks, int hw,
+                         float num_masks, float* workspace, float* out2, void* stream);
 
 #ifdef __cplusplus
 }

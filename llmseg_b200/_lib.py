@@ -57,13 +57,35 @@ def _declare(lib):
     lib.llmseg_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                      c_int, c_float, c_void_p, c_void_p]
     lib.llmseg_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
-                                   c_float, c_void_p]
+                                   c_float, c_void_p, c_void_p]
+    lib.llmseg_patchify.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.llmseg_embed_splice.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int, c_int, c_int, c_int, C.c_int64, C.c_int64,
+                                        c_int, c_void_p]
+    lib.llmseg_add_rows_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p]
+    lib.llmseg_im2col3x3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.llmseg_maskpool_workspace.argtypes = [c_int]
+    lib.llmseg_maskpool_workspace.restype = C.c_size_t
+    lib.llmseg_maskpool.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.llmseg_small_attention.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                           c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                           c_int, c_void_p]
+    lib.llmseg_select.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.llmseg_align_iou_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                          c_void_p]
+    lib.llmseg_dice_bce_loss.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
+                                         c_void_p, c_void_p]
 
 
 # every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
     "llmseg_gemm", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm",
+    "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_im2col3x3",
+    "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
+    "llmseg_align_iou_loss", "llmseg_dice_bce_loss",
 ]
 
 

@@ -113,14 +113,16 @@ embed_splice_kernel(const long long* __restrict__ ids, const unsigned char* __re
 // is 1, so the attention output is out_proj(v_proj(text)) broadcast over the K mask tokens —
 // reference transformer.py:264-269 with keys of length 1)
 __global__ void add_rows_bcast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
-                                      bf16* __restrict__ out, int rows, int dim, int group) {
+                                      bf16* __restrict__ out, int rows, int dim, int group,
+                                      const int* __restrict__ row_group) {
   const int nvec = dim >> 3;
   const long long total = (long long)rows * nvec;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(idx / nvec), v = (int)(idx % nvec);
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * dim) + v);
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(y + (size_t)(r / group) * dim) + v);
+    const int gidx = row_group ? row_group[r] : r / group;
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(y + (size_t)gidx * dim) + v);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
     uint32_t o[4];
 #pragma unroll
@@ -132,10 +134,49 @@ __global__ void add_rows_bcast_kernel(const bf16* __restrict__ x, const bf16* __
   }
 }
 
+// 3x3 / pad 1 im2col on token-major NHWC: out[(b,y,x), (ky,kx,c)] = in[(b,y+ky-1,x+kx-1), c] or 0.
+// One thread per 16-byte vector; feeds the SAM neck conv3x3 as a GEMM (image_encoder.py:100-106).
+__global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H,
+                                 int W, int Cc) {
+  const int vec_per_tap = Cc >> 3;
+  const long long total = (long long)B * H * W * 9 * vec_per_tap;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vec_per_tap);
+    long long r = idx / vec_per_tap;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int x = (int)(r % W);
+    r /= W;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      val = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * H + yy) * W + xx) * Cc) + v);
+    reinterpret_cast<uint4*>(out + (((size_t)b * H + y) * W + x) * (size_t)(9 * Cc) + tap * Cc)[v] = val;
+  }
+}
+
 }  // namespace
 }  // namespace llmseg
 
 using namespace llmseg;
+
+extern "C" int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width,
+                                int channels, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(in && out, LLMSEG_EARG, "llmseg_im2col3x3: null pointer");
+  LLMSEG_REQUIRE(batch > 0 && height > 0 && width > 0 && channels % 8 == 0, LLMSEG_ESHAPE,
+                 "llmseg_im2col3x3: %dx%dx%dx%d", batch, height, width, channels);
+  const long long total = (long long)batch * height * width * 9 * (channels >> 3);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  im2col3x3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(in), static_cast<bf16*>(out), batch, height, width, channels);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
 
 extern "C" int llmseg_patchify(const void* images, void* out, int batch, int img_size, int patch,
                                int k_pad, int cls_rows, void* stream) {
@@ -182,16 +223,16 @@ extern "C" int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* atte
 }
 
 extern "C" int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim,
-                                     int group, void* stream) {
+                                     int group, const int32_t* row_group, void* stream) {
   if (int e = check_arch()) return e;
   LLMSEG_REQUIRE(x && y && out, LLMSEG_EARG, "llmseg_add_rows_bcast: null pointer");
-  LLMSEG_REQUIRE(rows > 0 && dim % 8 == 0 && group > 0, LLMSEG_ESHAPE,
+  LLMSEG_REQUIRE(rows > 0 && dim % 8 == 0 && (group > 0 || row_group), LLMSEG_ESHAPE,
                  "llmseg_add_rows_bcast: rows=%d dim=%d group=%d", rows, dim, group);
   const long long total = (long long)rows * (dim >> 3);
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   add_rows_bcast_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), static_cast<const bf16*>(y), static_cast<bf16*>(out), rows, dim,
-      group);
+      group, row_group);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -141,7 +141,7 @@ extern "C" int llmseg_layernorm(const void* in, int ld_in, void* out, int ld_out
 }
 
 extern "C" int llmseg_rmsnorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
-                              int rows, int dim, float eps, void* stream) {
-  return llmseg::launch_norm<true>(in, ld_in, out, ld_out, gamma, nullptr, rows, dim, eps, nullptr,
-                                   static_cast<cudaStream_t>(stream));
+                              int rows, int dim, float eps, const int32_t* src_row_map, void* stream) {
+  return llmseg::launch_norm<true>(in, ld_in, out, ld_out, gamma, nullptr, rows, dim, eps,
+                                   src_row_map, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,442 @@
+// llmseg_b200 — mask-proposal selector kernels (HBM / latency bound; warp-shuffle reductions).
+//
+//   maskpool      fused  bilinear-upsample(64²→256²) ∘ mask-pooling   (reference LISA.py:201-218,350-361)
+//                 via the exact adjoint form  W·(U·E) = (Uᵀ·W)·E  (SURVEY §A.4): each soft mask is
+//                 read ONCE (K·65536·2 B), resampled to 64² with the transposed bilinear taps, then
+//                 contracted with the 64² embedding.  The 256-channel 256² upsampled tensor
+//                 (67 MB fp32 + 33 MB bf16 per image in the reference) never exists.
+//   small_attn    8-head × 32-dim attention among ≤128 mask tokens / from the single text token
+//                 (reference transformer.py:319-341) with the reference's bf16 rounding points
+//   select        IoU head output layer + sigmoid, cosine similarity, argmax
+//                 (reference LISA.py:387-408, training.py:627-629)
+//   losses        KL-align / weighted-MSE (reference loss.py:50-94) and dice / BCE (loss.py:4-47)
+#include <atomic>
+
+#include "common.cuh"
+
+namespace llmseg {
+extern std::atomic<uint64_t> g_launches;
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// maskpool, stage 1: adjoint resampling.  wt[k, jy, jx] = Σ_{y,x} a[jy,y]·a[jx,x]·w[k,y,x]
+// a[j, 4j-2+t] = {.125,.375,.625,.875,.875,.625,.375,.125}[t] with the align_corners=False edge
+// clamps a[0,0]=a[0,1]=1 and a[63,254]=a[63,255]=1 (F.interpolate bilinear, scale 4).
+// grid (8 row-groups, n_masks); block 256 threads (one per hi-res column).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tap_w(int j, int y) {
+  // weight of low-res cell j for hi-res pixel y (0 when out of the 8-tap support)
+  const int t = y - (4 * j - 2);
+  if (t < 0 || t > 7 || y < 0 || y > 255) return 0.f;
+  if ((j == 0 && y < 2) || (j == 63 && y > 253)) return 1.f;
+  return t < 4 ? 0.125f + 0.25f * (float)t : 0.125f + 0.25f * (float)(7 - t);
+}
+
+__global__ void __launch_bounds__(256)
+maskpool_adjoint_kernel(const bf16* __restrict__ segs, float* __restrict__ wt,
+                        float* __restrict__ part_sum) {
+  const int k = blockIdx.y;
+  const int grp = blockIdx.x;  // low-res rows [8*grp, 8*grp+8)
+  const int x = threadIdx.x;
+  const bf16* seg = segs + (size_t)k * 65536;
+  __shared__ float tmp[256 + 8];
+  __shared__ float red[8];
+  float own_sum = 0.f;
+  for (int jj = 0; jj < 8; ++jj) {
+    const int jy = grp * 8 + jj;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int y = 4 * jy - 2 + t;
+      if (y >= 0 && y < 256) {
+        const float v = __bfloat162float(seg[(size_t)y * 256 + x]);
+        acc += tap_w(jy, y) * v;
+        if (t >= 2 && t < 6) own_sum += v;  // rows 4jy..4jy+3 are owned by this low-res row
+      }
+    }
+    __syncthreads();
+    tmp[x + 2] = acc;
+    if (x < 2) { tmp[x] = 0.f; tmp[258 + x] = 0.f; }
+    __syncthreads();
+    if (x < 64) {
+      float o = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o += tap_w(x, 4 * x - 2 + t) * tmp[4 * x + t];
+      wt[(size_t)k * 4096 + jy * 64 + x] = o;
+    }
+  }
+  own_sum = warp_sum(own_sum);
+  if ((x & 31) == 0) red[x >> 5] = own_sum;
+  __syncthreads();
+  if (x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    part_sum[k * 8 + grp] = s;
+  }
+}
+
+// stage 2: out[k, c] = bf16( bf16(Σ_cell wt[k,cell]·E[img(k), cell, c]) / bf16(Σ_p w[k,p]) )
+// E is token-major [B, 4096, 256] bf16 (the SAM neck output in NHWC).  grid (ceil(n_masks/8));
+// block 256 threads (one per channel); 8 masks per block must belong to one image, so the host
+// guarantees per-image mask counts are padded/visited per image via mask_image[].
+__global__ void __launch_bounds__(256)
+maskpool_apply_kernel(const float* __restrict__ wt, const float* __restrict__ part_sum,
+                      const bf16* __restrict__ emb, const int* __restrict__ mask_image,
+                      bf16* __restrict__ out, int n_masks) {
+  const int c = threadIdx.x;
+  const int k0 = blockIdx.x * 8;
+  __shared__ float ws[8][512];
+  float acc[8];
+  int img[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] = 0.f;
+    img[i] = (k0 + i < n_masks) ? mask_image[k0 + i] : -1;
+  }
+  const bool same = (img[7] == img[0] || img[7] < 0);  // fast path: one image per block
+  for (int cell0 = 0; cell0 < 4096; cell0 += 512) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 512; i += 256) {
+      const int m = i >> 9, cc = i & 511;
+      ws[m][cc] = (k0 + m < n_masks) ? wt[(size_t)(k0 + m) * 4096 + cell0 + cc] : 0.f;
+    }
+    __syncthreads();
+    if (same) {
+      const bf16* e = emb + ((size_t)img[0] * 4096 + cell0) * 256 + c;
+#pragma unroll 4
+      for (int cc = 0; cc < 512; ++cc) {
+        const float ev = __bfloat162float(e[(size_t)cc * 256]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[m] = fmaf(ws[m][cc], ev, acc[m]);
+      }
+    } else {
+      for (int m = 0; m < 8; ++m) {
+        if (img[m] < 0) continue;
+        const bf16* e = emb + ((size_t)img[m] * 4096 + cell0) * 256 + c;
+        for (int cc = 0; cc < 512; ++cc) acc[m] = fmaf(ws[m][cc], __bfloat162float(e[(size_t)cc * 256]), acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    if (k0 + m >= n_masks) continue;
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += part_sum[(k0 + m) * 8 + i];
+    const float den = bf16_round(bf16_round(s) + 1e-8f);  // bf16 sum, +1e-8 vanishes in bf16
+    out[(size_t)(k0 + m) * 256 + c] = __float2bfloat16_rn(bf16_round(acc[m]) / den);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small attention: per (image, head) block; queries q_off[b]..q_off[b+1], keys kv_off[b]..kv_off[b+1].
+// Rounding as the bf16 reference: attn=bf16(q·k) → bf16(attn/√d) → softmax→bf16 → bf16(attn·v).
+// ---------------------------------------------------------------------------------------------
+constexpr int SA_MAX = 128;  // max keys per image
+constexpr int SA_HD = 32;
+
+__global__ void __launch_bounds__(128)
+small_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk,
+                  const bf16* __restrict__ v, int ldv, bf16* __restrict__ out, int ldo,
+                  const int* __restrict__ q_off, const int* __restrict__ kv_off, float inv_sqrt_d) {
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int q0 = q_off[b], nq = q_off[b + 1] - q0;
+  const int k0 = kv_off[b], nk = kv_off[b + 1] - k0;
+  __shared__ float ks[SA_MAX][SA_HD + 1];
+  __shared__ float vs[SA_MAX][SA_HD + 1];
+  for (int i = threadIdx.x; i < nk * SA_HD; i += blockDim.x) {
+    const int r = i / SA_HD, d = i % SA_HD;
+    ks[r][d] = __bfloat162float(k[(size_t)(k0 + r) * ldk + h * SA_HD + d]);
+    vs[r][d] = __bfloat162float(v[(size_t)(k0 + r) * ldv + h * SA_HD + d]);
+  }
+  __syncthreads();
+  for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    float qv[SA_HD];
+#pragma unroll
+    for (int d = 0; d < SA_HD; ++d) qv[d] = __bfloat162float(q[(size_t)(q0 + qi) * ldq + h * SA_HD + d]);
+    float mx = -INFINITY;
+    for (int j = 0; j < nk; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
+      s = bf16_round(bf16_round(s) * inv_sqrt_d);
+      mx = fmaxf(mx, s);
+    }
+    float den = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
+      s = bf16_round(bf16_round(s) * inv_sqrt_d);
+      den += __expf(s - mx);
+    }
+    float o[SA_HD];
+#pragma unroll
+    for (int d = 0; d < SA_HD; ++d) o[d] = 0.f;
+    const float inv = 1.f / den;
+    for (int j = 0; j < nk; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
+      s = bf16_round(bf16_round(s) * inv_sqrt_d);
+      const float p = bf16_round(__expf(s - mx) * inv);
+#pragma unroll
+      for (int d = 0; d < SA_HD; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
+    }
+    bf16* orow = out + (size_t)(q0 + qi) * ldo + h * SA_HD;
+#pragma unroll
+    for (int d = 0; d < SA_HD; d += 2)
+      *reinterpret_cast<uint32_t*>(orow + d) = pack_bf16(o[d], o[d + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// select: one block per image, one warp per mask token (looping).
+//   iou[k]  = sigmoid(bf16(h_iou[k]·w2 + b2))                      h_iou = relu(W1·q+b1) [*,128]
+//   sim[k]  = bf16( (t/‖t‖) · (e_k/‖e_k‖) )  with bf16 norms / quotients like the reference
+//   best    = first argmax_k sim[k]  (torch.argmax tie-break)
+// outputs are fp32 copies of the bf16 values, padded to k_stride per image (-inf / 0 beyond K_b).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+select_kernel(const bf16* __restrict__ feat, const bf16* __restrict__ text,
+              const bf16* __restrict__ h_iou, const bf16* __restrict__ w2, const bf16* __restrict__ b2,
+              const int* __restrict__ k_off, float* __restrict__ sim_out, float* __restrict__ iou_out,
+              int* __restrict__ best, int k_stride) {
+  const int b = blockIdx.x;
+  const int r0 = k_off[b], nk = k_off[b + 1] - r0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float tn[256];
+  __shared__ float sims[SA_MAX];
+  if (warp == 0) {
+    float t[8], ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      t[i] = __bfloat162float(text[(size_t)b * 256 + lane * 8 + i]);
+      ss += t[i] * t[i];
+    }
+    const float nrm = bf16_round(sqrtf(warp_sum(ss)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tn[lane * 8 + i] = bf16_round(t[i] / nrm);
+  }
+  __syncthreads();
+  for (int kk = warp; kk < k_stride; kk += 8) {
+    if (kk >= nk) {
+      if (lane == 0) {
+        sim_out[(size_t)b * k_stride + kk] = -INFINITY;
+        iou_out[(size_t)b * k_stride + kk] = 0.f;
+      }
+      continue;
+    }
+    const size_t r = (size_t)(r0 + kk);
+    float e[8], ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      e[i] = __bfloat162float(feat[r * 256 + lane * 8 + i]);
+      ss += e[i] * e[i];
+    }
+    const float nrm = bf16_round(sqrtf(warp_sum(ss)));
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot += tn[lane * 8 + i] * bf16_round(e[i] / nrm);
+    dot = bf16_round(warp_sum(dot));
+    float hi = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      hi += __bfloat162float(h_iou[r * 128 + lane * 4 + i]) * __bfloat162float(w2[lane * 4 + i]);
+    hi = bf16_round(warp_sum(hi) + __bfloat162float(b2[0]));
+    const float io = bf16_round(1.f / (1.f + __expf(-hi)));
+    if (lane == 0) {
+      sim_out[(size_t)b * k_stride + kk] = dot;
+      iou_out[(size_t)b * k_stride + kk] = io;
+      if (kk < SA_MAX) sims[kk] = dot;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bi = 0;
+    float bv = -INFINITY;
+    for (int i = 0; i < nk && i < SA_MAX; ++i)
+      if (sims[i] > bv) { bv = sims[i]; bi = i; }
+    best[b] = nk > 0 ? bi : -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses (training-side; one block each, fp32 math on bf16/fp32 inputs)
+// ---------------------------------------------------------------------------------------------
+__device__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+__device__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmaxf(t, sh[i]);
+  return t;
+}
+
+// out[0] = KL(softmax(gt/τ) ‖ softmax(sim/τ)) (sum), out[1] = mean((p-g)²·e^{g-1})·50   (loss.py:50-94)
+__global__ void __launch_bounds__(256)
+align_iou_loss_kernel(const float* __restrict__ sim, const float* __restrict__ pred_iou,
+                      const float* __restrict__ gt_iou, int K, float temperature, float* __restrict__ out) {
+  __shared__ float sh[8];
+  const float it = 1.f / temperature;
+  float ms = -INFINITY, mg = -INFINITY;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    ms = fmaxf(ms, sim[i] * it);
+    mg = fmaxf(mg, gt_iou[i] * it);
+  }
+  ms = block_max(ms, sh);
+  mg = block_max(mg, sh);
+  float zs = 0.f, zg = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    zs += __expf(sim[i] * it - ms);
+    zg += __expf(gt_iou[i] * it - mg);
+  }
+  zs = block_sum(zs, sh);
+  zg = block_sum(zg, sh);
+  const float ls = ms + __logf(zs), lg = mg + __logf(zg);
+  float kl = 0.f, mse = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const float lp_s = sim[i] * it - ls, lp_g = gt_iou[i] * it - lg;
+    const float pg = __expf(lp_g);
+    kl += pg > 0.f ? pg * (lp_g - lp_s) : 0.f;
+    const float d = pred_iou[i] - gt_iou[i];
+    mse += d * d * __expf(gt_iou[i] - 1.f);
+  }
+  kl = block_sum(kl, sh);
+  mse = block_sum(mse, sh);
+  if (threadIdx.x == 0) {
+    out[0] = kl;
+    out[1] = mse / (float)K * 50.f;
+  }
+}
+
+// per-mask partials for dice / BCE: grid (n_masks), out2[m] = {dice_m, bce_mean_m}   (loss.py:4-47)
+__global__ void __launch_bounds__(256)
+dice_bce_kernel(const float* __restrict__ logits, const float* __restrict__ targets, int hw, float scale,
+                float eps, float* __restrict__ out2) {
+  __shared__ float sh[8];
+  const float* x = logits + (size_t)blockIdx.x * hw;
+  const float* t = targets + (size_t)blockIdx.x * hw;
+  float num = 0.f, dp = 0.f, dt = 0.f, bce = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const float xv = x[i], tv = t[i];
+    const float p = 1.f / (1.f + __expf(-xv));
+    num += p / scale * tv;
+    dp += p / scale;
+    dt += tv / scale;
+    bce += fmaxf(xv, 0.f) - xv * tv + log1pf(__expf(-fabsf(xv)));
+  }
+  num = block_sum(num, sh);
+  dp = block_sum(dp, sh);
+  dt = block_sum(dt, sh);
+  bce = block_sum(bce, sh);
+  if (threadIdx.x == 0) {
+    out2[blockIdx.x * 2 + 0] = 1.f - (2.f * num + eps) / (dp + dt + eps);
+    out2[blockIdx.x * 2 + 1] = bce / (float)hw;
+  }
+}
+__global__ void dice_bce_final_kernel(const float* __restrict__ part, int n, float num_masks,
+                                      float* __restrict__ out) {
+  float d = 0.f, b = 0.f;
+  for (int i = 0; i < n; ++i) {
+    d += part[2 * i];
+    b += part[2 * i + 1];
+  }
+  out[0] = d / (num_masks + 1e-8f);
+  out[1] = b / (num_masks + 1e-8f);
+}
+
+}  // namespace
+}  // namespace llmseg
+
+using namespace llmseg;
+
+extern "C" size_t llmseg_maskpool_workspace(int n_masks) {
+  return (size_t)n_masks * (4096 + 8) * sizeof(float);
+}
+
+extern "C" int llmseg_maskpool(const void* segs, const void* emb, const int32_t* mask_image,
+                               int n_masks, void* out, void* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(segs && emb && mask_image && out && workspace, LLMSEG_EARG, "llmseg_maskpool: null pointer");
+  LLMSEG_REQUIRE(n_masks > 0, LLMSEG_ESHAPE, "llmseg_maskpool: n_masks=%d", n_masks);
+  float* wt = static_cast<float*>(workspace);
+  float* ps = wt + (size_t)n_masks * 4096;
+  maskpool_adjoint_kernel<<<dim3(8, n_masks), 256, 0, stream>>>(static_cast<const bf16*>(segs), wt, ps);
+  LLMSEG_CUDA(cudaGetLastError());
+  maskpool_apply_kernel<<<(n_masks + 7) / 8, 256, 0, stream>>>(wt, ps, static_cast<const bf16*>(emb),
+                                                               mask_image, static_cast<bf16*>(out), n_masks);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return 0;
+}
+
+extern "C" int llmseg_small_attention(const void* q, int ldq, const void* k, int ldk, const void* v,
+                                      int ldv, void* out, int ldo, const int32_t* q_off,
+                                      const int32_t* kv_off, int batch, int heads, int head_dim,
+                                      int max_kv, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(q && k && v && out && q_off && kv_off, LLMSEG_EARG, "llmseg_small_attention: null pointer");
+  LLMSEG_REQUIRE(head_dim == SA_HD && batch > 0 && heads > 0 && max_kv <= SA_MAX, LLMSEG_ESHAPE,
+                 "llmseg_small_attention: head_dim=%d (need 32) max_kv=%d (<= %d)", head_dim, max_kv, SA_MAX);
+  small_attn_kernel<<<dim3(batch, heads), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v),
+      ldv, static_cast<bf16*>(out), ldo, q_off, kv_off, 1.0f / sqrtf((float)head_dim));
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int llmseg_select(const void* feat, const void* text, const void* h_iou, const void* w2,
+                             const void* b2, const int32_t* k_off, int batch, int k_stride,
+                             float* sim_out, float* iou_out, int32_t* best, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(feat && text && h_iou && w2 && b2 && k_off && sim_out && iou_out && best, LLMSEG_EARG,
+                 "llmseg_select: null pointer");
+  LLMSEG_REQUIRE(batch > 0 && k_stride > 0 && k_stride <= SA_MAX, LLMSEG_ESHAPE,
+                 "llmseg_select: batch=%d k_stride=%d (<= %d)", batch, k_stride, SA_MAX);
+  select_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(feat), static_cast<const bf16*>(text), static_cast<const bf16*>(h_iou),
+      static_cast<const bf16*>(w2), static_cast<const bf16*>(b2), k_off, sim_out, iou_out, best, k_stride);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int llmseg_align_iou_loss(const float* sim, const float* pred_iou, const float* gt_iou, int K,
+                                     float temperature, float* out2, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(sim && pred_iou && gt_iou && out2 && K > 0 && temperature > 0.f, LLMSEG_EARG,
+                 "llmseg_align_iou_loss: bad arguments");
+  align_iou_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(sim, pred_iou, gt_iou, K,
+                                                                          temperature, out2);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int llmseg_dice_bce_loss(const float* logits, const float* targets, int n_masks, int hw,
+                                    float num_masks, float* workspace, float* out2, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(logits && targets && workspace && out2 && n_masks > 0 && hw > 0, LLMSEG_EARG,
+                 "llmseg_dice_bce_loss: bad arguments");
+  dice_bce_kernel<<<n_masks, 256, 0, stream>>>(logits, targets, hw, 1000.f, 1e-6f, workspace);
+  LLMSEG_CUDA(cudaGetLastError());
+  dice_bce_final_kernel<<<1, 1, 0, stream>>>(workspace, n_masks, num_masks, out2);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return 0;
+}

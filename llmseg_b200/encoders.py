@@ -1,0 +1,288 @@
+"""Host-side orchestration of the three encoders on top of the sm_100a kernels (ops.py).
+
+Each class takes a state dict with the reference's parameter names, re-lays the weights out once
+for the kernels (bf16, fused QKV / interleaved gate-up, conv weights flattened for conv-as-GEMM),
+and exposes a forward that only enqueues llmseg_* kernels.
+
+  SamEncoder   reference model/segment_anything/modeling/image_encoder.py:110-125 (ViT-H/16 @1024)
+  ClipTower    reference model/llava/model/multimodal_encoder/clip_encoder.py:31-60 + mm_projector
+               (llava_arch.py:93-96); arithmetic = transformers CLIPVisionTransformer
+  LlamaDecoder reference model/llava/model/language_model/llava_llama.py:93-102; arithmetic =
+               transformers LlamaModel (lm_head is skipped: dead work at inference, LISA.py:283,318)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+def _dev(t: Tensor, device) -> Tensor:
+    return t.detach().to(device=device, dtype=BF16).contiguous()
+
+
+class _Scratch:
+    """Zero-initialised attention staging buffers, cached by shape.  The pad rows/columns of
+    q/k/vt/qext are never written by the kernels and must stay zero (finite) for the masked tiles."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[tuple, Tensor] = {}
+
+    def zeros(self, tag: str, *shape) -> Tensor:
+        key = (tag,) + tuple(shape)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(shape, dtype=BF16, device=self.device)
+            self._bufs[key] = buf
+        return buf
+
+
+# ==============================================================================================
+# SAM ViT image encoder
+# ==============================================================================================
+class SamEncoder:
+    def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = ""):
+        self.cfg, self.device = cfg, device
+        D = cfg.embed_dim
+        self.heads, self.hd = cfg.num_heads, cfg.embed_dim // cfg.num_heads
+        if self.hd != 80:
+            raise ValueError(f"SAM attention kernel is instantiated for head_dim 80 (ViT-H), got {self.hd}")
+        g = cfg.grid
+        if g != 64 or cfg.window_size != 14:
+            raise ValueError("rel-pos score extension supports the 64x64 grid with 14x14 windows (SAM @1024)")
+        p = cfg.patch_size
+        d = lambda k: _dev(sd[prefix + k], device)
+        self.w_patch = d("patch_embed.proj.weight").reshape(D, 3 * p * p).contiguous()
+        self.b_patch = d("patch_embed.proj.bias")
+        self.pos = d("pos_embed").reshape(g * g, D).contiguous()
+        self.blocks = []
+        for i in range(cfg.depth):
+            bp = f"blocks.{i}."
+            self.blocks.append(dict(
+                window=0 if i in cfg.global_attn_indexes else cfg.window_size,
+                ln1_w=d(bp + "norm1.weight"), ln1_b=d(bp + "norm1.bias"),
+                ln2_w=d(bp + "norm2.weight"), ln2_b=d(bp + "norm2.bias"),
+                w_qkv=d(bp + "attn.qkv.weight"), b_qkv=d(bp + "attn.qkv.bias"),
+                w_proj=d(bp + "attn.proj.weight"), b_proj=d(bp + "attn.proj.bias"),
+                rel_hw=ops.make_rel_hw(d(bp + "attn.rel_pos_h"), d(bp + "attn.rel_pos_w")),
+                w1=d(bp + "mlp.lin1.weight"), b1=d(bp + "mlp.lin1.bias"),
+                w2=d(bp + "mlp.lin2.weight"), b2=d(bp + "mlp.lin2.bias"),
+            ))
+        self.w_neck1 = d("neck.0.weight").reshape(cfg.out_chans, D).contiguous()
+        self.ln_n1 = (d("neck.1.weight"), d("neck.1.bias"))
+        # conv3x3 weight [out, in, ky, kx] -> [out, (ky, kx, in)] to match im2col3x3's column order
+        self.w_neck2 = d("neck.2.weight").permute(0, 2, 3, 1).reshape(cfg.out_chans, 9 * cfg.out_chans).contiguous()
+        self.ln_n2 = (d("neck.3.weight"), d("neck.3.bias"))
+        self.kext_win = ops.make_kext(14, device)
+        self.kext_glb = ops.make_kext(64, device)
+        self.scratch = _Scratch(device)
+        self._maps: Dict[int, tuple] = {}
+
+    def _window_maps(self, B: int):
+        """win_src[r]: image token feeding window row r (or -1 = zero padding token);
+        unwin_dst[r]: token row receiving window row r (or -1 = cropped).  reference
+        image_encoder.py:263-318 as index maps."""
+        if B not in self._maps:
+            g, ws = self.cfg.grid, self.cfg.window_size
+            nw = (g + ws - 1) // ws
+            b = torch.arange(B).view(B, 1, 1, 1, 1)
+            wy = torch.arange(nw).view(1, nw, 1, 1, 1)
+            wx = torch.arange(nw).view(1, 1, nw, 1, 1)
+            ty = torch.arange(ws).view(1, 1, 1, ws, 1)
+            tx = torch.arange(ws).view(1, 1, 1, 1, ws)
+            y, x = wy * ws + ty, wx * ws + tx
+            tok = b * (g * g) + y * g + x
+            tok = torch.where((y < g) & (x < g), tok, torch.full_like(tok, -1))
+            m = tok.reshape(-1).to(torch.int32).to(self.device)
+            self._maps[B] = (m, nw * nw)
+        return self._maps[B]
+
+    def forward(self, images: Tensor) -> Tensor:
+        """[B,3,1024,1024] bf16 -> token-major neck output [B, 4096, out_chans] bf16 (NHWC)."""
+        cfg = self.cfg
+        B = images.shape[0]
+        g, D, H, hd = cfg.grid, cfg.embed_dim, self.heads, self.hd
+        S = g * g
+        a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
+        x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S)
+        del a
+        win_map, n_win = self._window_maps(B)
+        scale = hd ** -0.5
+        for blk in self.blocks:
+            if blk["window"] > 0:
+                ws = blk["window"]
+                sw, sw_pad = ws * ws, (ws * ws + 7) // 8 * 8
+                nb = B * n_win
+                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps, src_row_map=win_map, rows_out=nb * sw)
+                q = self.scratch.zeros("q", nb * H, sw_pad, hd)
+                k = self.scratch.zeros("k", nb * H, sw_pad, hd)
+                vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
+                qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
+                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+                ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
+                                inv_scale=1.0 / scale, qext=qext)
+                o = h  # reuse the LN output buffer for the attention output (same shape)
+                ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
+                              qext=qext, kext=self.kext_win, ext_cols=32)
+                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x, out_row_map=win_map)
+            else:
+                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
+                q = self.scratch.zeros("qg", B * H, S, hd)
+                k = self.scratch.zeros("kg", B * H, S, hd)
+                vt = self.scratch.zeros("vtg", B * H, hd, S)
+                qext = self.scratch.zeros("qext_g", B * H, S, 64)
+                rb = self.scratch.zeros("rb_g", B * H, S, 64)
+                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S)
+                ops.relpos_prep(q, blk["rel_hw"], bh=B * H, seq=S, seq_pad=S, head_dim=hd, grid=g,
+                                inv_scale=1.0 / scale, qext=qext, row_bias=rb)
+                o = h
+                ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale,
+                              qext=qext, kext=self.kext_glb, row_bias=rb, ext_cols=64)
+                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
+            h = ops.layernorm(x, blk["ln2_w"], blk["ln2_b"], cfg.ln_eps)
+            m = ops.gemm(h, blk["w1"], blk["b1"], act="gelu")
+            ops.gemm(m, blk["w2"], blk["b2"], residual=x, out=x)
+            del h, m
+        y = ops.gemm(x, self.w_neck1)
+        y = ops.layernorm(y, self.ln_n1[0], self.ln_n1[1], 1e-6)
+        y = ops.im2col3x3(y, B, g, g)
+        y = ops.gemm(y, self.w_neck2)
+        y = ops.layernorm(y, self.ln_n2[0], self.ln_n2[1], 1e-6)
+        return y.view(B, S, cfg.out_chans)
+
+
+# ==============================================================================================
+# CLIP ViT-L/14 tower + mm_projector
+# ==============================================================================================
+class ClipTower:
+    def __init__(self, sd: Dict[str, Tensor], cfg, device, proj_w: Tensor, proj_b: Tensor,
+                 prefix: str = "vision_model."):
+        self.cfg, self.device = cfg, device
+        D, p = cfg.hidden, cfg.patch_size
+        self.heads, self.hd = cfg.heads, cfg.hidden // cfg.heads
+        if self.hd != 64:
+            raise ValueError(f"CLIP attention kernel is instantiated for head_dim 64, got {self.hd}")
+        d = lambda k: _dev(sd[prefix + k], device)
+        K = 3 * p * p
+        self.k_pad = (K + 1 + 7) // 8 * 8
+        w = torch.zeros(D, self.k_pad, dtype=BF16, device=device)
+        w[:, :K] = d("embeddings.patch_embedding.weight").reshape(D, K)
+        w[:, K] = d("embeddings.class_embedding")  # selected by the CLS row's one-hot column
+        self.w_patch = w
+        self.pos = d("embeddings.position_embedding.weight")
+        self.pre_ln = (d("pre_layrnorm.weight"), d("pre_layrnorm.bias"))
+        n_run = cfg.layers + 1 + cfg.select_layer if cfg.select_layer < 0 else cfg.select_layer
+        self.layers = []
+        for i in range(n_run):
+            lp = f"encoder.layers.{i}."
+            self.layers.append(dict(
+                ln1=(d(lp + "layer_norm1.weight"), d(lp + "layer_norm1.bias")),
+                ln2=(d(lp + "layer_norm2.weight"), d(lp + "layer_norm2.bias")),
+                w_qkv=torch.cat([d(lp + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
+                b_qkv=torch.cat([d(lp + f"self_attn.{n}_proj.bias") for n in "qkv"], 0).contiguous(),
+                w_o=d(lp + "self_attn.out_proj.weight"), b_o=d(lp + "self_attn.out_proj.bias"),
+                w1=d(lp + "mlp.fc1.weight"), b1=d(lp + "mlp.fc1.bias"),
+                w2=d(lp + "mlp.fc2.weight"), b2=d(lp + "mlp.fc2.bias"),
+            ))
+        self.proj_w, self.proj_b = _dev(proj_w, device), _dev(proj_b, device)
+        self.scratch = _Scratch(device)
+        self._drop_cls: Dict[int, Tensor] = {}
+
+    def _drop_cls_map(self, N: int) -> Tensor:
+        if N not in self._drop_cls:
+            T = self.cfg.tokens
+            t = torch.arange(N * T)
+            n, s = t // T, t % T
+            m = torch.where(s > 0, n * (T - 1) + s - 1, torch.full_like(t, -1))
+            self._drop_cls[N] = m.to(torch.int32).to(self.device)
+        return self._drop_cls[N]
+
+    def forward(self, images_clip: Tensor) -> Tensor:
+        """[N,3,224,224] bf16 -> projected patch features [N, 256, proj_dim] bf16."""
+        cfg = self.cfg
+        N = images_clip.shape[0]
+        T, D, H, hd = cfg.tokens, cfg.hidden, self.heads, self.hd
+        T_pad = (T + 7) // 8 * 8
+        a = ops.patchify(images_clip.contiguous(), cfg.patch_size, self.k_pad, cls_rows=1)
+        x = ops.gemm(a, self.w_patch, None, residual=self.pos, res_mod=T)
+        x = ops.layernorm(x, self.pre_ln[0], self.pre_ln[1], cfg.eps)
+        q = self.scratch.zeros("q", N * H, T_pad, hd)
+        k = self.scratch.zeros("k", N * H, T_pad, hd)
+        vt = self.scratch.zeros("vt", N * H, hd, T_pad)
+        for L in self.layers:
+            h = ops.layernorm(x, L["ln1"][0], L["ln1"][1], cfg.eps)
+            ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
+            ops.attention(q, k, vt, h, batch=N, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
+            ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x)
+            h = ops.layernorm(x, L["ln2"][0], L["ln2"][1], cfg.eps)
+            m = ops.gemm(h, L["w1"], L["b1"], act="quick_gelu")
+            ops.gemm(m, L["w2"], L["b2"], residual=x, out=x)
+        feats = ops.gemm(x, self.proj_w, self.proj_b, out_row_map=self._drop_cls_map(N), out_rows=N * (T - 1))
+        return feats.view(N, T - 1, -1)
+
+
+# ==============================================================================================
+# LLaMA decoder stack
+# ==============================================================================================
+class LlamaDecoder:
+    def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = "", max_seq: int = 1024):
+        self.cfg, self.device = cfg, device
+        if cfg.head_dim != 128:
+            raise ValueError(f"LLaMA attention kernel is instantiated for head_dim 128, got {cfg.head_dim}")
+        d = lambda k: _dev(sd[prefix + k], device)
+        self.embed = d("embed_tokens.weight")
+        self.norm = d("norm.weight")
+        self.layers = []
+        for i in range(cfg.layers):
+            lp = f"layers.{i}."
+            gate, up = d(lp + "mlp.gate_proj.weight"), d(lp + "mlp.up_proj.weight")
+            self.layers.append(dict(
+                rms1=d(lp + "input_layernorm.weight"), rms2=d(lp + "post_attention_layernorm.weight"),
+                w_qkv=torch.cat([d(lp + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
+                w_o=d(lp + "self_attn.o_proj.weight"),
+                # rows interleaved (gate0, up0, gate1, up1, ...) for the SwiGLU epilogue
+                w_gu=torch.stack([gate, up], dim=1).reshape(2 * cfg.mlp, cfg.hidden).contiguous(),
+                w_down=d(lp + "mlp.down_proj.weight"),
+            ))
+            del gate, up
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.float32) / cfg.head_dim))
+        fr = torch.outer(torch.arange(max_seq, dtype=torch.float32), inv)
+        self.rope_cos = fr.cos().to(BF16).to(device).contiguous()
+        self.rope_sin = fr.sin().to(BF16).to(device).contiguous()
+        self.max_seq = max_seq
+        self.scratch = _Scratch(device)
+
+    def forward(self, embeds: Tensor, n_seq: int, T: int, kv_len: Optional[Tensor],
+                out_rows: Optional[Tensor] = None) -> Tensor:
+        """embeds [n_seq*T, hidden] bf16 -> final-norm hidden states; with `out_rows` (int32 flat row
+        indices) only those rows are normalised and returned (the row-wise norm commutes with the gather)."""
+        cfg = self.cfg
+        if T > self.max_seq:
+            raise ValueError(f"sequence length {T} exceeds the RoPE table ({self.max_seq})")
+        H, hd = cfg.heads, cfg.head_dim
+        T_pad = (T + 7) // 8 * 8
+        q = self.scratch.zeros("q", n_seq * H, T_pad, hd)
+        k = self.scratch.zeros("k", n_seq * H, T_pad, hd)
+        vt = self.scratch.zeros("vt", n_seq * H, hd, T_pad)
+        x = embeds
+        scale = 1.0 / math.sqrt(hd)
+        for L in self.layers:
+            h = ops.rmsnorm(x, L["rms1"], cfg.eps)
+            ops.gemm_qkv(h, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
+                         rope_cos=self.rope_cos, rope_sin=self.rope_sin)
+            ops.attention(q, k, vt, h, batch=n_seq, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=scale,
+                          causal=True, kv_len=kv_len)
+            ops.gemm(h, L["w_o"], None, residual=x, out=x)
+            h = ops.rmsnorm(x, L["rms2"], cfg.eps)
+            m = ops.gemm(h, L["w_gu"], None, swiglu=True)
+            ops.gemm(m, L["w_down"], None, residual=x, out=x)
+        if out_rows is not None:
+            return ops.rmsnorm(x, self.norm, cfg.eps, src_row_map=out_rows, rows_out=out_rows.numel())
+        return ops.rmsnorm(x, self.norm, cfg.eps)

@@ -1,0 +1,198 @@
+"""Drop-in host class for the LLM-Seg inference forward:  `LISAForCausalLM.forward(**input_dict)` →
+`model_forward(...)` with the reference's argument names and return dict
+(reference model/LISA.py:220-241,410-414), executed entirely by the sm_100a kernels.
+
+Variant A of SURVEY §0/T1: image features come from the SAM ViT-H encoder (`get_visual_embs`,
+LISA.py:173-184) — the encoder `north_star` names and the one fully in-tree.
+
+Differences from the reference that a caller can observe:
+  * batched inference is allowed (reference asserts one image per call, LISA.py:271); a batch of B
+    images with one conversation each is defined as B independent reference calls
+  * `inference=False` (training losses through the LLM) is outside the hot path and raises
+  * extra keys (`best_index`) are added to the returned dict; the reference keys are unchanged
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .encoders import BF16, ClipTower, LlamaDecoder, SamEncoder
+from .selector import Selector
+
+Tensor = torch.Tensor
+
+IMAGE_TOKEN_INDEX = -200  # reference utils/utils.py:12
+DEFAULT_SEG_TOKEN_IDX = 32000
+
+
+@dataclass
+class SamCfg:
+    img_size: int = 1024
+    patch_size: int = 16
+    embed_dim: int = 1280
+    depth: int = 32
+    num_heads: int = 16
+    mlp_ratio: float = 4.0
+    out_chans: int = 256
+    window_size: int = 14
+    global_attn_indexes: tuple = (7, 15, 23, 31)
+    ln_eps: float = 1e-6
+
+    @property
+    def grid(self) -> int:
+        return self.img_size // self.patch_size
+
+
+@dataclass
+class ClipCfg:
+    image_size: int = 224
+    patch_size: int = 14
+    hidden: int = 1024
+    layers: int = 24
+    heads: int = 16
+    mlp: int = 4096
+    eps: float = 1e-5
+    select_layer: int = -2
+
+    @property
+    def tokens(self) -> int:
+        return (self.image_size // self.patch_size) ** 2 + 1
+
+
+@dataclass
+class LlamaCfg:
+    hidden: int = 4096
+    layers: int = 32
+    heads: int = 32
+    mlp: int = 11008
+    vocab: int = 32003
+    eps: float = 1e-6
+    rope_theta: float = 10000.0
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+
+@dataclass
+class LisaCfg:
+    sam: SamCfg = field(default_factory=SamCfg)
+    clip: ClipCfg = field(default_factory=ClipCfg)
+    llama: LlamaCfg = field(default_factory=LlamaCfg)
+    seg_token_idx: int = DEFAULT_SEG_TOKEN_IDX
+    out_dim: int = 256
+
+
+def _sub(sd: Dict[str, Tensor], prefix: str) -> Dict[str, Tensor]:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def strip_peft_prefix(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """Accept checkpoints saved through PEFT (`base_model.model.` prefix, reference training.py:194-237)
+    and merge LoRA deltas W + (alpha/r)·B·A into q_proj/v_proj when present (r=8, alpha=16)."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("base_model.model."):
+            k = k[len("base_model.model."):]
+        out[k] = v
+    lora_a = {k: v for k, v in out.items() if ".lora_A." in k}
+    for ka, a in lora_a.items():
+        kb = ka.replace(".lora_A.", ".lora_B.")
+        base = ka.split(".lora_A.")[0] + ".weight"
+        if kb in out and base in out:
+            r = a.shape[0]
+            out[base] = out[base].float() + (16.0 / r) * (out[kb].float() @ a.float())
+    return {k: v for k, v in out.items() if ".lora_" not in k}
+
+
+class LISAForCausalLM:
+    """B200 implementation of the reference class of the same name (inference forward only)."""
+
+    def __init__(self, state_dict: Dict[str, Tensor], cfg: Optional[LisaCfg] = None, *,
+                 device: str = "cuda:0", seg_token_idx: Optional[int] = None, max_seq: int = 1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("llmseg_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
+        from . import _lib
+        _lib.lib()  # fail loudly now if the CUDA library is missing
+        self.cfg = cfg or LisaCfg()
+        if seg_token_idx is not None:
+            self.cfg.seg_token_idx = seg_token_idx
+        self.seg_token_idx = self.cfg.seg_token_idx
+        self.device = torch.device(device)
+        sd = strip_peft_prefix(state_dict)
+        self.sam = SamEncoder(_sub(sd, "model.visual_model.image_encoder."), self.cfg.sam, self.device)
+        self.clip = ClipTower(_sub(sd, "model.vision_tower.vision_tower."), self.cfg.clip, self.device,
+                              sd["model.mm_projector.weight"], sd["model.mm_projector.bias"])
+        self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq)
+        self.selector = Selector(_sub(sd, "model."), self.device)
+
+    # ---- reference API -------------------------------------------------------------------------
+    def forward(self, **kwargs):
+        if "past_key_values" in kwargs:
+            raise NotImplementedError("the HF generate() path (reference LISA.py:221-222) is outside the hot path")
+        return self.model_forward(**kwargs)
+
+    __call__ = forward
+
+    def get_visual_embs(self, pixel_values: Tensor) -> Tensor:
+        """SAM ViT-H features, returned NCHW [B,256,64,64] like reference LISA.py:173-184."""
+        tok = self.sam.forward(pixel_values.to(self.device, BF16))
+        g = self.cfg.sam.grid
+        return tok.view(tok.shape[0], g, g, -1).permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def model_forward(self, images: Tensor, images_clip: Tensor, input_ids: Tensor, labels: Optional[Tensor] = None,
+                      attention_masks: Optional[Tensor] = None, offset: Optional[Tensor] = None,
+                      masks_list: Optional[list] = None, label_list: Optional[list] = None,
+                      resize_list: Optional[list] = None, sam_segs_list: Optional[List[Tensor]] = None,
+                      sam_ious_list: Optional[list] = None, sam_iops_list: Optional[list] = None,
+                      inference: bool = False, **kwargs) -> dict:
+        if not inference:
+            raise NotImplementedError("llmseg_b200 implements the inference forward (inference=True); the training "
+                                      "losses are out of the hot path (SURVEY §8f)")
+        dev = self.device
+        images = images.to(dev, BF16)
+        images_clip = images_clip.to(dev, BF16)
+        input_ids = input_ids.to(dev, torch.int64).contiguous()
+        B = images.shape[0]
+        N = input_ids.shape[0]
+        if offset is None:
+            offset = torch.arange(B + 1)
+        assert B == len(offset) - 1, "batch_size == len(offset) - 1 (reference LISA.py:250)"
+        off = [int(v) for v in offset.tolist()]
+        assert off[-1] == N and sam_segs_list is not None and len(sam_segs_list) == B
+        # CLIP input per conversation: image i for conversations offset[i]..offset[i+1] (LISA.py:272,293-303)
+        if images_clip.shape[0] == 1 and N > 1 and B == 1:
+            conv_image = [0] * N
+        else:
+            assert images_clip.shape[0] == B
+            conv_image = [i for i in range(B) for _ in range(off[i + 1] - off[i])]
+
+        # 1. SAM image encoder -> token-major embeddings [B,4096,256]
+        emb_tokens = self.sam.forward(images)
+
+        # 2. CLIP tower + projector (once per distinct image; the reference recomputes per conversation)
+        feats_img = self.clip.forward(images_clip)                       # [B',256,4096]
+        feats = feats_img if conv_image == list(range(N)) else feats_img[torch.tensor(conv_image, device=dev)].contiguous()
+
+        # 3. splice + LLaMA; only the hidden state that predicts [SEG] is normalised and returned
+        embeds, kv_len, seg_row = ops.embed_splice(
+            input_ids, None if attention_masks is None else attention_masks.to(dev), self.llama.embed, feats,
+            image_token=IMAGE_TOKEN_INDEX, seg_token=self.seg_token_idx)
+        T = input_ids.shape[1] + feats.shape[1] - 1
+        first_conv = torch.tensor(off[:-1], device=dev, dtype=torch.long)
+        rows = seg_row.index_select(0, first_conv).contiguous()           # conversation 0 of each image (LISA.py:400)
+        hidden = self.llama.forward(embeds, N, T, kv_len, out_rows=rows)  # [B,4096]
+        text_embed = self.selector.text_embed(hidden)                     # [B,256]
+
+        # 4. selector
+        segs = [s.to(dev, BF16) for s in sam_segs_list]
+        sim, iou, best, Ks = self.selector.forward(emb_tokens, segs, text_embed)
+        pred_similarity = [sim[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
+        pred_iou = [iou[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
+        return {"pred_similarity": pred_similarity, "gt_masks": masks_list, "pred_iou": pred_iou,
+                "best_index": best, "similarity_padded": sim, "iou_padded": iou}

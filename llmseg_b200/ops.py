@@ -156,14 +156,130 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None, *,
+            src_row_map: Optional[torch.Tensor] = None, rows_out: Optional[int] = None) -> torch.Tensor:
     _req_bf16(x, gamma, out)
     dim = x.shape[-1]
     x2 = x.reshape(-1, dim) if x.dim() != 2 else x
+    rows = rows_out if rows_out is not None else x2.shape[0]
     if out is None:
-        out = torch.empty_like(x2)
+        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
     check(_lib.lib().llmseg_rmsnorm(x2.data_ptr(), x2.stride(0), out.data_ptr(), out.stride(0),
-                                    gamma.data_ptr(), x2.shape[0], dim, float(eps), _stream()),
-          "rmsnorm")
+                                    gamma.data_ptr(), rows, dim, float(eps), _ptr(src_row_map),
+                                    _stream()), "rmsnorm")
+    return out
+
+
+def patchify(images: torch.Tensor, patch: int, k_pad: int, cls_rows: int = 0) -> torch.Tensor:
+    """[B,3,S,S] bf16 NCHW -> [B*(g*g+cls_rows), k_pad] patch rows (conv-as-GEMM operand)."""
+    _req_bf16(images)
+    B, Cc, S, S2 = images.shape
+    assert Cc == 3 and S == S2 and images.is_contiguous()
+    g = S // patch
+    out = torch.empty((B * (g * g + cls_rows), k_pad), dtype=torch.bfloat16, device=images.device)
+    check(_lib.lib().llmseg_patchify(images.data_ptr(), out.data_ptr(), B, S, patch, k_pad, cls_rows,
+                                     _stream()), "patchify")
+    return out
+
+
+def embed_splice(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], embed: torch.Tensor,
+                 feats: torch.Tensor, *, image_token: int, seg_token: int):
+    """-> (embeds [N*T, D] bf16, kv_len int32 [N], seg_row int32 [N]) with T = T_text + F - 1."""
+    _req_bf16(embed, feats)
+    assert input_ids.dtype == torch.int64 and input_ids.is_cuda and input_ids.is_contiguous()
+    N, Tt = input_ids.shape
+    F_, D = feats.shape[-2], feats.shape[-1]
+    T = Tt + F_ - 1
+    m = None
+    if attention_mask is not None:
+        m = attention_mask.to(torch.uint8).contiguous()
+    out = torch.empty((N * T, D), dtype=torch.bfloat16, device=embed.device)
+    kv_len = torch.empty(N, dtype=torch.int32, device=embed.device)
+    seg_row = torch.empty(N, dtype=torch.int32, device=embed.device)
+    check(_lib.lib().llmseg_embed_splice(input_ids.data_ptr(), _ptr(m), embed.data_ptr(), feats.data_ptr(),
+                                         out.data_ptr(), kv_len.data_ptr(), seg_row.data_ptr(), N, Tt, F_,
+                                         D, image_token, seg_token, embed.shape[0], _stream()),
+          "embed_splice")
+    return out, kv_len, seg_row
+
+
+def add_rows_bcast(x: torch.Tensor, y: torch.Tensor, *, group: int = 0,
+                   row_group: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_bf16(x, y)
+    out = torch.empty_like(x)
+    check(_lib.lib().llmseg_add_rows_bcast(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.shape[0],
+                                           x.shape[1], group, _ptr(row_group), _stream()),
+          "add_rows_bcast")
+    return out
+
+
+def im2col3x3(x: torch.Tensor, batch: int, height: int, width: int) -> torch.Tensor:
+    """token-major NHWC [B*H*W, C] -> [B*H*W, 9*C] (zero padded 3x3 neighbourhoods, (ky,kx,c) order)."""
+    _req_bf16(x)
+    Cc = x.shape[1]
+    out = torch.empty((x.shape[0], 9 * Cc), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().llmseg_im2col3x3(x.data_ptr(), out.data_ptr(), batch, height, width, Cc, _stream()),
+          "im2col3x3")
+    return out
+
+
+def maskpool(segs: torch.Tensor, emb_tokens: torch.Tensor, mask_image: torch.Tensor) -> torch.Tensor:
+    """segs [n_masks,256,256] bf16, emb_tokens [B,4096,256] bf16, mask_image int32 [n_masks] -> [n_masks,256]."""
+    _req_bf16(segs, emb_tokens)
+    n = segs.shape[0]
+    assert segs.shape[1:] == (256, 256) and segs.is_contiguous() and emb_tokens.is_contiguous()
+    ws = torch.empty(int(_lib.lib().llmseg_maskpool_workspace(n)), dtype=torch.uint8, device=segs.device)
+    out = torch.empty((n, 256), dtype=torch.bfloat16, device=segs.device)
+    check(_lib.lib().llmseg_maskpool(segs.data_ptr(), emb_tokens.data_ptr(), mask_image.data_ptr(), n,
+                                     out.data_ptr(), ws.data_ptr(), _stream()), "maskpool")
+    return out
+
+
+def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_off: torch.Tensor,
+                    kv_off: torch.Tensor, *, batch: int, heads: int, max_kv: int) -> torch.Tensor:
+    """q/k/v are (possibly strided column views of) [rows, heads*32] bf16; offsets int32 [batch+1]."""
+    _req_bf16(q, k, v)
+    out = torch.empty((q.shape[0], heads * 32), dtype=torch.bfloat16, device=q.device)
+    check(_lib.lib().llmseg_small_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+                                            v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                                            q_off.data_ptr(), kv_off.data_ptr(), batch, heads, 32, max_kv,
+                                            _stream()), "small_attention")
+    return out
+
+
+def select(feat: torch.Tensor, text: torch.Tensor, h_iou: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+           k_off: torch.Tensor, *, batch: int, k_stride: int):
+    _req_bf16(feat, text, h_iou, w2, b2)
+    dev = feat.device
+    sim = torch.empty((batch, k_stride), dtype=torch.float32, device=dev)
+    iou = torch.empty((batch, k_stride), dtype=torch.float32, device=dev)
+    best = torch.empty(batch, dtype=torch.int32, device=dev)
+    check(_lib.lib().llmseg_select(feat.data_ptr(), text.data_ptr(), h_iou.data_ptr(), w2.data_ptr(),
+                                   b2.data_ptr(), k_off.data_ptr(), batch, k_stride, sim.data_ptr(),
+                                   iou.data_ptr(), best.data_ptr(), _stream()), "select")
+    return sim, iou, best
+
+
+def align_iou_loss(sim: torch.Tensor, pred_iou: torch.Tensor, gt_iou: torch.Tensor,
+                   temperature: float = 0.05) -> torch.Tensor:
+    """-> fp32 [2] = {softmax_align_loss, iou_regression_loss} (reference model/loss.py:50-94)."""
+    for t in (sim, pred_iou, gt_iou):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=sim.device)
+    check(_lib.lib().llmseg_align_iou_loss(sim.data_ptr(), pred_iou.data_ptr(), gt_iou.data_ptr(),
+                                           sim.numel(), float(temperature), out.data_ptr(), _stream()),
+          "align_iou_loss")
+    return out
+
+
+def dice_bce_loss(logits: torch.Tensor, targets: torch.Tensor, num_masks: float) -> torch.Tensor:
+    """logits/targets fp32 [n,H,W] -> fp32 [2] = {dice_loss, sigmoid_ce_loss} (reference model/loss.py:4-47)."""
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    assert targets.shape == logits.shape and targets.dtype == torch.float32 and targets.is_contiguous()
+    n = logits.shape[0]
+    hw = logits[0].numel()
+    ws = torch.empty(2 * n, dtype=torch.float32, device=logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    check(_lib.lib().llmseg_dice_bce_loss(logits.data_ptr(), targets.data_ptr(), n, hw, float(num_masks),
+                                          ws.data_ptr(), out.data_ptr(), _stream()), "dice_bce_loss")
     return out

@@ -1,0 +1,185 @@
+"""Seeded synthetic weights and inputs for the LLM-Seg forward: there are no
+checkpoints or datasets offline, so benchmarks and parity tests use random-init weights with the
+reference's parameter names/shapes and ReasonSeg-shaped inputs.
+
+Weights are generated directly on the target device in bf16 (a 7B-parameter state dict takes
+seconds on a GPU, minutes on the CPU).  This is set-up code, not part of the measured path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+
+from .lisa import IMAGE_TOKEN_INDEX, ClipCfg, LisaCfg, LlamaCfg, SamCfg
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+class _Gen:
+    def __init__(self, seed: int, device):
+        self.g = torch.Generator(device=device).manual_seed(seed)
+        self.device = device
+
+    def rn(self, *shape, std=0.02, mean=0.0) -> Tensor:
+        t = torch.randn(*shape, generator=self.g, device=self.device, dtype=torch.float32)
+        return (t * std + mean).to(BF16)
+
+
+def sam_state_dict(cfg: SamCfg, seed: int, device, prefix: str = "model.visual_model.image_encoder.") -> Dict[str, Tensor]:
+    G = _Gen(seed, device)
+    D, hd = cfg.embed_dim, cfg.embed_dim // cfg.num_heads
+    mlp, p, g = int(D * cfg.mlp_ratio), cfg.patch_size, cfg.grid
+    sd = {
+        prefix + "patch_embed.proj.weight": G.rn(D, 3, p, p, std=(3 * p * p) ** -0.5),
+        prefix + "patch_embed.proj.bias": G.rn(D),
+        prefix + "pos_embed": G.rn(1, g, g, D),
+        prefix + "neck.0.weight": G.rn(cfg.out_chans, D, 1, 1, std=D ** -0.5),
+        prefix + "neck.1.weight": G.rn(cfg.out_chans, std=0.1, mean=1.0), prefix + "neck.1.bias": G.rn(cfg.out_chans, std=0.1),
+        prefix + "neck.2.weight": G.rn(cfg.out_chans, cfg.out_chans, 3, 3, std=(9 * cfg.out_chans) ** -0.5),
+        prefix + "neck.3.weight": G.rn(cfg.out_chans, std=0.1, mean=1.0), prefix + "neck.3.bias": G.rn(cfg.out_chans, std=0.1),
+    }
+    for i in range(cfg.depth):
+        b = f"{prefix}blocks.{i}."
+        S = g if i in cfg.global_attn_indexes else cfg.window_size
+        sd.update({
+            b + "norm1.weight": G.rn(D, std=0.1, mean=1.0), b + "norm1.bias": G.rn(D, std=0.1),
+            b + "norm2.weight": G.rn(D, std=0.1, mean=1.0), b + "norm2.bias": G.rn(D, std=0.1),
+            b + "attn.qkv.weight": G.rn(3 * D, D, std=D ** -0.5), b + "attn.qkv.bias": G.rn(3 * D, std=0.1),
+            b + "attn.proj.weight": G.rn(D, D, std=0.5 * D ** -0.5), b + "attn.proj.bias": G.rn(D),
+            # the reference zero-initialises these; N(0, .) so the rel-pos path is exercised
+            b + "attn.rel_pos_h": G.rn(2 * S - 1, hd, std=0.1), b + "attn.rel_pos_w": G.rn(2 * S - 1, hd, std=0.1),
+            b + "mlp.lin1.weight": G.rn(mlp, D, std=D ** -0.5), b + "mlp.lin1.bias": G.rn(mlp),
+            b + "mlp.lin2.weight": G.rn(D, mlp, std=0.5 * mlp ** -0.5), b + "mlp.lin2.bias": G.rn(D),
+        })
+    return sd
+
+
+def clip_state_dict(cfg: ClipCfg, seed: int, device, prefix: str = "model.vision_tower.vision_tower.vision_model.") -> Dict[str, Tensor]:
+    G = _Gen(seed, device)
+    D, p = cfg.hidden, cfg.patch_size
+    sd = {
+        prefix + "embeddings.class_embedding": G.rn(D, std=0.5),
+        prefix + "embeddings.patch_embedding.weight": G.rn(D, 3, p, p, std=(3 * p * p) ** -0.5),
+        prefix + "embeddings.position_embedding.weight": G.rn(cfg.tokens, D, std=0.3),
+        prefix + "pre_layrnorm.weight": G.rn(D, std=0.1, mean=1.0), prefix + "pre_layrnorm.bias": G.rn(D, std=0.1),
+    }
+    for i in range(cfg.layers):
+        l = f"{prefix}encoder.layers.{i}."
+        for n in ("layer_norm1", "layer_norm2"):
+            sd[l + n + ".weight"] = G.rn(D, std=0.1, mean=1.0)
+            sd[l + n + ".bias"] = G.rn(D, std=0.1)
+        for n in ("q_proj", "k_proj", "v_proj"):
+            sd[l + f"self_attn.{n}.weight"] = G.rn(D, D, std=D ** -0.5)
+            sd[l + f"self_attn.{n}.bias"] = G.rn(D, std=0.1)
+        sd[l + "self_attn.out_proj.weight"] = G.rn(D, D, std=0.5 * D ** -0.5)
+        sd[l + "self_attn.out_proj.bias"] = G.rn(D)
+        sd[l + "mlp.fc1.weight"], sd[l + "mlp.fc1.bias"] = G.rn(cfg.mlp, D, std=D ** -0.5), G.rn(cfg.mlp)
+        sd[l + "mlp.fc2.weight"], sd[l + "mlp.fc2.bias"] = G.rn(D, cfg.mlp, std=0.5 * cfg.mlp ** -0.5), G.rn(D)
+    return sd
+
+
+def llama_state_dict(cfg: LlamaCfg, seed: int, device, prefix: str = "model.") -> Dict[str, Tensor]:
+    G = _Gen(seed, device)
+    D = cfg.hidden
+    sd = {prefix + "embed_tokens.weight": G.rn(cfg.vocab, D, std=1.0), prefix + "norm.weight": G.rn(D, std=0.1, mean=1.0)}
+    for i in range(cfg.layers):
+        l = f"{prefix}layers.{i}."
+        sd[l + "input_layernorm.weight"] = G.rn(D, std=0.1, mean=1.0)
+        sd[l + "post_attention_layernorm.weight"] = G.rn(D, std=0.1, mean=1.0)
+        for n in ("q_proj", "k_proj", "v_proj"):
+            sd[l + f"self_attn.{n}.weight"] = G.rn(D, D, std=D ** -0.5)
+        sd[l + "self_attn.o_proj.weight"] = G.rn(D, D, std=0.5 * D ** -0.5)
+        sd[l + "mlp.gate_proj.weight"] = G.rn(cfg.mlp, D, std=D ** -0.5)
+        sd[l + "mlp.up_proj.weight"] = G.rn(cfg.mlp, D, std=D ** -0.5)
+        sd[l + "mlp.down_proj.weight"] = G.rn(D, cfg.mlp, std=0.5 * cfg.mlp ** -0.5)
+    return sd
+
+
+def selector_state_dict(hidden: int, seed: int, device, prefix: str = "model.") -> Dict[str, Tensor]:
+    G = _Gen(seed, device)
+    E, MLP = 256, 2048
+    sd: Dict[str, Tensor] = {}
+
+    def lin(name, out_f, in_f):
+        sd[prefix + name + ".weight"] = G.rn(out_f, in_f, std=in_f ** -0.5)
+        sd[prefix + name + ".bias"] = G.rn(out_f, std=0.05)
+
+    def ln(name):
+        sd[prefix + name + ".weight"] = G.rn(E, std=0.1, mean=1.0)
+        sd[prefix + name + ".bias"] = G.rn(E, std=0.1)
+
+    lin("text_hidden_fcs.0.0", hidden, hidden)
+    lin("text_hidden_fcs.0.2", E, hidden)
+    for i in range(2):
+        p = f"lisa_attention_layers.{i}."
+        for att in ("self_attn", "cross_attn_token_to_image", "cross_attn_image_to_token"):
+            for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                lin(p + att + "." + proj, E, E)
+        for n in ("norm1", "norm2", "norm3", "norm4"):
+            ln(p + n)
+        lin(p + "mlp.lin1", MLP, E)
+        lin(p + "mlp.lin2", E, MLP)
+    for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        lin("lisa_final_attn." + proj, E, E)
+    ln("lisa_norm_final_attn")
+    lin("lisa_iou_head.0", 128, E)
+    lin("lisa_iou_head.2", 1, 128)
+    lin("lisa_embedding_head.0", 2048, E)
+    lin("lisa_embedding_head.2", E, 2048)
+    return sd
+
+
+def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda") -> Dict[str, Tensor]:
+    """Full random-init state dict with the reference's key names, bf16 on `device`."""
+    sd: Dict[str, Tensor] = {}
+    sd.update(sam_state_dict(cfg.sam, seed + 1, device))
+    sd.update(clip_state_dict(cfg.clip, seed + 2, device))
+    sd.update(llama_state_dict(cfg.llama, seed + 3, device))
+    sd.update(selector_state_dict(cfg.llama.hidden, seed + 4, device))
+    G = _Gen(seed + 5, device)
+    sd["model.mm_projector.weight"] = G.rn(cfg.llama.hidden, cfg.clip.hidden, std=cfg.clip.hidden ** -0.5)
+    sd["model.mm_projector.bias"] = G.rn(cfg.llama.hidden)
+    return sd
+
+
+def make_proposals(K: int, gen: torch.Generator, device) -> Tensor:
+    """K structured soft masks [K,256,256] in [0,1]: axis-aligned rectangles with log-uniform area in
+    [1%, 40%], blurred by a 3x3 box (mimics the antialiased resize of reference utils/dataset.py:620-622)."""
+    area = torch.exp(torch.empty(K, device=device).uniform_(-4.605, -0.916, generator=gen))  # ln(0.01)..ln(0.4)
+    aspect = torch.exp(torch.empty(K, device=device).uniform_(-0.7, 0.7, generator=gen))
+    h = (area * aspect).sqrt().clamp(max=1.0) * 256
+    w = (area / aspect).sqrt().clamp(max=1.0) * 256
+    cy = torch.rand(K, device=device, generator=gen) * (256 - h) + h / 2
+    cx = torch.rand(K, device=device, generator=gen) * (256 - w) + w / 2
+    yy = torch.arange(256, device=device).view(1, 256, 1).float() + 0.5
+    xx = torch.arange(256, device=device).view(1, 1, 256).float() + 0.5
+    m = ((yy - cy.view(K, 1, 1)).abs() <= h.view(K, 1, 1) / 2) & ((xx - cx.view(K, 1, 1)).abs() <= w.view(K, 1, 1) / 2)
+    m = torch.nn.functional.avg_pool2d(m.float().unsqueeze(1), 3, 1, 1).squeeze(1)
+    return m.to(BF16)
+
+
+def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int = 1234, device="cuda") -> dict:
+    """ReasonSeg-shaped synthetic `input_dict` (keys of reference utils/dataset.py:150-170 that the
+    forward reads).  Token layout per SURVEY §8d: [bos, .., <im_start>, IMAGE, <im_end>, text.., [SEG], '.', eos]."""
+    assert t_text >= 8
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    S, Sc = cfg.sam.img_size, cfg.clip.image_size
+    images = torch.randn(batch, 3, S, S, generator=g, device=dev).to(BF16)
+    images_clip = torch.randn(batch, 3, Sc, Sc, generator=g, device=dev).to(BF16)
+    ids = torch.randint(3, 31999, (batch, t_text), generator=g, device=dev, dtype=torch.int64)
+    ids[:, 0] = 1
+    ids[:, 1], ids[:, 2], ids[:, 3] = 32001, IMAGE_TOKEN_INDEX, 32002
+    ids[:, t_text - 3] = cfg.seg_token_idx
+    ids[:, t_text - 2] = 29889
+    ids[:, t_text - 1] = 2
+    return {
+        "images": images, "images_clip": images_clip, "input_ids": ids, "labels": ids.clone(),
+        "attention_masks": torch.ones(batch, t_text, dtype=torch.bool, device=dev),
+        "offset": torch.arange(batch + 1), "masks_list": [None] * batch, "label_list": [None] * batch,
+        "resize_list": [(S, S)] * batch,
+        "sam_segs_list": [make_proposals(n_props, g, dev) for _ in range(batch)],
+        "sam_ious_list": None, "sam_iops_list": None, "inference": True,
+    }
