@@ -1,0 +1,107 @@
+"""ORACLE-side CPU baseline (test/bench infrastructure, never on the product path).
+
+Times the reference algorithm (the oracle restatement: fp32 eager PyTorch, as the reference runs
+on a CPU) on the host cores, on a BOUNDED sample of the forward, and extrapolates to images/s:
+
+    one image = patch-embed + 28 windowed + 4 global SAM blocks + neck
+              + CLIP embed + 23 CLIP layers + projector
+              + 32 LLaMA layers at T = T_text + 255
+              + selector (upsample, pooling, 2 two-way blocks, heads, cosine)
+
+Every distinct layer type is executed for real at full width (one instance each, random weights),
+timed after one warm-up, and multiplied by its count; the full 32+23+32-layer stack would take
+~1 minute per image on 8 cores, which is why the sample is bounded.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+from . import clip_llama, sam_encoder, selector
+
+
+def _timeit(fn, reps: int = 1) -> float:
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def cpu_forward_sample(t_text: int = 64, k_props: int = 64, threads: int | None = None, reps: int = 1) -> Dict:
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    out: Dict = {"cores": threads, "kind": "port"}
+    parts = {}
+    with torch.no_grad():
+        # ---- SAM ViT-H: one windowed block, one global block, patch embed, neck
+        scfg = sam_encoder.SamConfig(depth=2, global_attn_indexes=(1,))
+        sd = sam_encoder.random_state_dict(scfg, seed=0)
+        x = rn(1, 64, 64, 1280, std=1.0)
+        img = rn(1, 3, 1024, 1024, std=1.0)
+        parts["sam_window_block"] = _timeit(lambda: sam_encoder.block(x, sd, "blocks.0.", scfg, 14), reps)
+        parts["sam_global_block"] = _timeit(lambda: sam_encoder.block(x, sd, "blocks.1.", scfg, 0), reps)
+        parts["sam_patch_embed"] = _timeit(lambda: F.conv2d(img, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=16), reps)
+
+        def neck():
+            y = F.conv2d(x.permute(0, 3, 1, 2), sd["neck.0.weight"])
+            y = sam_encoder.layer_norm_2d(y, sd["neck.1.weight"], sd["neck.1.bias"])
+            y = F.conv2d(y, sd["neck.2.weight"], padding=1)
+            return sam_encoder.layer_norm_2d(y, sd["neck.3.weight"], sd["neck.3.bias"])
+        parts["sam_neck"] = _timeit(neck, reps)
+        sam_s = parts["sam_patch_embed"] + 28 * parts["sam_window_block"] + 4 * parts["sam_global_block"] + parts["sam_neck"]
+        del sd
+
+        # ---- CLIP ViT-L/14: embeddings + one layer (x23) ; projector
+        ccfg1 = clip_llama.ClipConfig(layers=1, select_layer=1)
+        csd = clip_llama.clip_random_state_dict(ccfg1, seed=1)
+        imc = rn(1, 3, 224, 224, std=1.0)
+        t_one = _timeit(lambda: clip_llama.clip_patch_features(imc, csd, ccfg1), reps)
+        ccfg0 = clip_llama.ClipConfig(layers=1, select_layer=0)
+        t_zero = _timeit(lambda: clip_llama.clip_patch_features(imc, csd, ccfg0), reps)
+        wproj = rn(4096, 1024)
+        feats = rn(1, 256, 1024, std=1.0)
+        parts["clip_embed"] = t_zero
+        parts["clip_layer"] = max(t_one - t_zero, 0.0)
+        parts["mm_projector"] = _timeit(lambda: F.linear(feats, wproj), reps)
+        clip_s = parts["clip_embed"] + 23 * parts["clip_layer"] + parts["mm_projector"]
+        del csd
+
+        # ---- LLaMA-7B: one decoder layer at T = t_text + 255 (x32)
+        lcfg = clip_llama.LlamaConfig(layers=1)
+        lsd = clip_llama.llama_random_state_dict(clip_llama.LlamaConfig(layers=1, vocab=8), seed=2)
+        T = t_text + 255
+        emb = rn(1, T, 4096, std=1.0)
+        parts["llama_layer"] = _timeit(lambda: clip_llama.llama_last_hidden(emb, None, lsd, lcfg), reps)
+        llama_s = 32 * parts["llama_layer"]
+        del lsd
+
+        # ---- selector stage (full)
+        ssd = selector.random_state_dict(seed=3, hidden=4096)
+        e = rn(1, 256, 64, 64, std=1.0)
+        segs = torch.rand(k_props, 256, 256, generator=g)
+        hid = rn(1, 4096, std=1.0)
+
+        def sel():
+            t = selector.text_hidden_fc(hid, ssd)
+            return selector.selector_forward(selector.upsample_embeddings(e)[0], segs, t, ssd)
+        parts["selector"] = _timeit(sel, reps)
+
+    total = sam_s + clip_s + llama_s + parts["selector"]
+    out.update(value=1.0 / total, unit="images/s", seconds_per_image=total,
+               parts_s={k: round(v, 4) for k, v in parts.items()},
+               sample=(f"fp32 eager oracle, 1 image, {t_text}-tok prompt, {k_props} proposals: one instance of each "
+                       f"layer type timed at full width (SAM window+global block, CLIP layer, LLaMA layer @T={T}, "
+                       f"patch embeds, neck, projector, full selector) x layer counts 28/4/23/32"))
+    return out
+
+
+if __name__ == "__main__":
+    import json
+    print(json.dumps(cpu_forward_sample(), indent=1))

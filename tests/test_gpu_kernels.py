@@ -1,0 +1,263 @@
+"""GPU (-m gpu): each sm_100a kernel, called through the C ABI, against a plain PyTorch fp32
+reference of the same op on the same bf16 inputs.  Tolerances are bf16 rounding-level: the kernels
+accumulate in fp32 and round once per reference rounding point."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf(t):
+    return t.to(DEV).bfloat16()
+
+
+def _ulp_tol(ref, rel=2 ** -7):
+    """bf16 has 8 bits of mantissa: allow ~2 ulp of the largest magnitude involved."""
+    return float(ref.abs().max()) * rel + 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 1032, 1288), (4096, 3840, 1280), (257, 1024, 1024), (1, 256, 4096)])
+@pytest.mark.parametrize("act", [None, "gelu", "quick_gelu", "relu"])
+def test_gemm_bias_act_residual(cuda_lib, M, N, K, act):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w = _bf(torch.randn(M, K, generator=g)), _bf(torch.randn(N, K, generator=g) / K ** 0.5)
+    b, r = _bf(torch.randn(N, generator=g)), _bf(torch.randn(M, N, generator=g))
+    out = ops.gemm(a, w, b, act=act, residual=r)
+    ref = (a.float() @ w.float().T + b.float()).bfloat16().float()
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref).bfloat16().float()
+    elif act == "quick_gelu":
+        ref = (ref * torch.sigmoid(1.702 * ref)).bfloat16().float()
+    elif act == "relu":
+        ref = torch.relu(ref)
+    ref = ref + r.float()
+    assert (out.float() - ref).abs().max().item() <= _ulp_tol(ref)
+
+
+def test_gemm_row_scatter_and_broadcast_residual(cuda_lib):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, N, K, R = 500, 256, 128, 300
+    a, w = _bf(torch.randn(M, K, generator=g)), _bf(torch.randn(N, K, generator=g) / K ** 0.5)
+    perm = torch.randperm(M, generator=g)[:R]
+    m = torch.full((M,), -1, dtype=torch.int32)
+    m[perm] = torch.arange(R, dtype=torch.int32)
+    res = _bf(torch.randn(50, N, generator=g))
+    out = torch.zeros(R, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, None, residual=res, res_mod=50, out=out, out_row_map=m.to(DEV))
+    full = (a.float() @ w.float().T).bfloat16().float()
+    ref = full[perm.to(DEV)] + res.float()[torch.arange(R, device=DEV) % 50]
+    assert (out.float() - ref).abs().max().item() <= _ulp_tol(ref)
+
+
+def test_gemm_swiglu(cuda_lib):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    M, F, K = 319, 1024, 512
+    a = _bf(torch.randn(M, K, generator=g))
+    gate, up = _bf(torch.randn(F, K, generator=g) / K ** 0.5), _bf(torch.randn(F, K, generator=g) / K ** 0.5)
+    w = torch.stack([gate, up], 1).reshape(2 * F, K).contiguous()
+    out = ops.gemm(a, w, None, swiglu=True)
+    gg, uu = (a.float() @ gate.float().T).bfloat16().float(), (a.float() @ up.float().T).bfloat16().float()
+    ref = torch.nn.functional.silu(gg).bfloat16().float() * uu
+    assert out.shape == (M, F)
+    assert (out.float() - ref).abs().max().item() <= _ulp_tol(ref)
+
+
+@pytest.mark.parametrize("rows,dim,eps", [(4096, 1280, 1e-6), (257, 1024, 1e-5), (319, 4096, 1e-6), (64, 256, 1e-5)])
+def test_norms(cuda_lib, rows, dim, eps):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    x = _bf(torch.randn(rows, dim, generator=g) * 2 + 0.5)
+    gm, bt = _bf(1 + 0.1 * torch.randn(dim, generator=g)), _bf(0.1 * torch.randn(dim, generator=g))
+    y = ops.layernorm(x, gm, bt, eps)
+    ref = torch.nn.functional.layer_norm(x.float(), (dim,), gm.float(), bt.float(), eps)
+    assert (y.float() - ref).abs().max().item() <= _ulp_tol(ref)
+    y = ops.rmsnorm(x, gm, eps)
+    xf = x.float()
+    ref = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).bfloat16().float() * gm.float()
+    assert (y.float() - ref).abs().max().item() <= _ulp_tol(ref)
+    # gather + zero rows (window padding tokens are zeros AFTER the norm)
+    m = torch.tensor([3, -1, 0, rows - 1], dtype=torch.int32, device=DEV)
+    y = ops.layernorm(x, gm, bt, eps, src_row_map=m, rows_out=4)
+    ref4 = torch.nn.functional.layer_norm(x.float()[[3, 0, 0, rows - 1]], (dim,), gm.float(), bt.float(), eps)
+    ref4[1] = 0
+    assert (y.float() - ref4).abs().max().item() <= _ulp_tol(ref4)
+
+
+def _qkv_setup(B, H, hd, S, g, rope=False):
+    from llmseg_b200 import ops
+    D = H * hd
+    S_pad = (S + 7) // 8 * 8
+    x = _bf(torch.randn(B * S, D, generator=g))
+    w = _bf(torch.randn(3 * D, D, generator=g) / D ** 0.5)
+    bias = None if rope else _bf(torch.randn(3 * D, generator=g) * 0.1)
+    q = torch.zeros(B * H, S_pad, hd, device=DEV, dtype=torch.bfloat16)
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B * H, hd, S_pad, device=DEV, dtype=torch.bfloat16)
+    cos = sin = None
+    if rope:
+        inv = 1.0 / (10000 ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
+        fr = torch.outer(torch.arange(S, dtype=torch.float32), inv)
+        cos, sin = _bf(fr.cos()).contiguous(), _bf(fr.sin()).contiguous()
+    ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S_pad, rope_cos=cos, rope_sin=sin)
+    ref = x.float() @ w.float().T
+    if bias is not None:
+        ref = ref + bias.float()
+    ref = ref.bfloat16().float().reshape(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    rq, rk, rv = ref[0], ref[1], ref[2]
+    if rope:
+        c = torch.cat([cos, cos], -1).float()[None, None]
+        s_ = torch.cat([sin, sin], -1).float()[None, None]
+        rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)
+        ap = lambda t: ((t * c).bfloat16().float() + (rot(t) * s_).bfloat16().float()).bfloat16().float()
+        rq, rk = ap(rq), ap(rk)
+    return q, k, vt, rq, rk, rv, S_pad
+
+
+def _attn_ref(qf, kf, vf, scale, mask=None, bias=None):
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    if bias is not None:
+        s = s + bias
+    if mask is not None:
+        s = s.masked_fill(mask, float("-inf"))
+    return torch.softmax(s, -1) @ vf
+
+
+@pytest.mark.parametrize("B,H,hd,S,causal,rope", [(2, 16, 64, 257, False, False), (1, 4, 80, 300, False, False),
+                                                   (2, 32, 128, 319, True, True), (1, 2, 64, 128, False, False),
+                                                   (1, 2, 128, 767, True, True)])
+def test_qkv_split_and_attention(cuda_lib, B, H, hd, S, causal, rope):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    q, k, vt, rq, rk, rv, S_pad = _qkv_setup(B, H, hd, S, g, rope)
+    tol = _ulp_tol(rq)
+    assert (q[:, :S].float().reshape(B, H, S, hd) - rq).abs().max().item() <= tol
+    assert (k[:, :S].float().reshape(B, H, S, hd) - rk).abs().max().item() <= tol
+    assert (vt[:, :, :S].float().reshape(B, H, hd, S).transpose(-1, -2) - rv).abs().max().item() <= tol
+    kv_len = None
+    mask = None
+    if causal:
+        lens = [S] + [max(S - 69, 1)] * (B - 1)
+        kv_len = torch.tensor(lens, dtype=torch.int32, device=DEV)
+        i = torch.arange(S, device=DEV)
+        mask = (i[None, :] > i[:, None])[None, None] | (i[None, None, None, :] >= kv_len[:, None, None, None])
+    qf, kf = q[:, :S].float().reshape(B, H, S, hd), k[:, :S].float().reshape(B, H, S, hd)
+    vf = vt[:, :, :S].float().reshape(B, H, hd, S).transpose(-1, -2)
+    ref = _attn_ref(qf, kf, vf, hd ** -0.5, mask).permute(0, 2, 1, 3).reshape(B * S, H * hd)
+    out = torch.full((B * S, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k, vt, out, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S_pad, scale=hd ** -0.5,
+                  causal=causal, kv_len=kv_len)
+    valid = torch.ones(B, S, dtype=torch.bool, device=DEV)
+    if kv_len is not None:
+        valid = torch.arange(S, device=DEV)[None] < kv_len[:, None]   # padded query rows are don't-care
+    d = (out.float() - ref).reshape(B, S, -1)[valid]
+    assert not torch.isnan(d).any()
+    assert d.abs().max().item() <= 2e-2 * max(1.0, float(ref.abs().max()))
+    assert d.abs().mean().item() <= 2e-3
+
+
+@pytest.mark.parametrize("grid,nb", [(14, 25), (64, 1)])
+def test_sam_relpos_attention(cuda_lib, grid, nb):
+    """decomposed rel-pos through the tensor-core score extension vs the reference formula
+    (reference image_encoder.py:354-392, restated in oracle/sam_encoder.py)."""
+    from llmseg_b200 import ops
+    from oracle import sam_encoder as o_sam
+    H, hd, S = 4, 80, grid * grid
+    g = torch.Generator().manual_seed(grid)
+    q, k, vt, rq, rk, rv, S_pad = _qkv_setup(nb, H, hd, S, g)
+    rel_h, rel_w = _bf(torch.randn(2 * grid - 1, hd, generator=g) * 0.2), _bf(torch.randn(2 * grid - 1, hd, generator=g) * 0.2)
+    scale = hd ** -0.5
+    ext = 32 if grid == 14 else 64
+    qext = torch.zeros(nb * H, S_pad, ext, device=DEV, dtype=torch.bfloat16)
+    rb = torch.zeros(nb * H, S_pad, 64, device=DEV, dtype=torch.bfloat16) if grid == 64 else None
+    ops.relpos_prep(q, ops.make_rel_hw(rel_h, rel_w), bh=nb * H, seq=S, seq_pad=S_pad, head_dim=hd, grid=grid,
+                    inv_scale=1 / scale, qext=qext, row_bias=rb)
+    out = torch.empty(nb * S, H * hd, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k, vt, out, batch=nb, heads=H, head_dim=hd, seq=S, seq_pad=S_pad, scale=scale, qext=qext,
+                  kext=ops.make_kext(grid, DEV), row_bias=rb, ext_cols=ext)
+    qf = q[:, :S].float()
+    bias = o_sam.decomposed_rel_pos_bias(qf, rel_h.float(), rel_w.float(), (grid, grid))
+    vf = vt[:, :, :S].float().transpose(-1, -2)
+    ref = _attn_ref(qf, k[:, :S].float(), vf, scale, bias=bias).reshape(nb, H, S, hd).permute(0, 2, 1, 3).reshape(nb * S, H * hd)
+    d = out.float() - ref
+    assert d.abs().max().item() <= 6e-2 * max(1.0, float(ref.abs().max()))
+    assert d.abs().mean().item() <= 4e-3
+
+
+def test_patchify_embed_splice_im2col(cuda_lib):
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    img = _bf(torch.randn(2, 3, 224, 224, generator=g))
+    out = ops.patchify(img, 14, 592, cls_rows=1)
+    ref = torch.nn.functional.unfold(img.float(), 14, stride=14).transpose(1, 2)     # [2,256,588] (c,py,px)
+    got = out.float().reshape(2, 257, 592)
+    assert torch.equal(got[:, 1:, :588], ref) and float(got[:, 1:, 588:].abs().sum()) == 0
+    assert float(got[:, 0, :588].abs().sum()) == 0 and torch.all(got[:, 0, 588] == 1)
+    img16 = _bf(torch.randn(1, 3, 64, 64, generator=g))
+    o16 = ops.patchify(img16, 16, 768)
+    assert torch.equal(o16.float().reshape(1, 16, 768), torch.nn.functional.unfold(img16.float(), 16, stride=16).transpose(1, 2))
+    # splice (oracle: lisa_forward.splice_inputs / seg_token_mask)
+    from oracle import lisa_forward as o_lf
+    V, D, F_ = 100, 64, 256
+    emb = _bf(torch.randn(V, D, generator=g))
+    feats = _bf(torch.randn(2, F_, D, generator=g))
+    ids = torch.tensor([[1, 7, -200, 8, 5, 6, 9, 50, 3, 2], [1, 7, -200, 8, 50, 6, 9, 11, 3, 2]], device=DEV)
+    am = torch.ones(2, 10, dtype=torch.bool, device=DEV)
+    am[1, 7:] = False
+    cfg = o_lf.LisaConfig(seg_token_idx=50)
+    e_ref, m_ref = o_lf.splice_inputs(ids, am, feats.float(), emb.float())
+    e, kv_len, seg_row = ops.embed_splice(ids, am, emb, feats, image_token=-200, seg_token=50)
+    assert torch.equal(e.float().reshape(2, 265, D), e_ref)
+    assert kv_len.tolist() == m_ref.sum(-1).tolist()
+    sm = o_lf.seg_token_mask(ids, cfg)
+    assert seg_row.tolist() == [int(n * 265 + sm[n].nonzero()[0]) for n in range(2)]
+    # im2col 3x3
+    x = _bf(torch.randn(2 * 8 * 8, 16, generator=g))
+    col = ops.im2col3x3(x, 2, 8, 8)
+    xr = x.float().reshape(2, 8, 8, 16).permute(0, 3, 1, 2)
+    refc = torch.nn.functional.unfold(xr, 3, padding=1).reshape(2, 16, 9, 64).permute(0, 3, 2, 1).reshape(128, 144)
+    assert torch.equal(col.float(), refc)
+
+
+@pytest.mark.parametrize("K", [7, 32, 64])
+def test_maskpool_matches_oracle(cuda_lib, K):
+    """adjoint upsample∘pool vs the reference order of operations (LISA.py:201-218,350-354)."""
+    from llmseg_b200 import ops
+    from oracle import selector as o_sel
+    emb, segs, _ = o_sel.synthetic_case(100 + K, K)
+    emb_b, segs_b = _bf(emb), _bf(segs)
+    tok = emb_b[0].permute(1, 2, 0).reshape(1, 4096, 256).contiguous()
+    out = ops.maskpool(segs_b, tok, torch.zeros(K, dtype=torch.int32, device=DEV))
+    ref = o_sel.mask_pooling(o_sel.upsample_embeddings(emb_b.float())[0], segs_b.float())
+    assert (out.float() - ref).abs().max().item() <= 2e-3 + 2 ** -7 * float(ref.abs().max())
+
+
+def test_losses_match_golden(cuda_lib, golden_dir):
+    """loss kernels vs the values produced by the reference's own model/loss.py (tests/golden/losses.pt)."""
+    from llmseg_b200 import ops
+    fx = torch.load(golden_dir / "losses.pt", weights_only=False)
+    pe, te = fx["pe"], fx["te"]
+    sim = ((pe / pe.norm(dim=-1, keepdim=True)) @ (te / te.norm(dim=-1, keepdim=True)).t()).flatten()
+    out = ops.align_iou_loss(sim.to(DEV).contiguous(), fx["pred_ious"].flatten().to(DEV).contiguous(),
+                             fx["gt_ious"].flatten().to(DEV).contiguous())
+    assert abs(out[0].item() - fx["expected"]["softmax_align"]) < 1e-3
+    assert abs(out[1].item() - fx["expected"]["iou_regression"]) < 1e-3
+    out = ops.dice_bce_loss(fx["logits"].to(DEV).contiguous(), fx["targets"].to(DEV).contiguous(), 3.0)
+    assert abs(out[0].item() - fx["expected"]["dice"]) < 1e-4
+    assert abs(out[1].item() - fx["expected"]["sigmoid_ce"]) < 1e-4
+
+
+def test_ops_reject_bad_inputs(cuda_lib):
+    from llmseg_b200 import ops
+    a = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)      # K % 8 != 0
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, a)
+    with pytest.raises(TypeError):
+        ops.gemm(a.float(), a.float())
+    with pytest.raises(RuntimeError):
+        ops.gemm(a.cpu(), a.cpu())
