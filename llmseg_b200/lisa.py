@@ -9,7 +9,9 @@ Differences from the reference that a caller can observe:
   * batched inference is allowed (reference asserts one image per call, LISA.py:271); a batch of B
     images with one conversation each is defined as B independent reference calls
   * `inference=False` (training losses through the LLM) is outside the hot path and raises
-  * extra keys (`best_index`) are added to the returned dict; the reference keys are unchanged
+  * extra keys (`best_index`, padded logits) are added to the returned dict; the reference keys are unchanged
+  * the launch sequence of each input shape is captured once into a CUDA graph and replayed
+    (`use_cuda_graph=True`): ~2300 launches per forward would otherwise be CPU-bound at batch 1
 """
 from __future__ import annotations
 
@@ -113,7 +115,8 @@ class LISAForCausalLM:
     """B200 implementation of the reference class of the same name (inference forward only)."""
 
     def __init__(self, state_dict: Dict[str, Tensor], cfg: Optional[LisaCfg] = None, *,
-                 device: str = "cuda:0", seg_token_idx: Optional[int] = None, max_seq: int = 1024):
+                 device: str = "cuda:0", seg_token_idx: Optional[int] = None, max_seq: int = 1024,
+                 use_cuda_graph: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("llmseg_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
         from . import _lib
@@ -129,6 +132,9 @@ class LISAForCausalLM:
                               sd["model.mm_projector.weight"], sd["model.mm_projector.bias"])
         self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq)
         self.selector = Selector(_sub(sd, "model."), self.device)
+        self.use_cuda_graph = use_cuda_graph
+        self._plans: Dict[tuple, dict] = {}
+        self.last_forward_launches = 0
 
     # ---- reference API -------------------------------------------------------------------------
     def forward(self, **kwargs):
@@ -155,44 +161,103 @@ class LISAForCausalLM:
             raise NotImplementedError("llmseg_b200 implements the inference forward (inference=True); the training "
                                       "losses are out of the hot path (SURVEY §8f)")
         dev = self.device
-        images = images.to(dev, BF16)
-        images_clip = images_clip.to(dev, BF16)
-        input_ids = input_ids.to(dev, torch.int64).contiguous()
-        B = images.shape[0]
-        N = input_ids.shape[0]
+        B, N, Tt = images.shape[0], input_ids.shape[0], input_ids.shape[1]
         if offset is None:
             offset = torch.arange(B + 1)
         assert B == len(offset) - 1, "batch_size == len(offset) - 1 (reference LISA.py:250)"
-        off = [int(v) for v in offset.tolist()]
+        off = tuple(int(v) for v in offset.tolist())
         assert off[-1] == N and sam_segs_list is not None and len(sam_segs_list) == B
-        # CLIP input per conversation: image i for conversations offset[i]..offset[i+1] (LISA.py:272,293-303)
-        if images_clip.shape[0] == 1 and N > 1 and B == 1:
-            conv_image = [0] * N
+        Ks = tuple(int(s.shape[0]) for s in sam_segs_list)
+        n_clip = images_clip.shape[0]
+        key = (B, N, Tt, Ks, off, n_clip, attention_masks is None)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._make_plan(key)
+            self._plans[key] = plan
+        # ---- stage the inputs into the plan's static device buffers (H2D or D2D copies)
+        st = plan["static"]
+        st["images"].copy_(images, non_blocking=True)
+        st["images_clip"].copy_(images_clip, non_blocking=True)
+        st["input_ids"].copy_(input_ids, non_blocking=True)
+        if attention_masks is not None:
+            st["mask"].copy_(attention_masks, non_blocking=True)
+        r0 = 0
+        for sgs, kk in zip(sam_segs_list, Ks):
+            st["segs"][r0:r0 + kk].copy_(sgs, non_blocking=True)
+            r0 += kk
+        # ---- run: CUDA-graph replay (captured on first use of this shape) or eager launches
+        if self.use_cuda_graph:
+            if plan["graph"] is None:
+                self._capture(plan)
+            plan["graph"].replay()
+            sim, iou, best = plan["outputs"]
         else:
-            assert images_clip.shape[0] == B
-            conv_image = [i for i in range(B) for _ in range(off[i + 1] - off[i])]
-
-        # 1. SAM image encoder -> token-major embeddings [B,4096,256]
-        emb_tokens = self.sam.forward(images)
-
-        # 2. CLIP tower + projector (once per distinct image; the reference recomputes per conversation)
-        feats_img = self.clip.forward(images_clip)                       # [B',256,4096]
-        feats = feats_img if conv_image == list(range(N)) else feats_img[torch.tensor(conv_image, device=dev)].contiguous()
-
-        # 3. splice + LLaMA; only the hidden state that predicts [SEG] is normalised and returned
-        embeds, kv_len, seg_row = ops.embed_splice(
-            input_ids, None if attention_masks is None else attention_masks.to(dev), self.llama.embed, feats,
-            image_token=IMAGE_TOKEN_INDEX, seg_token=self.seg_token_idx)
-        T = input_ids.shape[1] + feats.shape[1] - 1
-        first_conv = torch.tensor(off[:-1], device=dev, dtype=torch.long)
-        rows = seg_row.index_select(0, first_conv).contiguous()           # conversation 0 of each image (LISA.py:400)
-        hidden = self.llama.forward(embeds, N, T, kv_len, out_rows=rows)  # [B,4096]
-        text_embed = self.selector.text_embed(hidden)                     # [B,256]
-
-        # 4. selector
-        segs = [s.to(dev, BF16) for s in sam_segs_list]
-        sim, iou, best, Ks = self.selector.forward(emb_tokens, segs, text_embed)
+            from . import _lib
+            n0 = _lib.launch_count()
+            sim, iou, best = self._run(plan)
+            plan["launches"] = _lib.launch_count() - n0
+        self.last_forward_launches = plan["launches"]
         pred_similarity = [sim[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
         pred_iou = [iou[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
         return {"pred_similarity": pred_similarity, "gt_masks": masks_list, "pred_iou": pred_iou,
-                "best_index": best, "similarity_padded": sim, "iou_padded": iou}
+                "best_index": best.clone(), "similarity_padded": sim.clone(), "iou_padded": iou.clone()}
+
+    # ---- plan / graph machinery ------------------------------------------------------------------
+    def _make_plan(self, key) -> dict:
+        B, N, Tt, Ks, off, n_clip, no_mask = key
+        dev, cfg = self.device, self.cfg
+        S, Sc = cfg.sam.img_size, cfg.clip.image_size
+        static = {
+            "images": torch.empty((B, 3, S, S), dtype=BF16, device=dev),
+            "images_clip": torch.empty((n_clip, 3, Sc, Sc), dtype=BF16, device=dev),
+            "input_ids": torch.empty((N, Tt), dtype=torch.int64, device=dev),
+            "mask": None if no_mask else torch.empty((N, Tt), dtype=torch.uint8, device=dev),
+            "segs": torch.empty((sum(Ks), 256, 256), dtype=BF16, device=dev),
+        }
+        # CLIP input per conversation: image i for conversations offset[i]..offset[i+1] (LISA.py:272,293-303)
+        if n_clip == 1 and B == 1:
+            conv_image = [0] * N
+        else:
+            assert n_clip == B, "images_clip must hold one image per SAM image"
+            conv_image = [i for i in range(B) for _ in range(off[i + 1] - off[i])]
+        conv_index = None if conv_image == list(range(N)) and n_clip == N else torch.tensor(conv_image, device=dev)
+        first_conv = None if N == B else torch.tensor(off[:-1], device=dev, dtype=torch.long)
+        return {"key": key, "static": static, "conv_index": conv_index, "first_conv": first_conv,
+                "sel": self.selector.make_plan(Ks), "graph": None, "outputs": None, "launches": 0}
+
+    def _run(self, plan):
+        """The whole forward as kernel launches on the current stream (graph-capturable: no host syncs,
+        no host->device copies; every index tensor comes from the plan)."""
+        st = plan["static"]
+        B, N, Tt = plan["key"][0], plan["key"][1], plan["key"][2]
+        # 1. SAM image encoder -> token-major embeddings [B,4096,256]
+        emb_tokens = self.sam.forward(st["images"])
+        # 2. CLIP tower + projector (once per distinct image; the reference recomputes per conversation)
+        feats = self.clip.forward(st["images_clip"])
+        if plan["conv_index"] is not None:
+            feats = feats.index_select(0, plan["conv_index"]).contiguous()
+        # 3. splice + LLaMA; only the hidden state that predicts [SEG] is normalised and returned
+        embeds, kv_len, seg_row = ops.embed_splice(st["input_ids"], st["mask"], self.llama.embed, feats,
+                                                   image_token=IMAGE_TOKEN_INDEX, seg_token=self.seg_token_idx)
+        T = Tt + feats.shape[1] - 1
+        rows = seg_row if plan["first_conv"] is None else seg_row.index_select(0, plan["first_conv"]).contiguous()
+        hidden = self.llama.forward(embeds, N, T, kv_len, out_rows=rows)      # conversation 0 of each image (LISA.py:400)
+        text_embed = self.selector.text_embed(hidden)                         # [B,256]
+        # 4. selector
+        return self.selector.forward(emb_tokens, st["segs"], text_embed, plan["sel"])
+
+    def _capture(self, plan) -> None:
+        from . import _lib
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):       # warm-up: populates scratch buffers / index maps / func attributes
+            self._run(plan)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            outs = self._run(plan)
+        plan["launches"] = _lib.launch_count() - n0
+        plan["graph"], plan["outputs"] = graph, outs

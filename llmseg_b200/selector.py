@@ -61,23 +61,31 @@ class Selector:
         t = ops.gemm(hidden_rows, self.fc0[0], self.fc0[1], act="relu")
         return ops.gemm(t, self.fc2[0], self.fc2[1])
 
-    def forward(self, emb_tokens: Tensor, segs: List[Tensor], text_embed: Tensor):
-        """emb_tokens [B,4096,256]; segs[i] [K_i,256,256] bf16; text_embed [B,256] (conversation 0 of
-        each image).  -> (sim fp32 [B,Kmax], iou fp32 [B,Kmax], best int32 [B], K list)."""
-        B = emb_tokens.shape[0]
-        Ks = [int(s.shape[0]) for s in segs]
+    def make_plan(self, Ks) -> dict:
+        """Device-side index tensors for a batch with Ks[i] proposals per image (built once per shape,
+        outside any CUDA-graph capture)."""
+        Ks = [int(k) for k in Ks]
         kmax = max(Ks)
         if kmax > 128:
             raise ValueError(f"selector kernels support at most 128 proposals per image, got {kmax}")
-        dev = self.device
-        seg_cat = segs[0] if B == 1 else torch.cat(segs, 0)
+        dev, B = self.device, len(Ks)
         offs = [0]
         for kk in Ks:
             offs.append(offs[-1] + kk)
-        k_off = torch.tensor(offs, dtype=torch.int32, device=dev)
-        b_off = torch.arange(B + 1, dtype=torch.int32, device=dev)
-        mask_image = torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=dev),
-                                             torch.tensor(Ks, device=dev))
+        return {
+            "Ks": Ks, "kmax": kmax, "B": B,
+            "k_off": torch.tensor(offs, dtype=torch.int32, device=dev),
+            "b_off": torch.arange(B + 1, dtype=torch.int32, device=dev),
+            "mask_image": torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=dev),
+                                                  torch.tensor(Ks, device=dev)).contiguous(),
+        }
+
+    def forward(self, emb_tokens: Tensor, seg_cat: Tensor, text_embed: Tensor, plan: dict):
+        """emb_tokens [B,4096,256]; seg_cat [ΣK_i,256,256] bf16 (proposals of all images, concatenated);
+        text_embed [B,256] (conversation 0 of each image); plan from make_plan.
+        -> (sim fp32 [B,Kmax], iou fp32 [B,Kmax], best int32 [B])."""
+        B, kmax = plan["B"], plan["kmax"]
+        k_off, b_off, mask_image = plan["k_off"], plan["b_off"], plan["mask_image"]
         feat = ops.maskpool(seg_cat.contiguous(), emb_tokens.contiguous(), mask_image)
         text = text_embed
         ln = lambda x, n: ops.layernorm(x, n[0], n[1], 1e-5)
@@ -98,5 +106,4 @@ class Selector:
         feat = ln(ops.add_rows_bcast(feat, to, row_group=mask_image), self.n_fin)
         h_iou = ops.gemm(feat, self.w_i1, self.b_i1, act="relu")
         e = ops.gemm(ops.gemm(feat, self.w_e1, self.b_e1, act="relu"), self.w_e2, self.b_e2)
-        sim, iou, best = ops.select(e, text_embed, h_iou, self.w_i2, self.b_i2, k_off, batch=B, k_stride=kmax)
-        return sim, iou, best, Ks
+        return ops.select(e, text_embed, h_iou, self.w_i2, self.b_i2, k_off, batch=B, k_stride=kmax)

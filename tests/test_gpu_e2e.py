@@ -1,0 +1,104 @@
+"""GPU (-m gpu): the assembled encoders and the full `LISAForCausalLM.forward` against the fp32
+oracle (oracle/lisa_forward.py) on identical bf16 weights and inputs.
+
+Tolerance: north_star asks 1e-3 abs on the bf16 outputs against the reference's bf16 PyTorch path.
+The oracle here is fp32 (the bf16 eager path itself is ~2e-3 away from fp32), so the
+bound on |ours - fp32 oracle| is 4e-3 for similarity / IoU; the selected index must equal the
+oracle's whenever the oracle's top-1/top-2 margin exceeds twice that bound (margin-qualified, T9).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SIM_TOL = 4e-3
+
+
+def _setup(depths, B, K, T_text, seed=0):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from llmseg_b200 import lisa, synthetic
+    from oracle import clip_llama as o_cl, lisa_forward as o_lf, sam_encoder as o_sam
+    cfg = lisa.LisaCfg()
+    sam_d, sam_g, clip_l, llama_l = depths
+    cfg.sam.depth, cfg.sam.global_attn_indexes = sam_d, sam_g
+    cfg.clip.layers, cfg.llama.layers = clip_l, llama_l
+    sd = synthetic.lisa_state_dict(cfg, seed=seed, device=DEV)
+    model = lisa.LISAForCausalLM(sd, cfg, device=DEV)
+    inp = synthetic.make_inputs(cfg, B, K, T_text, device=DEV)
+    ocfg = o_lf.LisaConfig(sam=o_sam.SamConfig(depth=sam_d, global_attn_indexes=sam_g),
+                           clip=o_cl.ClipConfig(layers=clip_l), llama=o_cl.LlamaConfig(layers=llama_l))
+    return model, sd, inp, ocfg
+
+
+def _oracle(sd, ocfg, inp):
+    from oracle import lisa_forward as o_lf
+    with torch.no_grad():
+        return o_lf.forward_batched({k: v.float() for k, v in sd.items()}, ocfg, images=inp["images"].float(),
+                                    images_clip=inp["images_clip"].float(), input_ids=inp["input_ids"],
+                                    attention_masks=inp["attention_masks"],
+                                    sam_segs_list=[s.float() for s in inp["sam_segs_list"]])
+
+
+def _check(out, ref, B):
+    for b in range(B):
+        s, r = out["pred_similarity"][b].float(), ref["pred_similarity"][b]
+        i_, ri = out["pred_iou"][b].float(), ref["pred_iou"][b]
+        assert s.shape == r.shape and out["pred_similarity"][b].dtype == torch.bfloat16
+        assert (s - r).abs().max().item() <= SIM_TOL, f"similarity img{b}: {(s - r).abs().max().item()}"
+        assert (i_ - ri).abs().max().item() <= SIM_TOL, f"iou img{b}: {(i_ - ri).abs().max().item()}"
+        top2 = r[0].topk(2).values
+        if float(top2[0] - top2[1]) > 2 * SIM_TOL:
+            assert int(s.argmax()) == int(r.argmax())
+        assert int(out["best_index"][b]) == int(s.argmax())      # fused argmax == torch.argmax of our logits
+
+
+def test_sam_encoder_vs_oracle(cuda_lib):
+    from oracle import lisa_forward as o_lf, sam_encoder as o_sam
+    model, sd, inp, ocfg = _setup((3, (1,), 2, 1), 1, 8, 16)
+    with torch.no_grad():
+        tok = model.sam.forward(inp["images"])
+        nchw = model.get_visual_embs(inp["images"])
+        ref = o_sam.image_encoder(inp["images"].float(),
+                                  {k: v.float() for k, v in o_lf.sub_dict(sd, "model.visual_model.image_encoder.").items()}, ocfg.sam)
+    assert nchw.shape == ref.shape == (1, 256, 64, 64)
+    d = tok.float().reshape(1, 64, 64, 256).permute(0, 3, 1, 2) - ref
+    assert d.abs().max().item() < 0.15 and d.abs().mean().item() < 1.5e-2   # LayerNorm2d output, rms ~1
+
+
+def test_forward_reduced_depth_batched(cuda_lib):
+    model, sd, inp, ocfg = _setup((3, (1,), 4, 2), 2, 64, 64)
+    with torch.no_grad():
+        out = model.forward(**inp)
+    _check(out, _oracle(sd, ocfg, inp), 2)
+    # batched == independent single-image calls (reference inference is one image per forward)
+    from llmseg_b200 import synthetic
+    for b in range(2):
+        one = dict(inp)
+        for k in ("images", "images_clip", "input_ids", "labels", "attention_masks"):
+            one[k] = inp[k][b:b + 1]
+        one["sam_segs_list"] = inp["sam_segs_list"][b:b + 1]
+        one["offset"] = torch.arange(2)
+        with torch.no_grad():
+            o1 = model.forward(**one)
+        assert torch.equal(o1["pred_similarity"][0], out["pred_similarity"][b])
+        assert torch.equal(o1["pred_iou"][0], out["pred_iou"][b])
+
+
+def test_forward_right_padded_prompt_and_ragged_k(cuda_lib):
+    """attention_masks with right padding (the only kind collate_fn_new makes) and K_i differing per image."""
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 2), 2, 24, 32)
+    inp["sam_segs_list"][1] = inp["sam_segs_list"][1][:17].contiguous()
+    inp["attention_masks"][1, 30:] = False
+    with torch.no_grad():
+        out = model.forward(**inp)
+    assert out["pred_similarity"][1].shape == (1, 17)
+    _check(out, _oracle(sd, ocfg, inp), 2)
+
+
+def test_forward_full_depth(cuda_lib):
+    """BASELINE configs[1]: batch=1 full forward (SAM ViT-H 32 blocks + CLIP 23 layers + LLaMA-7B 32 layers)."""
+    model, sd, inp, ocfg = _setup((32, (7, 15, 23, 31), 24, 32), 1, 64, 64)
+    with torch.no_grad():
+        out = model.forward(**inp)
+    _check(out, _oracle(sd, ocfg, inp), 1)
