@@ -33,10 +33,20 @@ def _timeit(fn, reps: int = 1) -> float:
 
 
 def cpu_forward_sample(t_text: int = 64, k_props: int = 64, threads: int | None = None, reps: int = 1) -> Dict:
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
     rn = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    if threads is None:
+        # "all the host threads it can use": eager PyTorch stops scaling (and regresses) well before
+        # 100+ threads, so pick the fastest of {all cores, 64, 32, 16} on one SAM-sized GEMM
+        ncpu = os.cpu_count() or 1
+        a, b = rn(4096, 1280, std=1.0), rn(5120, 1280, std=1.0)
+        best_t, threads = None, ncpu
+        for cand in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
+            torch.set_num_threads(cand)
+            t = _timeit(lambda: a @ b.T, 2)
+            if best_t is None or t < best_t:
+                best_t, threads = t, cand
+    torch.set_num_threads(threads)
     out: Dict = {"cores": threads, "kind": "port"}
     parts = {}
     with torch.no_grad():
