@@ -1,15 +1,15 @@
 // llmseg_b200 — fused flash-style attention for sm_100a:  O = softmax(scale·[q|qext]·[k|kext]ᵀ + mask)·V
 //
-// One CTA = one (batch·head, 128-query tile); 192 threads, two CTAs co-resident per SM so one
+// One CTA = one (batch·head, 128-query tile); 320 threads, two CTAs co-resident per SM so one
 // CTA's softmax overlaps the other's tensor-core work.
 //   warp 0      TMA producer: Q tile once, then K tile and Vᵀ tile per 128-key step (single buffers
 //               with separate full/empty barriers: K(j+1) streams in under softmax(j)+PV(j))
 //   warp 1      TMEM allocator + MMA issuer (one lane):
 //                 S(128×128 fp32, TMEM cols 0..127)   = Q·Kᵀ   tcgen05.mma SS, K-major operands
 //                 O(128×HD  fp32, TMEM cols 128..)   += P·V    tcgen05.mma TS: P is read from TMEM
-//   warps 2..5  softmax: thread = query row (tcgen05.ld 32x32b).  Two passes over S in TMEM
-//               (row max, then exp2 → bf16 P written back over the first 64 columns of S), lazy
-//               rescale of O (only when the running max grew by > 2^8), final O/l → HBM.
+//   warps 2..9  softmax: thread = (query row, 64-key half) (tcgen05.ld 32x32b).  Two passes over S in
+//               TMEM (row max, then exp2 → bf16 P written back over S), lazy rescale of O (only when
+//               the running max grew by > 2^8), final O/l → HBM.
 // S never reaches shared or global memory; HBM traffic is Q, K, V, O only.
 //
 // Decomposed rel-pos (reference image_encoder.py:354-392) enters through the extended reduction
@@ -42,7 +42,8 @@ struct ACfg {
   static constexpr int OFF_K1 = OFF_K0 + Q0_BYTES;
   static constexpr int OFF_V = OFF_K1 + Q1_BYTES;
   static constexpr int OFF_BAR = OFF_V + 2 * V_CHUNK;
-  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int OFF_XCH = OFF_BAR + 128;                 // float[2][2][128] row-max exchange + float[2][128] row sums
+  static constexpr int SMEM_BYTES = OFF_XCH + 3072 + 1024;
   static constexpr int Q_TX = Q0_BYTES + Q1_BYTES + QX_BYTES + E_BYTES;
   static constexpr int K_TX = Q0_BYTES + Q1_BYTES;
   static constexpr int V_TX = 2 * V_CHUNK;
@@ -67,7 +68,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 template <int HD, int EXT>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
             const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
@@ -103,7 +104,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
     tma_prefetch_desc(&tmKa);
     tma_prefetch_desc(&tmV);
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -190,8 +191,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
         mbar_wait(v_full, ph);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tO, tS + k * 8,
+        for (int k = 0; k < 8; ++k)  // P(keys 0..63) sits at S columns [0,32), P(keys 64..127) at [64,96)
+          umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8,
                   umma_smem_desc(sV + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128),
                   idesc_o, (j | k) != 0);
         umma_commit(v_empty);
@@ -200,11 +201,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
     }
   } else {
     // ================================ softmax / correction / epilogue ================================
+    // 8 warps: two per TMEM lane quarter; warp "half" h owns score columns [64h, 64h+64) of its 32 rows
+    // and a share of the O columns.  Row maxima / sums are exchanged through shared memory.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     const int q_row = q0 + row_in_tile;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t tS_mine = t_row + half * 64;
     const uint32_t tO = t_row + C::O_COL;
+    float* xmax = reinterpret_cast<float*>(smem + C::OFF_XCH);        // [2 parity][2 half][128]
+    float* xsum = xmax + 512;                                          // [2 half][128]
+    constexpr int O_CHUNKS = HD / 16;
+    const int oc0 = half == 0 ? 0 : (O_CHUNKS + 1) / 2;
+    const int oc1 = half == 0 ? (O_CHUNKS + 1) / 2 : O_CHUNKS;
     const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;  // key valid iff key < lim
     const bf16* rb = nullptr;
     if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
@@ -213,25 +223,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
 
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
-      const int key0 = j * BN;
-      float add0 = 0.f, add1 = 0.f;
-      if (EXT == 2) {
-        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(rb + 2 * j);
-        add0 = __low2float(v2) * LOG2E;
-        add1 = __high2float(v2) * LOG2E;
-      }
-      const bool need_mask = (key0 + BN > kv_limit) || (p.causal && key0 + BN - 1 > q0);
+      const int key0 = j * BN + half * 64;
+      float add = 0.f;
+      if (EXT == 2) add = __bfloat162float(rb[2 * j + half]) * LOG2E;
+      const bool need_mask = (key0 + 64 > kv_limit) || (p.causal && key0 + 63 > q0);
       mbar_wait(bar_s, ph);
       tc_fence_after();
 
-      // ---- pass 1: row max ----
+      // ---- pass 1: row max over this warp's 64 columns ----
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
+        tmem_ld32(tS_mine + c * 32, r);
         tmem_ld_wait();
-        const float add = c < 2 ? add0 : add1;
         if (need_mask) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -242,20 +247,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
           float mc = -INFINITY;
 #pragma unroll
           for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
-          // c1 > 0: max commutes with the affine map
-          mx = fmaxf(mx, fmaf(mc, c1, add));
+          mx = fmaxf(mx, fmaf(mc, c1, add));  // c1 > 0: max commutes with the affine map
         }
       }
+      xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
       const float m_new = fmaxf(m, mx);
 
-      // ---- lazy O rescale ----
+      // ---- lazy O rescale (both halves take the same decision: they see the same m, m_new) ----
       if (j == 0) {
         m = m_new;
       } else if (__any_sync(0xffffffffu, m_new > m + 8.0f)) {
         float f = ex2(m - m_new);
         if (m_new == -INFINITY) f = 1.f;
 #pragma unroll 1
-        for (int c = 0; c < HD / 16; ++c) {
+        for (int c = oc0; c < oc1; ++c) {
           uint32_t r[16];
           tmem_ld16(tO + c * 16, r);
           tmem_ld_wait();
@@ -268,19 +275,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
       }
       const float m_use = (m == -INFINITY) ? 0.f : m;
 
-      // ---- pass 2: P = exp2(t - m), written as packed bf16 over S columns [0,64) ----
+      // ---- pass 2: P = exp2(t - m) as packed bf16 over the first 32 columns of this warp's S half ----
       float lsum = 0.f;
+      const float addm = add - m_use;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
+        tmem_ld32(tS_mine + c * 32, r);
         tmem_ld_wait();
-        const float add = (c < 2 ? add0 : add1) - m_use;
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float t0 = fmaf(__uint_as_float(r[e]), c1, add);
-          float t1 = fmaf(__uint_as_float(r[e + 1]), c1, add);
+          float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
+          float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
           if (need_mask) {
             if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
             if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
@@ -289,7 +296,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
           lsum += p0 + p1;
           pk[e >> 1] = pack_bf16(p0, p1);
         }
-        tmem_st16(t_row + c * 16, pk);
+        tmem_st16(tS_mine + c * 16, pk);
       }
       l += lsum;
       tmem_st_wait();
@@ -302,11 +309,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
       mbar_wait(bar_s, n_tiles & 1);
       tc_fence_after();
     }
+    xsum[half * 128 + row_in_tile] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xsum[(half ^ 1) * 128 + row_in_tile];
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const int h = bh - b * p.heads;
     bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
 #pragma unroll 1
-    for (int c = 0; c < HD / 16; ++c) {
+    for (int c = oc0; c < oc1; ++c) {
       uint32_t r[16];
       if (n_tiles > 0) {
         tmem_ld16(tO + c * 16, r);
@@ -395,7 +405,7 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid((p->seq + BM - 1) / BM, BH);
-  kern<<<grid, 192, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
+  kern<<<grid, 320, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -4,7 +4,8 @@
 //   warp 1 (1 lane)  MMA issuer:   tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 ×4 per stage,
 //                                  fp32 accumulators in TMEM, double-buffered (2×BN columns)
 //   warp 2           TMEM allocator
-//   warps 4..7       epilogue: tcgen05.ld 32 lanes × 32 columns → bias / act / residual / layout → HBM
+//   warps 4..11      epilogue (2 per TMEM lane quarter): tcgen05.ld 32 lanes × 32 columns → bias / act /
+//                    residual / layout → HBM
 //
 // The epilogue variants replace the reference's separate elementwise passes:
 //   PLAIN   bias + {GELU, quick-GELU, ReLU} + residual (+ row scatter for window un-partition,
@@ -13,6 +14,7 @@
 //   QKV     split into per-head Q, K, Vᵀ (reference image_encoder.py:238-242) with optional
 //           rotate-half RoPE on q,k (transformers LlamaAttention.apply_rotary_pos_emb)
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -47,6 +49,8 @@ struct GemmDev {
   float rp_inv_scale;
   bf16* rp_qext;
   bf16* rp_rh;
+  int cluster;    // CTAs per cluster along M (1, 2 or 4)
+  int n_fastest;  // work-item order (see kernel)
 };
 
 constexpr int MODE_RELPOS = 3;
@@ -60,9 +64,36 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the bf16 rounding that follows):
+// 2 MUFU + ~10 FMA/ALU instead of libdevice erff's ~30 instructions — the GELU epilogue of the SAM
+// MLP GEMM was epilogue-bound with erff (ncu: profiles/r01_ncu_summary.md).
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = fast_ex2(-1.4426950408889634f * ax * ax);
+  return copysignf(fmaf(-poly, e, 1.0f), x);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == LLMSEG_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-  if (act == LLMSEG_ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));
+  if (act == LLMSEG_ACT_GELU) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+  if (act == LLMSEG_ACT_QUICK_GELU) return x * fast_sigmoid(1.702f * x);
   if (act == LLMSEG_ACT_RELU) return fmaxf(x, 0.0f);
   return x;
 }
@@ -127,7 +158,7 @@ __device__ __forceinline__ void epi_swiglu(const GemmDev& p, const uint32_t* r, 
     for (int e = 0; e < 8; ++e) {
       const float g = bf16_round(__uint_as_float(r[j + 2 * e]));
       const float u = bf16_round(__uint_as_float(r[j + 2 * e + 1]));
-      const float a = bf16_round(g / (1.0f + __expf(-g)));
+      const float a = bf16_round(g * fast_sigmoid(g));
       o[e] = a * u;
     }
     uint4 w;
@@ -270,7 +301,7 @@ __device__ __forceinline__ void epi_qkv_rope(const GemmDev& p, const uint32_t* l
 }
 
 template <int BN, int MODE, bool ROPE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmDev p) {
   using C = Cfg<BN>;
@@ -290,39 +321,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
+  // Thread-block cluster of `cl` CTAs along M: the CTAs of a cluster work on `cl` vertically adjacent
+  // output tiles that share the same W tile; each CTA TMA-loads 1/cl of it and multicasts the slice to
+  // every CTA of the cluster, cutting L2->SM operand traffic from (BM+BN) to (BM+BN/cl) rows per k-block.
+  const int cl = p.cluster;
+  const int cta_rank = cl > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], cl);  // one tcgen05.commit arrival from every CTA that reads the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // work items are groups of `cl` M-tiles x one N-tile, M-groups fastest; cluster c takes groups
+  // c, c + num_clusters, ...  (all CTAs of a cluster iterate the same groups in lockstep)
+  // group order keeps the smaller operand L2-resident: N fastest when A is the big (streamed-once)
+  // operand (SAM: M >> N), M fastest when the weights are (LLaMA: N >> M).
+  const int m_groups = (p.num_m_tiles + cl - 1) / cl;
+  const int num_groups = m_groups * p.num_n_tiles;
+  const bool n_fastest = p.n_fastest != 0;
+  const int cluster_id = blockIdx.x / cl;
+  const int num_clusters = gridDim.x / cl;
+  const int slice_rows = BN / cl;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_tiles;
-        const int n_blk = tile / p.num_m_tiles;
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * cl + cta_rank;
+        const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          if (cl == 1) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+            tma_load_2d_mcast(sb + cta_rank * slice_rows * 128, &tmB, &full_bar[stage], kb * BK,
+                              n_blk * BN + cta_rank * slice_rows, cl_mask);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -337,7 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -352,7 +404,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
             umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (cl == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], cl_mask);  // frees the slot in every CTA of the cluster
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
           if (++stage == C::STAGES) {
             stage = 0;
@@ -366,12 +419,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
+    // 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's columns
     const int quarter = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_tiles;
-      const int n_blk = tile / p.num_m_tiles;
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * cl + cta_rank;
+      const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
@@ -383,8 +438,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (MODE == LLMSEG_GEMM_QKV && ROPE) {
 #pragma unroll 1
         for (int c = 0; c < BN / 128; ++c) {
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          {
+            const int half = chalf;
             uint32_t lo[32], hi[32];
             tmem_ld32(taddr + c * 128 + half * 32, lo);
             tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
@@ -395,7 +450,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -419,6 +474,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -435,10 +491,43 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int
                                      Cfg<BN>::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, 256, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, d);
-  LLMSEG_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = d.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, d));
   g_launches.fetch_add(1);
   return 0;
+}
+
+// cluster size along M for a problem with `m_tiles` row tiles: share the W tile between up to 4 CTAs.
+// LLMSEG_GEMM_CLUSTER=1|2|4 overrides (tuning / debugging).
+int pick_cluster(int m_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("LLMSEG_GEMM_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  int cl = m_tiles >= 8 ? 4 : (m_tiles >= 2 ? 2 : 1);
+  if (forced == 1 || forced == 2 || forced == 4) cl = forced < cl ? forced : cl;
+  return cl;
+}
+
+// persistent grid: as many whole clusters as fit the machine (<= one CTA per SM), never more than the work
+int pick_grid(int groups, int cl, int sms) {
+  int clusters = sms / cl;
+  if (cl == 4) clusters = clusters > 33 ? 33 : clusters;  // 4-CTA clusters strand a few SMs (GPC packing)
+  if (clusters > groups) clusters = groups;
+  if (clusters < 1) clusters = 1;
+  return clusters * cl;
 }
 
 int num_sms() {
@@ -516,8 +605,9 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   d.num_m_tiles = m_tiles;
   d.num_n_tiles = (p->N + bn - 1) / bn;
   d.num_k_blocks = (p->K + BK - 1) / BK;
-  const int tiles = d.num_m_tiles * d.num_n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
+  d.cluster = pick_cluster(m_tiles);
+  d.n_fastest = p->M > p->N ? 1 : 0;
+  const int grid = pick_grid(((m_tiles + d.cluster - 1) / d.cluster) * d.num_n_tiles, d.cluster, sms);
 
   CUtensorMap tmA, tmB;
   {
@@ -529,7 +619,7 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     uint64_t str[1] = {(uint64_t)p->ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
+    uint32_t box[2] = {BK, (uint32_t)(bn / d.cluster)};  // each CTA loads (and multicasts) 1/cluster of the W tile
     if (int e = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, 128)) return e;
   }
 
@@ -573,8 +663,9 @@ extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, 
   d.num_m_tiles = (d.M + BM - 1) / BM;
   d.num_n_tiles = (d.N + bn - 1) / bn;
   d.num_k_blocks = (d.K + BK - 1) / BK;
-  const int tiles = d.num_m_tiles * d.num_n_tiles;
-  const int grid_x = tiles < sms ? tiles : sms;
+  d.cluster = pick_cluster(d.num_m_tiles);
+  d.n_fastest = 1;
+  const int grid_x = pick_grid(((d.num_m_tiles + d.cluster - 1) / d.cluster) * d.num_n_tiles, d.cluster, sms);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)head_dim, (uint64_t)d.M};
@@ -585,7 +676,7 @@ extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, 
   {
     uint64_t dims[2] = {(uint64_t)head_dim, (uint64_t)n_pad};
     uint64_t str[1] = {(uint64_t)head_dim * 2};
-    uint32_t box[2] = {BK, (uint32_t)bn};
+    uint32_t box[2] = {BK, (uint32_t)(bn / d.cluster)};
     if (int e = make_tmap_bf16(&tmB, rel_hw, 2, dims, str, box, 128)) return e;
   }
   return launch<128, MODE_RELPOS, false>(tmA, tmB, d, grid_x, stream);
