@@ -230,73 +230,92 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
       mbar_wait(bar_s, ph);
       tc_fence_after();
 
-      // ---- pass 1: row max over this warp's 64 columns ----
-      float mx = -INFINITY;
-#pragma unroll 1
+      // ---- single pass (fast path): P = exp2(t - m) against the RUNNING max m while tracking this
+      //      tile's max; S is read from TMEM once (the TMEM->RF path is the scarce resource here,
+      //      profiles/r01a_ncu_summary.md).  Only when some row's max grew by more than 2^8 — always on
+      //      the first tile, rarely afterwards — the slow path below rescales O and recomputes P. ----
+      float mx = -INFINITY, lsum = 0.f;
+      uint32_t pk[32];
+      const float m_fast = (m == -INFINITY) ? 0.f : m;
+      const float addm_fast = add - m_fast;
+#pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld32(tS_mine + c * 32, r);
         tmem_ld_wait();
-        if (need_mask) {
+        if (j == 0) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const float t = fmaf(__uint_as_float(r[e]), c1, add);
-            mx = fmaxf(mx, (key0 + c * 32 + e < lim) ? t : -INFINITY);
+            float t = fmaf(__uint_as_float(r[e]), c1, add);
+            if (need_mask && key0 + c * 32 + e >= lim) t = -INFINITY;
+            mx = fmaxf(mx, t);
           }
         } else {
-          float mc = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
-          mx = fmaxf(mx, fmaf(mc, c1, add));  // c1 > 0: max commutes with the affine map
+          for (int e = 0; e < 32; e += 2) {
+            float t0 = fmaf(__uint_as_float(r[e]), c1, addm_fast);
+            float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm_fast);
+            if (need_mask) {
+              if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
+              if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+            }
+            mx = fmaxf(mx, fmaxf(t0, t1));
+            const float p0 = ex2(t0), p1 = ex2(t1);
+            lsum += p0 + p1;
+            pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
+          }
         }
       }
+      if (j > 0) mx += m_fast;  // back to absolute (log2-domain) units
       xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
       const float m_new = fmaxf(m, mx);
 
-      // ---- lazy O rescale (both halves take the same decision: they see the same m, m_new) ----
-      if (j == 0) {
-        m = m_new;
-      } else if (__any_sync(0xffffffffu, m_new > m + 8.0f)) {
-        float f = ex2(m - m_new);
-        if (m_new == -INFINITY) f = 1.f;
+      // both halves of a row quarter see identical (m, m_new) and therefore take the same branch
+      if (__any_sync(0xffffffffu, m_new > m + 8.0f)) {
+        // ---- slow path: adopt the new max, rescale O and l, recompute P from S ----
+        if (j > 0) {
+          float f = ex2(m - m_new);
+          if (m_new == -INFINITY) f = 1.f;
 #pragma unroll 1
-        for (int c = oc0; c < oc1; ++c) {
-          uint32_t r[16];
-          tmem_ld16(tO + c * 16, r);
-          tmem_ld_wait();
+          for (int c = oc0; c < oc1; ++c) {
+            uint32_t r[16];
+            tmem_ld16(tO + c * 16, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
-          tmem_st16(tO + c * 16, r);
-        }
-        l *= f;
-        m = m_new;
-      }
-      const float m_use = (m == -INFINITY) ? 0.f : m;
-
-      // ---- pass 2: P = exp2(t - m) as packed bf16 over the first 32 columns of this warp's S half ----
-      float lsum = 0.f;
-      const float addm = add - m_use;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS_mine + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
-          float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
-          if (need_mask) {
-            if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
-            if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
+            tmem_st16(tO + c * 16, r);
           }
-          const float p0 = ex2(t0), p1 = ex2(t1);
-          lsum += p0 + p1;
-          pk[e >> 1] = pack_bf16(p0, p1);
+          l *= f;
         }
-        tmem_st16(tS_mine + c * 16, pk);
+        m = m_new;
+        const float m_use = (m == -INFINITY) ? 0.f : m;
+        const float addm = add - m_use;
+        lsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tS_mine + c * 32, r);
+          tmem_ld_wait();
+          uint32_t pq[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
+            float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
+            if (need_mask) {
+              if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
+              if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+            }
+            const float p0 = ex2(t0), p1 = ex2(t1);
+            lsum += p0 + p1;
+            pq[e >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(tS_mine + c * 16, pq);
+        }
+      } else {
+        tmem_st16(tS_mine, pk);
+        tmem_st16(tS_mine + 16, pk + 16);
       }
       l += lsum;
       tmem_st_wait();

@@ -516,8 +516,11 @@ int pick_cluster(int m_tiles) {
     const char* e = getenv("LLMSEG_GEMM_CLUSTER");
     forced = e ? atoi(e) : 0;
   }
-  int cl = m_tiles >= 8 ? 4 : (m_tiles >= 2 ? 2 : 1);
-  if (forced == 1 || forced == 2 || forced == 4) cl = forced < cl ? forced : cl;
+  // measured on B200 (profiles/r01b_gemm_cluster.md): pairs give +3..7 % on M >= 4096, 4-CTA clusters
+  // lose it again (stranded SMs), and an odd tile count wastes a whole CTA-tile per group on small M.
+  int cl = (m_tiles >= 2 && (m_tiles % 2 == 0 || m_tiles >= 16)) ? 2 : 1;
+  if (forced == 1) cl = 1;
+  if ((forced == 2 || forced == 4) && m_tiles >= forced) cl = forced;
   return cl;
 }
 
