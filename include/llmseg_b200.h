@@ -123,8 +123,10 @@ int llmseg_attention(const llmseg_attn_params* p, void* stream);
  * epilogue), scattered into qext (and row_bias for the global case) as described above.
  * Replaces get_rel_pos + the two einsums of add_decomposed_rel_pos (image_encoder.py:321-392);
  * q is the UNSCALED query, values are rounded to bf16 like the reference's einsum outputs.
- *   q      bf16 [bh, seq_pad, head_dim]      rel_hw bf16 [n_pad >= 2*(2*grid-1), head_dim]
- *          (rows 0..2g-2 = rel_pos_h, rows 2g-1..4g-3 = rel_pos_w, rest zero; n_pad % 8 == 0)
+ *   q      bf16 [bh, seq_pad, head_dim]
+ *   rel_hw bf16 [n_pad, head_dim], zero padded:
+ *            grid 14 (windows): n_pad 64,  rows [0,27)  = rel_pos_h, rows [32,59)   = rel_pos_w
+ *            grid 64 (global) : n_pad 256, rows [0,127) = rel_pos_h, rows [128,255) = rel_pos_w
  *   seq == grid*grid; grid == 14 -> ext_cols 32, row_bias NULL; grid == 64 -> ext_cols 64 + row_bias */
 int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int seq, int seq_pad,
                        int head_dim, int grid, float inv_scale, void* qext, int ext_cols,

@@ -62,6 +62,10 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // rel-pos mode: K <= 128 needs only 2 stages; 4 x 16 KB fp32 staging tiles (one per TMEM lane quarter)
+  static constexpr int RP_STAGES = 2;
+  static constexpr int RP_STAGING = 4 * 128 * 32 * 4;
+  static constexpr int RP_SMEM_BYTES = RP_STAGES * STAGE_BYTES + RP_STAGING + 1024 + 256;
 };
 
 __device__ __forceinline__ float fast_ex2(float x) {
@@ -215,31 +219,72 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
 }
 
 // ---- rel-pos gather: QR[row, i] -> qext / row_bias (see include/llmseg_b200.h) --------------
-__device__ __forceinline__ void epi_relpos(const GemmDev& p, const uint32_t* r, int row, int n0) {
+// The QR tile (128 table columns) of the warp pair that shares a TMEM lane quarter is staged in shared
+// memory as stage[col][lane] (fp32, conflict-free both ways); every thread then assembles its own
+// output row with a per-row dynamic column index and writes it with 16-byte stores, so a warp writes
+// one contiguous 2-4 KB block instead of 32-way scattered 2-byte stores.
+//   table layout (ops.make_rel_hw): windows  rel_h rows [0,2G-1), rel_w rows [32,32+2G-1)   (1 N-tile)
+//                                   global   rel_h rows [0,127),  rel_w rows [128,255)       (2 N-tiles)
+__device__ __forceinline__ void relpos_tile(const GemmDev& p, float* stage, uint32_t taddr, int row,
+                                            int n_blk, int quarter, int chalf, int lane, bool row_ok) {
+  // 1. stage this warp's 64 accumulator columns (rounded to bf16 like the reference's einsum output)
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + chalf * 64 + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      stage[(chalf * 64 + c * 32 + e) * 32 + lane] = bf16_round(__uint_as_float(r[e]));
+  }
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+  // 2. assemble + store
   const int s = row % p.rp_seq_pad;
-  if (s >= p.rp_seq) return;
+  const bool live = row_ok && s < p.rp_seq;
   const int G = p.rp_grid;
   const int qh = s / G, qw = s - qh * G;
-  const int T = 2 * G - 1;
+  if (p.rp_rh == nullptr) {
+    // windows: out[j<G] = QR[qh+G-1-j], out[G+j] = QR[32+qw+G-1-j], j<G; 16 outputs per warp half
+    const int j0 = chalf * 16;
+    float v[16];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const int col = n0 + e;
-    if (col >= 2 * T) break;
-    const float v = bf16_round(__uint_as_float(r[e]));
-    if (col < T) {
-      const int kh = qh + G - 1 - col;
-      if (kh >= 0 && kh < G) {
-        if (p.rp_rh) p.rp_rh[(size_t)row * 64 + kh] = __float2bfloat16_rn(v);
-        else p.rp_qext[(size_t)row * p.rp_ext + kh] = __float2bfloat16_rn(v * p.rp_inv_scale);
+    for (int t = 0; t < 16; ++t) {
+      const int j = j0 + t;
+      float x = 0.f;
+      if (j < G) x = stage[(qh + G - 1 - j) * 32 + lane];
+      else if (j < 2 * G) x = stage[(32 + qw + 2 * G - 1 - j) * 32 + lane];
+      v[t] = x * p.rp_inv_scale;
+    }
+    if (live) {
+      uint4 o0, o1;
+      o0.x = pack_bf16(v[0], v[1]); o0.y = pack_bf16(v[2], v[3]); o0.z = pack_bf16(v[4], v[5]); o0.w = pack_bf16(v[6], v[7]);
+      o1.x = pack_bf16(v[8], v[9]); o1.y = pack_bf16(v[10], v[11]); o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
+      uint4* dst = reinterpret_cast<uint4*>(p.rp_qext + (size_t)row * 32 + j0);
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+  } else {
+    // global: N-tile 0 -> row_bias[kh] = QR[qh+63-kh]; N-tile 1 -> qext[kw] = QR[qw+63-kw]/scale
+    const int pos = n_blk == 0 ? qh : qw;
+    const float sc = n_blk == 0 ? 1.0f : p.rp_inv_scale;
+    bf16* dstp = (n_blk == 0 ? p.rp_rh : p.rp_qext) + (size_t)row * 64 + chalf * 32;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int j = chalf * 32 + g8 * 8 + t;
+        const int col = pos + G - 1 - j;
+        v[t] = (col >= 0 && col < 128 ? stage[col * 32 + lane] : 0.f) * sc;
       }
-    } else {
-      const int kw = qw + G - 1 - (col - T);
-      if (kw >= 0 && kw < G) {
-        const int dst = p.rp_rh ? kw : G + kw;
-        p.rp_qext[(size_t)row * p.rp_ext + dst] = __float2bfloat16_rn(v * p.rp_inv_scale);
+      if (live) {
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        reinterpret_cast<uint4*>(dstp)[g8] = o;
       }
     }
   }
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");  // staging buffer is reused by the next tile
 }
 
 // ---- QKV split with rotate-half RoPE, head_dim == 128: lo/hi are columns [d0,d0+32) and
@@ -308,9 +353,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full = empty_bar + C::STAGES;
+  constexpr int NST = MODE == MODE_RELPOS ? C::RP_STAGES : C::STAGES;
+  float* rp_stage = reinterpret_cast<float*>(smem + NST * C::STAGE_BYTES);  // RELPOS only
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NST * C::STAGE_BYTES +
+                                                   (MODE == MODE_RELPOS ? C::RP_STAGING : 0));
+  uint64_t* empty_bar = full_bar + NST;
+  uint64_t* tmem_full = empty_bar + NST;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -328,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int cta_rank = cl > 1 ? (int)cluster_ctarank() : 0;
   const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], cl);  // one tcgen05.commit arrival from every CTA that reads the slot
     }
@@ -375,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d_mcast(sb + cta_rank * slice_rows * 128, &tmB, &full_bar[stage], kb * BK,
                               n_blk * BN + cta_rank * slice_rows, cl_mask);
           }
-          if (++stage == C::STAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
@@ -407,7 +455,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (cl == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mcast(&empty_bar[stage], cl_mask);  // frees the slot in every CTA of the cluster
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
-          if (++stage == C::STAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
@@ -435,7 +483,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (MODE == LLMSEG_GEMM_PLAIN && p.out_row_map != nullptr && row < p.M)
         out_row = p.out_row_map[row];
       const bool live = row < p.M && out_row >= 0;
-      if (MODE == LLMSEG_GEMM_QKV && ROPE) {
+      if (MODE == MODE_RELPOS) {
+        relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
+      } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
 #pragma unroll 1
         for (int c = 0; c < BN / 128; ++c) {
           {
@@ -458,7 +508,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (live && n0 < p.N) {
             if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0);
             else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
-            else if (MODE == MODE_RELPOS) epi_relpos(p, r, row, n0);
             else epi_qkv(p, r, row, n0);
           }
         }
@@ -485,16 +534,16 @@ template <int BN, int MODE, bool ROPE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int grid,
            cudaStream_t stream) {
   auto kern = gemm_kernel<BN, MODE, ROPE>;
+  constexpr int smem_bytes = MODE == MODE_RELPOS ? Cfg<BN>::RP_SMEM_BYTES : Cfg<BN>::SMEM_BYTES;
   static bool attr_done = false;  // idempotent; a race only repeats the call
   if (!attr_done) {
-    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<BN>::SMEM_BYTES));
+    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -649,9 +698,9 @@ extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, 
   if (int e = check_arch()) return e;
   LLMSEG_REQUIRE(q && rel_hw && qext, LLMSEG_EARG, "llmseg_relpos_prep: null pointer");
   LLMSEG_REQUIRE(grid > 0 && seq == grid * grid && seq_pad >= seq && head_dim % 8 == 0 &&
-                     n_pad % 8 == 0 && n_pad >= 2 * (2 * grid - 1),
-                 LLMSEG_ESHAPE, "llmseg_relpos_prep: grid=%d seq=%d seq_pad=%d n_pad=%d", grid, seq,
-                 seq_pad, n_pad);
+                     head_dim <= 128 && n_pad == (row_bias ? 256 : 64),
+                 LLMSEG_ESHAPE, "llmseg_relpos_prep: grid=%d seq=%d seq_pad=%d head_dim=%d n_pad=%d", grid,
+                 seq, seq_pad, head_dim, n_pad);
   LLMSEG_REQUIRE((row_bias == nullptr && ext_cols == 32 && 2 * grid <= 32) ||
                      (row_bias != nullptr && ext_cols == 64 && grid <= 64),
                  LLMSEG_ESHAPE, "llmseg_relpos_prep: ext_cols=%d inconsistent with grid=%d", ext_cols, grid);

@@ -18,7 +18,9 @@ namespace {
 
 constexpr int MAX_VEC = 16;  // 16 * 32 lanes * 8 elems = 4096 max dim
 
-template <bool RMS>
+// NV = 16-byte vectors held per lane (1,2,4,8,16): sized to the row so narrow rows keep few registers
+// and many warps (= many loads) in flight per SM.
+template <bool RMS, int NV>
 __global__ void __launch_bounds__(256)
 norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
             const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int rows, int dim, float eps,
@@ -35,10 +37,10 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
     return;
   }
   const uint4* irow = reinterpret_cast<const uint4*>(in + (size_t)src * ld_in);
-  uint4 v[MAX_VEC];
+  uint4 v[NV];
   float s = 0.f, ss = 0.f;
 #pragma unroll
-  for (int t = 0; t < MAX_VEC; ++t) {
+  for (int t = 0; t < NV; ++t) {
     const int i = lane + t * 32;
     if (i < nvec) {
       v[t] = __ldg(irow + i);
@@ -62,7 +64,7 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
     // two-pass variance from registers for accuracy (the row is already resident)
     float sq = 0.f;
 #pragma unroll
-    for (int t = 0; t < MAX_VEC; ++t) {
+    for (int t = 0; t < NV; ++t) {
       const int i = lane + t * 32;
       if (i < nvec) {
         const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
@@ -80,7 +82,7 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
   const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
   const uint4* b4 = reinterpret_cast<const uint4*>(beta);
 #pragma unroll
-  for (int t = 0; t < MAX_VEC; ++t) {
+  for (int t = 0; t < NV; ++t) {
     const int i = lane + t * 32;
     if (i < nvec) {
       const uint4 g = __ldg(g4 + i);
@@ -122,9 +124,17 @@ int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* ga
                  LLMSEG_EALIGN, "norm: pointers / leading dims must be 16-byte aligned");
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  norm_kernel<RMS><<<blocks, warps_per_block * 32, 0, stream>>>(
-      static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out,
-      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), rows, dim, eps, src_map);
+  const int per_lane = (dim / 8 + 31) / 32;
+#define LLMSEG_NORM_LAUNCH(NV_)                                                              \
+  norm_kernel<RMS, NV_><<<blocks, warps_per_block * 32, 0, stream>>>(                        \
+      static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out,                  \
+      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), rows, dim, eps, src_map)
+  if (per_lane <= 1) LLMSEG_NORM_LAUNCH(1);
+  else if (per_lane <= 2) LLMSEG_NORM_LAUNCH(2);
+  else if (per_lane <= 4) LLMSEG_NORM_LAUNCH(4);
+  else if (per_lane <= 8) LLMSEG_NORM_LAUNCH(8);
+  else LLMSEG_NORM_LAUNCH(16);
+#undef LLMSEG_NORM_LAUNCH
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -134,10 +134,15 @@ def make_kext(grid: int, device) -> torch.Tensor:
 def make_rel_hw(rel_h: torch.Tensor, rel_w: torch.Tensor) -> torch.Tensor:
     """Stack rel_pos_h / rel_pos_w ([2g-1, hd] each) into the zero-padded table relpos_prep reads."""
     t = rel_h.shape[0]
-    n_pad = (2 * t + 7) // 8 * 8
+    if t == 27:      # 14x14 windows: one 128-column GEMM tile, rel_w at row 32
+        n_pad, w0 = 64, 32
+    elif t == 127:   # 64x64 global: rel_h -> N-tile 0, rel_w -> N-tile 1
+        n_pad, w0 = 256, 128
+    else:
+        raise ValueError(f"rel-pos tables must have 27 (window 14) or 127 (grid 64) rows, got {t}")
     out = torch.zeros(n_pad, rel_h.shape[1], dtype=torch.bfloat16, device=rel_h.device)
     out[:t] = rel_h
-    out[t:2 * t] = rel_w
+    out[w0:w0 + t] = rel_w
     return out
 
 
