@@ -67,6 +67,89 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ---- softmax building blocks (thread = one query row x 64 keys).  MASK is a template parameter and the
+// callers branch on it explicitly: when the compiler if-converts a runtime mask test it executes the
+// index/compare/select instructions for every element of every tile (measured: 2x the instruction count
+// on the unmasked SAM-global tiles), and instruction issue is the limiter of this kernel. ----
+template <bool MASK>
+__device__ __forceinline__ float softmax_row_max(uint32_t t_s, float c1, float add, int key0, int lim) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_s + c * 32, r);
+    tmem_ld_wait();
+    if (MASK) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float t = fmaf(__uint_as_float(r[e]), c1, add);
+        mx = fmaxf(mx, (key0 + c * 32 + e < lim) ? t : -INFINITY);
+      }
+    } else {
+      float mc = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
+      mx = fmaxf(mx, fmaf(mc, c1, add));  // c1 > 0: max commutes with the affine map
+    }
+  }
+  return mx;
+}
+
+// P = exp2(s*c1 + addm) for this thread's 64 keys, packed bf16 into pk[32]; returns the max exponent
+// argument (relative to the reference max folded into addm) and accumulates the row sum.
+template <bool MASK>
+__device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float addm, int key0, int lim,
+                                                  float& lsum, uint32_t* pk) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_s + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
+      float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
+      if (MASK) {
+        if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
+        if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+      }
+      mx = fmaxf(mx, fmaxf(t0, t1));
+      const float p0 = ex2(t0), p1 = ex2(t1);
+      lsum += p0 + p1;
+      pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
+    }
+  }
+  return mx;
+}
+
+// slow path: recompute P against a new max and store it straight to TMEM
+template <bool MASK>
+__device__ __forceinline__ float softmax_exp_store(uint32_t t_s, float c1, float addm, int key0, int lim) {
+  float lsum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_s + c * 32, r);
+    tmem_ld_wait();
+    uint32_t pq[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
+      float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
+      if (MASK) {
+        if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
+        if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+      }
+      const float p0 = ex2(t0), p1 = ex2(t1);
+      lsum += p0 + p1;
+      pq[e >> 1] = pack_bf16(p0, p1);
+    }
+    tmem_st16(t_s + c * 16, pq);
+  }
+  return lsum;
+}
+
 template <int HD, int EXT>
 __global__ void __launch_bounds__(320, 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
@@ -231,50 +314,26 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
       tc_fence_after();
 
       // ---- single pass (fast path): P = exp2(t - m) against the RUNNING max m while tracking this
-      //      tile's max; S is read from TMEM once (the TMEM->RF path is the scarce resource here,
-      //      profiles/r01a_ncu_summary.md).  Only when some row's max grew by more than 2^8 — always on
-      //      the first tile, rarely afterwards — the slow path below rescales O and recomputes P. ----
-      float mx = -INFINITY, lsum = 0.f;
+      //      tile's max; S is read from TMEM once.  Only when some row's max grew by more than 2^8 —
+      //      always on the first tile, rarely afterwards — the slow path rescales O and recomputes P. ----
+      float mx, lsum = 0.f;
       uint32_t pk[32];
-      const float m_fast = (m == -INFINITY) ? 0.f : m;
-      const float addm_fast = add - m_fast;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS_mine + c * 32, r);
-        tmem_ld_wait();
-        if (j == 0) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float t = fmaf(__uint_as_float(r[e]), c1, add);
-            if (need_mask && key0 + c * 32 + e >= lim) t = -INFINITY;
-            mx = fmaxf(mx, t);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float t0 = fmaf(__uint_as_float(r[e]), c1, addm_fast);
-            float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm_fast);
-            if (need_mask) {
-              if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
-              if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
-            }
-            mx = fmaxf(mx, fmaxf(t0, t1));
-            const float p0 = ex2(t0), p1 = ex2(t1);
-            lsum += p0 + p1;
-            pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
-          }
-        }
+      if (j == 0) {
+        mx = need_mask ? softmax_row_max<true>(tS_mine, c1, add, key0, lim)
+                       : softmax_row_max<false>(tS_mine, c1, add, key0, lim);
+      } else {
+        const float m_fast = (m == -INFINITY) ? 0.f : m;
+        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)
+                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)) +
+             m_fast;  // back to absolute (log2-domain) units
       }
-      if (j > 0) mx += m_fast;  // back to absolute (log2-domain) units
       xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
       const float m_new = fmaxf(m, mx);
 
       // both halves of a row quarter see identical (m, m_new) and therefore take the same branch
-      if (__any_sync(0xffffffffu, m_new > m + 8.0f)) {
-        // ---- slow path: adopt the new max, rescale O and l, recompute P from S ----
+      if (j == 0 || __any_sync(0xffffffffu, m_new > m + 8.0f)) {
         if (j > 0) {
           float f = ex2(m - m_new);
           if (m_new == -INFINITY) f = 1.f;
@@ -290,29 +349,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
           l *= f;
         }
         m = m_new;
-        const float m_use = (m == -INFINITY) ? 0.f : m;
-        const float addm = add - m_use;
-        lsum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tS_mine + c * 32, r);
-          tmem_ld_wait();
-          uint32_t pq[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
-            float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
-            if (need_mask) {
-              if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
-              if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
-            }
-            const float p0 = ex2(t0), p1 = ex2(t1);
-            lsum += p0 + p1;
-            pq[e >> 1] = pack_bf16(p0, p1);
-          }
-          tmem_st16(tS_mine + c * 16, pq);
-        }
+        const float addm = add - ((m == -INFINITY) ? 0.f : m);
+        lsum = need_mask ? softmax_exp_store<true>(tS_mine, c1, addm, key0, lim)
+                         : softmax_exp_store<false>(tS_mine, c1, addm, key0, lim);
       } else {
         tmem_st16(tS_mine, pk);
         tmem_st16(tS_mine + 16, pk + 16);
