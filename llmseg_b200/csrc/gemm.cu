@@ -345,6 +345,44 @@ __device__ __forceinline__ void epi_qkv_rope(const GemmDev& p, const uint32_t* l
   }
 }
 
+// One warp's share of a finished 128 x BN accumulator tile: quarter = TMEM lane quarter (32 rows),
+// chalf = which half of the tile's columns.
+template <int BN, int MODE, bool ROPE>
+__device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage, uint32_t taddr, int m_blk,
+                                              int n_blk, int quarter, int chalf, int lane) {
+  const int row = m_blk * BM + quarter * 32 + lane;
+  int out_row = row;
+  if (MODE == LLMSEG_GEMM_PLAIN && p.out_row_map != nullptr && row < p.M) out_row = p.out_row_map[row];
+  const bool live = row < p.M && out_row >= 0;
+  if (MODE == MODE_RELPOS) {
+    relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
+  } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 128; ++c) {
+      const int half = chalf;
+      uint32_t lo[32], hi[32];
+      tmem_ld32(taddr + c * 128 + half * 32, lo);
+      tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
+      tmem_ld_wait();
+      const int col = n_blk * BN + c * 128 + half * 32;
+      if (live && col < p.N) epi_qkv_rope(p, lo, hi, row, col);
+    }
+  } else {
+#pragma unroll 1
+    for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c * 32, r);
+      tmem_ld_wait();
+      const int n0 = n_blk * BN + c * 32;
+      if (live && n0 < p.N) {
+        if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0);
+        else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
+        else epi_qkv(p, r, row, n0);
+      }
+    }
+  }
+}
+
 template <int BN, int MODE, bool ROPE>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -477,41 +515,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      int out_row = row;
-      if (MODE == LLMSEG_GEMM_PLAIN && p.out_row_map != nullptr && row < p.M)
-        out_row = p.out_row_map[row];
-      const bool live = row < p.M && out_row >= 0;
-      if (MODE == MODE_RELPOS) {
-        relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
-      } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 128; ++c) {
-          {
-            const int half = chalf;
-            uint32_t lo[32], hi[32];
-            tmem_ld32(taddr + c * 128 + half * 32, lo);
-            tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
-            tmem_ld_wait();
-            const int col = n_blk * BN + c * 128 + half * 32;
-            if (live && col < p.N) epi_qkv_rope(p, lo, hi, row, col);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-          const int n0 = n_blk * BN + c * 32;
-          if (live && n0 < p.N) {
-            if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0);
-            else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
-            else epi_qkv(p, r, row, n0);
-          }
-        }
-      }
+      epilogue_tile<BN, MODE, ROPE>(p, rp_stage, taddr, m_blk, n_blk, quarter, chalf, lane);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
       if (++as == 2) {
@@ -528,6 +533,195 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA
+// TMA-loads its own 128 A rows and HALF of the W tile; one thread of the leader CTA issues
+// M=256 MMAs that read both CTAs' shared memory and write 128 accumulator rows into each CTA's TMEM.
+// Per CTA a stage is 16 KB (A) + BN/2*128 B (W half) = 32 KB at BN=256: 6 stages instead of 4 in the
+// same 192 KB, and the shared-memory operand traffic per MMA drops from 12 KB to 8 KB per CTA — the
+// single-CTA kernel sits at 50 % tensor-pipe with its smem operand path and L2->SM path both half
+// used (profiles/r01a_ncu_summary.md): it is latency-bound on a 4-stage ring.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int MODE, bool ROPE>
+__global__ void __launch_bounds__(384, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const GemmDev p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = (int)cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's copy is the one in use: 1 arrive (expect_tx) + both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);  // one multicast commit per consumed stage
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int m_groups = (p.num_m_tiles + 1) / 2;
+  const int num_groups = m_groups * p.num_n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const bool n_fastest = p.n_fastest != 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * 2 + cta_rank;
+        const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(sa, &tmA, lbar, kb * BK, m_blk * BM);
+          tma_load_2d_pair(sb, &tmB, lbar, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 1024, UMMA_SW128);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
+            umma2_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma2_commit_mcast(&empty_bar[stage], 3);  // frees the slot in both CTAs
+          if (kb == p.num_k_blocks - 1) umma2_commit_mcast(&tmem_full[as], 3);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int chalf = (warp - 4) >> 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * 2 + cta_rank;
+      const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+      epilogue_tile<BN, MODE, ROPE>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int MODE, bool ROPE>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int grid,
+            cudaStream_t stream) {
+  auto kern = gemm2_kernel<BN, MODE, ROPE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, d));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// LLMSEG_GEMM_2CTA=0|1 selects the CTA-pair kernel for problems with >= 2 row tiles
+bool use_pair_kernel(int m_tiles) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_GEMM_2CTA");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode == 1 && m_tiles >= 2;
 }
 
 template <int BN, int MODE, bool ROPE>
@@ -673,6 +867,29 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
     uint64_t str[1] = {(uint64_t)p->ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)(bn / d.cluster)};  // each CTA loads (and multicasts) 1/cluster of the W tile
     if (int e = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, 128)) return e;
+  }
+
+  if (use_pair_kernel(m_tiles)) {
+    d.cluster = 2;
+    const int pgrid = pick_grid(((m_tiles + 1) / 2) * d.num_n_tiles, 2, sms);
+    uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+    uint64_t str[1] = {(uint64_t)p->ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)(bn / 2)};
+    if (int e = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, 128)) return e;
+#define LLMSEG_GEMM2_DISPATCH(BN_)                                                              \
+  switch (p->mode) {                                                                            \
+    case LLMSEG_GEMM_PLAIN: return launch2<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, d, pgrid, stream);   \
+    case LLMSEG_GEMM_SWIGLU: return launch2<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, d, pgrid, stream); \
+    default:                                                                                    \
+      return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, d, pgrid, stream)              \
+                  : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, d, pgrid, stream);            \
+  }
+    if (bn == 256) {
+      LLMSEG_GEMM2_DISPATCH(256)
+    } else {
+      LLMSEG_GEMM2_DISPATCH(128)
+    }
+#undef LLMSEG_GEMM2_DISPATCH
   }
 
 #define LLMSEG_GEMM_DISPATCH(BN_)                                                            \
