@@ -714,14 +714,18 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, in
   return 0;
 }
 
-// LLMSEG_GEMM_2CTA=0|1 selects the CTA-pair kernel for problems with >= 2 row tiles
+// The CTA-pair kernel is the default for problems with >= 8 row tiles (measured +4..15 % over the
+// single-CTA kernel there, profiles/r01e_gemm_2cta.md; small-M problems keep the single-CTA kernel:
+// a pair wastes half its tile on an odd tile count).  LLMSEG_GEMM_2CTA=0 disables, =1 forces (>= 2 tiles).
 bool use_pair_kernel(int m_tiles) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("LLMSEG_GEMM_2CTA");
-    mode = e ? atoi(e) : 0;
+    mode = e ? atoi(e) : 2;
   }
-  return mode == 1 && m_tiles >= 2;
+  if (mode == 0) return false;
+  if (mode == 1) return m_tiles >= 2;
+  return m_tiles >= 8;
 }
 
 template <int BN, int MODE, bool ROPE>
