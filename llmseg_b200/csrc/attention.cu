@@ -16,6 +16,7 @@
 // columns qext/kext (see include/llmseg_b200.h): windows use 32 extra columns (rel_h and rel_w),
 // global attention 64 extra columns (rel_w) plus a per-(row, 64-key block) additive constant (rel_h).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -407,6 +408,334 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
   }
 }
 
+// =============================================================================================
+// v2: two 128-query tiles per CTA ("ping-pong"), one CTA per SM.
+//
+// The v1 kernel above serialises  S -> softmax -> PV -> next S  inside a CTA and relies on two
+// co-resident CTAs to overlap; ncu (profiles/r01a..r01f) shows its softmax warps parked on the S
+// barrier for ~40 % of their time and the tensor pipe ~37 % active.  Here one MMA-issuing thread
+// interleaves the two query tiles
+//        ... PV0(j)  S0(j+1)  PV1(j)  S1(j+1)  PV0(j+1) ...
+// so that while softmax group g works on S_g(j) the tensor core runs the other tile's MMAs, and a
+// group's next score tile is already being computed when its P is consumed.  K/V tiles are
+// double-buffered and shared by both query tiles (half the K/V smem traffic per query row).
+//   TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD)
+//   warps: 0 TMA producer, 1 MMA issuer + TMEM alloc, 2..9 softmax group 0, 10..17 softmax group 1
+// =============================================================================================
+template <int HD, int EXT>
+struct ACfg2 {
+  static constexpr int Q0_BYTES = 128 * 128;
+  static constexpr int Q1_BYTES = HD == 80 ? 128 * 32 : (HD == 128 ? 128 * 128 : 0);
+  static constexpr int QX_BYTES = EXT == 1 ? 128 * 64 : (EXT == 2 ? 128 * 128 : 0);
+  static constexpr int QT_BYTES = Q0_BYTES + Q1_BYTES + QX_BYTES;  // one query tile (+ its ext columns)
+  static constexpr int E_BYTES = EXT ? 16384 : 0;
+  static constexpr int K_BYTES = Q0_BYTES + Q1_BYTES;
+  static constexpr int V_CHUNK = HD * 128;
+  static constexpr int V_BYTES = 2 * V_CHUNK;
+  static constexpr int OFF_Q = 0;                        // 2 query tiles
+  static constexpr int OFF_E = OFF_Q + 2 * QT_BYTES;
+  static constexpr int OFF_K = OFF_E + E_BYTES;          // 2 stages
+  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;      // 2 stages
+  static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
+  static constexpr int OFF_XCH = OFF_BAR + 256;          // per group: float[2][2][128] + float[2][128]
+  static constexpr int SMEM_BYTES = OFF_XCH + 2 * 3072 + 1024;
+  static constexpr int Q_TX = 2 * QT_BYTES + E_BYTES;
+  static constexpr int TMEM_COLS = 512;
+};
+
+template <int HD, int EXT>
+__global__ void __launch_bounds__(576, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+             const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
+             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
+             const __grid_constant__ CUtensorMap tmE, const AttnDev p) {
+  using C = ACfg2<HD, EXT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* bar_s = bars + 9;     // [2] per softmax group
+  uint64_t* bar_p = bars + 11;    // [2] per softmax group
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * BM);
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+
+  int kv_limit = p.seq;
+  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
+  int kv_hi = kv_limit;
+  if (p.causal) kv_hi = min(kv_hi, q0 + 2 * BM);
+  const int n_tiles = (kv_hi + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQa);
+    tma_prefetch_desc(&tmKa);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 11; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_p[0], 256);
+    mbar_init(&bar_p[1], 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, C::Q_TX);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        uint8_t* sq = smem + C::OFF_Q + t * C::QT_BYTES;
+        const int r0 = q0 + t * BM;
+        tma_load_3d(sq, &tmQa, bar_q, 0, r0, bh);
+        if (HD == 80) tma_load_3d(sq + C::Q0_BYTES, &tmQb, bar_q, 64, r0, bh);
+        if (HD == 128) tma_load_3d(sq + C::Q0_BYTES, &tmQa, bar_q, 64, r0, bh);
+        if (EXT) tma_load_3d(sq + C::Q0_BYTES + C::Q1_BYTES, &tmQx, bar_q, 0, r0, bh);
+      }
+      if (EXT == 1) {
+        tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
+        tma_load_2d(smem + C::OFF_E + 8192, &tmE, bar_q, 0, 128);
+      }
+      if (EXT == 2) tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int key0 = j * BN;
+        uint8_t* sk = smem + C::OFF_K + st * C::K_BYTES;
+        uint8_t* sv = smem + C::OFF_V + st * C::V_BYTES;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], C::K_BYTES);
+        tma_load_3d(sk, &tmKa, &k_full[st], 0, key0, bh);
+        if (HD == 80) tma_load_3d(sk + C::Q0_BYTES, &tmKb, &k_full[st], 64, key0, bh);
+        if (HD == 128) tma_load_3d(sk + C::Q0_BYTES, &tmKa, &k_full[st], 64, key0, bh);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], C::V_BYTES);
+        tma_load_3d(sv, &tmV, &v_full[st], key0, 0, bh);
+        tma_load_3d(sv + C::V_CHUNK, &tmV, &v_full[st], key0 + 64, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+      const uint32_t sE = smem_u32(smem + C::OFF_E);
+      // S_g(j) = [q_g|qext_g] . [k_j|kext]^T   into TMEM columns [128g, 128g+128)
+      auto issue_s = [&](int g, int j) {
+        const uint32_t sq = smem_u32(smem + C::OFF_Q + g * C::QT_BYTES);
+        const uint32_t sk = smem_u32(smem + C::OFF_K + (j & 1) * C::K_BYTES);
+        const uint32_t tS = tmem_base + g * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tS, umma_smem_desc(sq + k * 32, 1024, UMMA_SW128),
+                  umma_smem_desc(sk + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
+        if (HD == 80)
+          umma_ss(tS, umma_smem_desc(sq + C::Q0_BYTES, 256, UMMA_SW32),
+                  umma_smem_desc(sk + C::Q0_BYTES, 256, UMMA_SW32), idesc_s, 1);
+        if (HD == 128) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_smem_desc(sq + C::Q0_BYTES + k * 32, 1024, UMMA_SW128),
+                    umma_smem_desc(sk + C::Q0_BYTES + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+        }
+        const uint32_t sqx = sq + C::Q0_BYTES + C::Q1_BYTES;
+        if (EXT == 1) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_ss(tS, umma_smem_desc(sqx + k * 32, 512, UMMA_SW64),
+                    umma_smem_desc(sE + j * 8192 + k * 32, 512, UMMA_SW64), idesc_s, 1);
+        }
+        if (EXT == 2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_smem_desc(sqx + k * 32, 1024, UMMA_SW128),
+                    umma_smem_desc(sE + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+        }
+      };
+      // O_g += P_g(j) . V_j ; P_g sits at S_g columns [0,32) (keys 0..63) and [64,96) (keys 64..127)
+      auto issue_pv = [&](int g, int j) {
+        const uint32_t sv = smem_u32(smem + C::OFF_V + (j & 1) * C::V_BYTES);
+        const uint32_t tS = tmem_base + g * 128;
+        const uint32_t tO = tmem_base + 256 + g * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8,
+                  umma_smem_desc(sv + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128), idesc_o,
+                  (j | k) != 0);
+      };
+      mbar_wait(bar_q, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      umma_commit(&bar_s[0]);
+      issue_s(1, 0);
+      umma_commit(&bar_s[1]);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = j & 1;            // bar_p / bar_s complete once per tile
+        const uint32_t kvph = (j >> 1) & 1;   // 2-stage K/V rings
+        const bool more = j + 1 < n_tiles;
+        // ---- query tile 0 ----
+        mbar_wait(&bar_p[0], ph);
+        mbar_wait(&v_full[st], kvph);
+        tc_fence_after();
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(0, j + 1);
+        }
+        umma_commit(&bar_s[0]);  // S0(j+1) ready — or, after the last tile, O0 complete
+        // ---- query tile 1 ----
+        mbar_wait(&bar_p[1], ph);
+        tc_fence_after();
+        issue_pv(1, j);
+        umma_commit(&v_empty[st]);
+        if (more) {
+          issue_s(1, j + 1);
+          umma_commit(&k_empty[st ^ 1]);
+        }
+        umma_commit(&bar_s[1]);
+      }
+    }
+  } else {
+    // ================================ softmax groups ================================
+    const int g = warp >= 10 ? 1 : 0;          // query tile / softmax group
+    const int wg = warp - 2 - 8 * g;           // 0..7 inside the group
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
+    const int half = wg >> 2;                  // which 64-key half of the score tile
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + g * BM + row_in_tile;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t tS_mine = t_row + g * 128 + half * 64;
+    const uint32_t tO = t_row + 256 + g * 128;
+    float* xmax = reinterpret_cast<float*>(smem + C::OFF_XCH + g * 3072);  // [2 parity][2 half][128]
+    float* xsum = xmax + 512;                                              // [2 half][128]
+    const int bar_id = 1 + g;
+    constexpr int O_CHUNKS = HD / 16;
+    const int oc0 = half == 0 ? 0 : (O_CHUNKS + 1) / 2;
+    const int oc1 = half == 0 ? (O_CHUNKS + 1) / 2 : O_CHUNKS;
+    const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;
+    const bf16* rb = nullptr;
+    if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
+    const float c1 = p.c1;
+    float m = -INFINITY, l = 0.f;
+    const int q_tile0 = q0 + g * BM;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const int key0 = j * BN + half * 64;
+      float add = 0.f;
+      if (EXT == 2) add = __bfloat162float(rb[2 * j + half]) * LOG2E;
+      const bool need_mask = (key0 + 64 > kv_limit) || (p.causal && key0 + 63 > q_tile0);
+      mbar_wait(&bar_s[g], ph);
+      tc_fence_after();
+
+      float mx, lsum = 0.f;
+      uint32_t pk[32];
+      if (j == 0) {
+        mx = need_mask ? softmax_row_max<true>(tS_mine, c1, add, key0, lim)
+                       : softmax_row_max<false>(tS_mine, c1, add, key0, lim);
+      } else {
+        const float m_fast = (m == -INFINITY) ? 0.f : m;
+        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)
+                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)) +
+             m_fast;
+      }
+      xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
+      const float m_new = fmaxf(m, mx);
+
+      if (j == 0 || __any_sync(0xffffffffu, m_new > m + 8.0f)) {
+        if (j > 0) {
+          float f = ex2(m - m_new);
+          if (m_new == -INFINITY) f = 1.f;
+#pragma unroll 1
+          for (int c = oc0; c < oc1; ++c) {
+            uint32_t r[16];
+            tmem_ld16(tO + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
+            tmem_st16(tO + c * 16, r);
+          }
+          l *= f;
+        }
+        m = m_new;
+        const float addm = add - ((m == -INFINITY) ? 0.f : m);
+        lsum = need_mask ? softmax_exp_store<true>(tS_mine, c1, addm, key0, lim)
+                         : softmax_exp_store<false>(tS_mine, c1, addm, key0, lim);
+      } else {
+        tmem_st16(tS_mine, pk);
+        tmem_st16(tS_mine + 16, pk + 16);
+      }
+      l += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_p[g]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> out[b*seq + q_row, h*HD + d] ----
+    mbar_wait(&bar_s[g], n_tiles & 1);
+    tc_fence_after();
+    xsum[half * 128 + row_in_tile] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    l += xsum[(half ^ 1) * 128 + row_in_tile];
+    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+    const int h = bh - b * p.heads;
+    bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
+#pragma unroll 1
+    for (int c = oc0; c < oc1; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tO + c * 16, r);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+        uint4 o0, o1;
+        o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        o0.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        o0.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        o1.x = pack_bf16(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+        o1.y = pack_bf16(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+        o1.z = pack_bf16(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+        o1.w = pack_bf16(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 16) = o0;
+        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// LLMSEG_ATTN_V2=0|1: select the two-query-tile kernel
+bool use_attn_v2() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_ATTN_V2");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode == 1;
+}
+
 template <int HD, int EXT>
 int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   using C = ACfg<HD, EXT>;
@@ -456,6 +785,20 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   d.kv_len = p->kv_len;
   d.row_bias = static_cast<const bf16*>(p->row_bias);
 
+  if (use_attn_v2()) {
+    using C2 = ACfg2<HD, EXT>;
+    auto kern2 = attn2_kernel<HD, EXT>;
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      LLMSEG_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
+      attr2_done = true;
+    }
+    dim3 grid2((p->seq + 2 * BM - 1) / (2 * BM), BH);
+    kern2<<<grid2, 576, C2::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
+    LLMSEG_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
   auto kern = attn_kernel<HD, EXT>;
   static bool attr_done = false;
   if (!attr_done) {
