@@ -53,6 +53,7 @@ struct ACfg {
 };
 
 struct AttnDev {
+  int dbg;  // developer timing knob (LLMSEG_ATTN_DBG): 1 no ex2, 2 no TMEM score loads, 3 no MMAs, 4 no P stores
   bf16* out;
   int ldo;
   int heads, seq, seq_pad;
@@ -100,13 +101,18 @@ __device__ __forceinline__ float softmax_row_max(uint32_t t_s, float c1, float a
 // argument (relative to the reference max folded into addm) and accumulates the row sum.
 template <bool MASK>
 __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float addm, int key0, int lim,
-                                                  float& lsum, uint32_t* pk) {
+                                                  float& lsum, uint32_t* pk, int dbg = 0) {
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t r[32];
-    tmem_ld32(t_s + c * 32, r);
-    tmem_ld_wait();
+    if (dbg == 2) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(0.001f * (float)(e + c));
+    } else {
+      tmem_ld32(t_s + c * 32, r);
+      tmem_ld_wait();
+    }
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
@@ -116,7 +122,7 @@ __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float 
         if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
       }
       mx = fmaxf(mx, fmaxf(t0, t1));
-      const float p0 = ex2(t0), p1 = ex2(t1);
+      const float p0 = dbg == 1 ? t0 * 0.01f : ex2(t0), p1 = dbg == 1 ? t1 * 0.01f : ex2(t1);
       lsum += p0 + p1;
       pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
     }
@@ -533,6 +539,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
       const uint32_t sE = smem_u32(smem + C::OFF_E);
       // S_g(j) = [q_g|qext_g] . [k_j|kext]^T   into TMEM columns [128g, 128g+128)
       auto issue_s = [&](int g, int j) {
+        if (p.dbg == 3 && j > 0) return;
         const uint32_t sq = smem_u32(smem + C::OFF_Q + g * C::QT_BYTES);
         const uint32_t sk = smem_u32(smem + C::OFF_K + (j & 1) * C::K_BYTES);
         const uint32_t tS = tmem_base + g * 128;
@@ -565,6 +572,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
       };
       // O_g += P_g(j) . V_j ; P_g sits at S_g columns [0,32) (keys 0..63) and [64,96) (keys 64..127)
       auto issue_pv = [&](int g, int j) {
+        if (p.dbg == 3 && j > 0) return;
         const uint32_t sv = smem_u32(smem + C::OFF_V + (j & 1) * C::V_BYTES);
         const uint32_t tS = tmem_base + g * 128;
         const uint32_t tO = tmem_base + 256 + g * 128;
@@ -650,9 +658,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
                        : softmax_row_max<false>(tS_mine, c1, add, key0, lim);
       } else {
         const float m_fast = (m == -INFINITY) ? 0.f : m;
-        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)
-                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk)) +
+        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)
+                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)) +
              m_fast;
+        if (p.dbg == 1 || p.dbg == 2) mx = m;  // keep the fast path
       }
       xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
@@ -678,7 +687,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
         const float addm = add - ((m == -INFINITY) ? 0.f : m);
         lsum = need_mask ? softmax_exp_store<true>(tS_mine, c1, addm, key0, lim)
                          : softmax_exp_store<false>(tS_mine, c1, addm, key0, lim);
-      } else {
+      } else if (p.dbg != 4) {
         tmem_st16(tS_mine, pk);
         tmem_st16(tS_mine + 16, pk + 16);
       }
@@ -784,6 +793,14 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   d.causal = p->causal;
   d.kv_len = p->kv_len;
   d.row_bias = static_cast<const bf16*>(p->row_bias);
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("LLMSEG_ATTN_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    d.dbg = dbg;
+  }
 
   if (use_attn_v2()) {
     using C2 = ACfg2<HD, EXT>;

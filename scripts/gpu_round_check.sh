@@ -1,7 +1,11 @@
-# one GPU-box visit: validate the ping-pong attention kernel, then bench with it
-LLMSEG_ATTN_V2=1 timeout 200 python scripts/gpu_attn_check.py > gpurun_out/attn5_v2.log 2>&1; rc=$?; echo exit=$rc >> gpurun_out/attn5_v2.log
-if [ $rc -ne 0 ]; then tail -20 gpurun_out/attn5_v2.log; exit 1; fi
-LLMSEG_ATTN_V2=1 timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu7_v2.log 2>&1; echo exit=$? >> gpurun_out/pytest_gpu7_v2.log
-LLMSEG_ATTN_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench7_v2.log 2>&1; echo exit=$? >> gpurun_out/bench7_v2.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench7.log 2>&1; echo exit=$? >> gpurun_out/bench7.log
-grep -E "attention [0-9]|maxerr" gpurun_out/attn5_v2.log; tail -3 gpurun_out/pytest_gpu7_v2.log; tail -c 500 gpurun_out/bench7_v2.log; tail -c 300 gpurun_out/bench7.log
+# investigation: where does the SAM global attention tile time go?
+./tests/probe/mufu_bench > gpurun_out/mufu.log 2>&1
+for dbg in 0 1 2 3 4; do
+  echo "=== LLMSEG_ATTN_DBG=$dbg" >> gpurun_out/attn_knobs.log
+  LLMSEG_ATTN_V2=1 LLMSEG_ATTN_DBG=$dbg timeout 120 python scripts/gpu_attn_check.py glob 2>&1 | grep -E "attention [0-9]" >> gpurun_out/attn_knobs.log
+done
+for dbg in 0 1; do
+  echo "=== v1 LLMSEG_ATTN_DBG=$dbg" >> gpurun_out/attn_knobs.log
+  LLMSEG_ATTN_DBG=$dbg timeout 120 python scripts/gpu_attn_check.py glob 2>&1 | grep -E "attention [0-9]" >> gpurun_out/attn_knobs.log
+done
+cat gpurun_out/mufu.log gpurun_out/attn_knobs.log
