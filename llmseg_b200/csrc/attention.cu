@@ -103,16 +103,19 @@ template <bool MASK>
 __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float addm, int key0, int lim,
                                                   float& lsum, uint32_t* pk, int dbg = 0) {
   float mx = -INFINITY;
+  uint32_t r0[32], r1[32];
+  if (dbg == 2) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) r0[e] = r1[e] = __float_as_uint(0.001f * (float)e);
+  } else {
+    tmem_ld32(t_s, r0);
+    tmem_ld_wait();
+    tmem_ld32(t_s + 32, r1);  // in flight while chunk 0 is processed
+  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    if (dbg == 2) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(0.001f * (float)(e + c));
-    } else {
-      tmem_ld32(t_s + c * 32, r);
-      tmem_ld_wait();
-    }
+    if (c == 1 && dbg != 2) tmem_ld_wait();
+    const uint32_t* r = c == 0 ? r0 : r1;
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
@@ -450,7 +453,7 @@ struct ACfg2 {
 };
 
 template <int HD, int EXT>
-__global__ void __launch_bounds__(576, 1)
+__global__ void __maxnreg__(112)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
              const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
@@ -486,8 +489,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
     tma_prefetch_desc(&tmKa);
     tma_prefetch_desc(&tmV);
     for (int i = 0; i < 11; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 256);
-    mbar_init(&bar_p[1], 256);
+    mbar_init(&bar_p[0], 8);   // one elected arrival per softmax warp
+    mbar_init(&bar_p[1], 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -694,7 +697,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
       l += lsum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar_p[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[g]);
     }
 
     // ---- epilogue: O / l -> bf16 -> out[b*seq + q_row, h*HD + d] ----

@@ -1,11 +1,5 @@
-# investigation: where does the SAM global attention tile time go?
-./tests/probe/mufu_bench > gpurun_out/mufu.log 2>&1
-for dbg in 0 1 2 3 4; do
-  echo "=== LLMSEG_ATTN_DBG=$dbg" >> gpurun_out/attn_knobs.log
-  LLMSEG_ATTN_V2=1 LLMSEG_ATTN_DBG=$dbg timeout 120 python scripts/gpu_attn_check.py glob 2>&1 | grep -E "attention [0-9]" >> gpurun_out/attn_knobs.log
-done
-for dbg in 0 1; do
-  echo "=== v1 LLMSEG_ATTN_DBG=$dbg" >> gpurun_out/attn_knobs.log
-  LLMSEG_ATTN_DBG=$dbg timeout 120 python scripts/gpu_attn_check.py glob 2>&1 | grep -E "attention [0-9]" >> gpurun_out/attn_knobs.log
-done
-cat gpurun_out/mufu.log gpurun_out/attn_knobs.log
+LLMSEG_ATTN_V2=1 timeout 200 python scripts/gpu_attn_check.py > gpurun_out/attn6_v2.log 2>&1; rc=$?; echo exit=$rc >> gpurun_out/attn6_v2.log
+grep -E "attention [0-9]|maxerr|exit" gpurun_out/attn6_v2.log
+if [ $rc -ne 0 ]; then tail -20 gpurun_out/attn6_v2.log; exit 1; fi
+LLMSEG_ATTN_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench8_v2.log 2>&1; echo exit=$? >> gpurun_out/bench8_v2.log
+tail -c 600 gpurun_out/bench8_v2.log
