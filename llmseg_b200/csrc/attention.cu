@@ -103,19 +103,16 @@ template <bool MASK>
 __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float addm, int key0, int lim,
                                                   float& lsum, uint32_t* pk, int dbg = 0) {
   float mx = -INFINITY;
-  uint32_t r0[32], r1[32];
-  if (dbg == 2) {
-#pragma unroll
-    for (int e = 0; e < 32; ++e) r0[e] = r1[e] = __float_as_uint(0.001f * (float)e);
-  } else {
-    tmem_ld32(t_s, r0);
-    tmem_ld_wait();
-    tmem_ld32(t_s + 32, r1);  // in flight while chunk 0 is processed
-  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    if (c == 1 && dbg != 2) tmem_ld_wait();
-    const uint32_t* r = c == 0 ? r0 : r1;
+    uint32_t r[32];
+    if (dbg == 2) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(0.001f * (float)(e + c));
+    } else {
+      tmem_ld32(t_s + c * 32, r);
+      tmem_ld_wait();
+    }
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
@@ -417,107 +414,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
   }
 }
 
-// ---- full-row variants for the v2 kernel: one thread owns a whole 128-key score row, so the row max
-// needs no cross-warp exchange.  TMEM loads are double-buffered in registers (the load of chunk c+1 is
-// in flight while chunk c is processed).  add0/add1: per-row additive constants of the two 64-key halves. ----
-template <bool MASK>
-__device__ __forceinline__ float row128_max(uint32_t t_s, float c1, float add0, float add1, int key0, int lim) {
-  float mx = -INFINITY;
-  uint32_t ra[32], rb[32];
-  tmem_ld32(t_s, ra);
-  tmem_ld_wait();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t* cur = (c & 1) ? rb : ra;
-    uint32_t* nxt = (c & 1) ? ra : rb;
-    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, nxt);
-    const float add = c < 2 ? add0 : add1;
-    if (MASK) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float t = fmaf(__uint_as_float(cur[e]), c1, add);
-        mx = fmaxf(mx, (key0 + c * 32 + e < lim) ? t : -INFINITY);
-      }
-    } else {
-      float mc = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(cur[e]));
-      mx = fmaxf(mx, fmaf(mc, c1, add));
-    }
-    if (c < 3) tmem_ld_wait();
-  }
-  return mx;
-}
-
-// fast path: P = exp2(s*c1 + add - m_ref) for the whole row, packed bf16 kept in pk[64]; returns the
-// row's max exponent argument RELATIVE to m_ref and accumulates the row sum.  16-column TMEM loads,
-// double-buffered: chunk c+1 is in flight while chunk c is processed.
-template <bool MASK>
-__device__ __forceinline__ float row128_exp_regs(uint32_t t_s, float c1, float add0, float add1, float m_ref,
-                                                 int key0, int lim, float& lsum, uint32_t* pk, int dbg) {
-  float mx = -INFINITY;
-  uint32_t ra[16], rb[16];
-  if (dbg == 2) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) ra[e] = rb[e] = __float_as_uint(0.001f * (float)e);
-  } else {
-    tmem_ld16(t_s, ra);
-    tmem_ld_wait();
-  }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t* cur = (c & 1) ? rb : ra;
-    uint32_t* nxt = (c & 1) ? ra : rb;
-    if (c < 7 && dbg != 2) tmem_ld16(t_s + (c + 1) * 16, nxt);
-    const float addm = (c < 4 ? add0 : add1) - m_ref;
-#pragma unroll
-    for (int e = 0; e < 16; e += 2) {
-      float t0 = fmaf(__uint_as_float(cur[e]), c1, addm);
-      float t1 = fmaf(__uint_as_float(cur[e + 1]), c1, addm);
-      if (MASK) {
-        if (key0 + c * 16 + e >= lim) t0 = -INFINITY;
-        if (key0 + c * 16 + e + 1 >= lim) t1 = -INFINITY;
-      }
-      mx = fmaxf(mx, fmaxf(t0, t1));
-      const float p0 = dbg == 1 ? t0 * 0.01f : ex2(t0), p1 = dbg == 1 ? t1 * 0.01f : ex2(t1);
-      lsum += p0 + p1;
-      pk[c * 8 + (e >> 1)] = pack_bf16(p0, p1);
-    }
-    if (c < 7 && dbg != 2) tmem_ld_wait();
-  }
-  return mx;
-}
-
-// slow path: recompute P against a new reference max and store it to TMEM chunk by chunk
-// (P of keys 0..63 -> S columns [0,32), keys 64..127 -> [64,96), the layout the PV MMA reads).
-template <bool MASK>
-__device__ __forceinline__ float row128_exp_store(uint32_t t_s, float c1, float add0, float add1, float m_ref,
-                                                  int key0, int lim) {
-  float lsum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tmem_ld32(t_s + c * 32, r);
-    tmem_ld_wait();
-    const float addm = (c < 2 ? add0 : add1) - m_ref;
-    uint32_t pq[16];
-#pragma unroll
-    for (int e = 0; e < 32; e += 2) {
-      float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
-      float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
-      if (MASK) {
-        if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
-        if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
-      }
-      const float p0 = ex2(t0), p1 = ex2(t1);
-      lsum += p0 + p1;
-      pq[e >> 1] = pack_bf16(p0, p1);
-    }
-    tmem_st16(t_s + (c >> 1) * 64 + (c & 1) * 16, pq);
-  }
-  return lsum;
-}
-
 // =============================================================================================
 // v2: two 128-query tiles per CTA ("ping-pong"), one CTA per SM.
 //
@@ -530,8 +426,7 @@ __device__ __forceinline__ float row128_exp_store(uint32_t t_s, float c1, float 
 // group's next score tile is already being computed when its P is consumed.  K/V tiles are
 // double-buffered and shared by both query tiles (half the K/V smem traffic per query row).
 //   TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD)
-//   warps: 0 TMA producer, 1 MMA issuer + TMEM alloc, 2..5 softmax group 0, 6..9 softmax group 1
-//   (one thread = one full 128-key score row: no cross-warp reductions, ~160 registers per thread)
+//   warps: 0 TMA producer, 1 MMA issuer + TMEM alloc, 2..9 softmax group 0, 10..17 softmax group 1
 // =============================================================================================
 template <int HD, int EXT>
 struct ACfg2 {
@@ -548,13 +443,14 @@ struct ACfg2 {
   static constexpr int OFF_K = OFF_E + E_BYTES;          // 2 stages
   static constexpr int OFF_V = OFF_K + 2 * K_BYTES;      // 2 stages
   static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_XCH = OFF_BAR + 256;          // per group: float[2][2][128] + float[2][128]
+  static constexpr int SMEM_BYTES = OFF_XCH + 2 * 3072 + 1024;
   static constexpr int Q_TX = 2 * QT_BYTES + E_BYTES;
   static constexpr int TMEM_COLS = 512;
 };
 
 template <int HD, int EXT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
              const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
@@ -590,8 +486,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
     tma_prefetch_desc(&tmKa);
     tma_prefetch_desc(&tmV);
     for (int i = 0; i < 11; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 4);   // one elected arrival per softmax warp
-    mbar_init(&bar_p[1], 4);
+    mbar_init(&bar_p[0], 256);
+    mbar_init(&bar_p[1], 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -724,13 +620,21 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
     }
   } else {
     // ================================ softmax groups ================================
-    const int g = warp >= 6 ? 1 : 0;           // query tile / softmax group
+    const int g = warp >= 10 ? 1 : 0;          // query tile / softmax group
+    const int wg = warp - 2 - 8 * g;           // 0..7 inside the group
     const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
+    const int half = wg >> 2;                  // which 64-key half of the score tile
     const int row_in_tile = quarter * 32 + lane;
     const int q_row = q0 + g * BM + row_in_tile;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t tS = t_row + g * 128;
+    const uint32_t tS_mine = t_row + g * 128 + half * 64;
     const uint32_t tO = t_row + 256 + g * 128;
+    float* xmax = reinterpret_cast<float*>(smem + C::OFF_XCH + g * 3072);  // [2 parity][2 half][128]
+    float* xsum = xmax + 512;                                              // [2 half][128]
+    const int bar_id = 1 + g;
+    constexpr int O_CHUNKS = HD / 16;
+    const int oc0 = half == 0 ? 0 : (O_CHUNKS + 1) / 2;
+    const int oc1 = half == 0 ? (O_CHUNKS + 1) / 2 : O_CHUNKS;
     const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;
     const bf16* rb = nullptr;
     if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
@@ -740,38 +644,36 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
 
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
-      const int key0 = j * BN;
-      float add0 = 0.f, add1 = 0.f;
-      if (EXT == 2) {
-        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(rb + 2 * j);
-        add0 = __low2float(v2) * LOG2E;
-        add1 = __high2float(v2) * LOG2E;
-      }
-      const bool need_mask = (key0 + BN > kv_limit) || (p.causal && key0 + BN - 1 > q_tile0);
+      const int key0 = j * BN + half * 64;
+      float add = 0.f;
+      if (EXT == 2) add = __bfloat162float(rb[2 * j + half]) * LOG2E;
+      const bool need_mask = (key0 + 64 > kv_limit) || (p.causal && key0 + 63 > q_tile0);
       mbar_wait(&bar_s[g], ph);
       tc_fence_after();
 
       float mx, lsum = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[32];
       if (j == 0) {
-        mx = need_mask ? row128_max<true>(tS, c1, add0, add1, key0, lim)
-                       : row128_max<false>(tS, c1, add0, add1, key0, lim);
+        mx = need_mask ? softmax_row_max<true>(tS_mine, c1, add, key0, lim)
+                       : softmax_row_max<false>(tS_mine, c1, add, key0, lim);
       } else {
-        const float m_ref = (m == -INFINITY) ? 0.f : m;
-        mx = (need_mask ? row128_exp_regs<true>(tS, c1, add0, add1, m_ref, key0, lim, lsum, pk, p.dbg)
-                        : row128_exp_regs<false>(tS, c1, add0, add1, m_ref, key0, lim, lsum, pk, p.dbg)) +
-             m_ref;  // back to absolute (log2-domain) units
-        if (p.dbg == 1 || p.dbg == 2) mx = m;
+        const float m_fast = (m == -INFINITY) ? 0.f : m;
+        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)
+                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)) +
+             m_fast;
+        if (p.dbg == 1 || p.dbg == 2) mx = m;  // keep the fast path
       }
+      xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
       const float m_new = fmaxf(m, mx);
 
       if (j == 0 || __any_sync(0xffffffffu, m_new > m + 8.0f)) {
-        // slow path (always on the first tile): adopt the new max, rescale this row of O, recompute P
         if (j > 0) {
           float f = ex2(m - m_new);
           if (m_new == -INFINITY) f = 1.f;
 #pragma unroll 1
-          for (int c = 0; c < HD / 16; ++c) {
+          for (int c = oc0; c < oc1; ++c) {
             uint32_t r[16];
             tmem_ld16(tO + c * 16, r);
             tmem_ld_wait();
@@ -782,30 +684,30 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
           l *= f;
         }
         m = m_new;
-        const float m_ref = (m == -INFINITY) ? 0.f : m;
-        lsum = need_mask ? row128_exp_store<true>(tS, c1, add0, add1, m_ref, key0, lim)
-                         : row128_exp_store<false>(tS, c1, add0, add1, m_ref, key0, lim);
+        const float addm = add - ((m == -INFINITY) ? 0.f : m);
+        lsum = need_mask ? softmax_exp_store<true>(tS_mine, c1, addm, key0, lim)
+                         : softmax_exp_store<false>(tS_mine, c1, addm, key0, lim);
       } else if (p.dbg != 4) {
-        tmem_st16(tS, pk);
-        tmem_st16(tS + 16, pk + 16);
-        tmem_st16(tS + 64, pk + 32);
-        tmem_st16(tS + 80, pk + 48);
+        tmem_st16(tS_mine, pk);
+        tmem_st16(tS_mine + 16, pk + 16);
       }
       l += lsum;
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[g]);
+      mbar_arrive(&bar_p[g]);
     }
 
     // ---- epilogue: O / l -> bf16 -> out[b*seq + q_row, h*HD + d] ----
     mbar_wait(&bar_s[g], n_tiles & 1);
     tc_fence_after();
+    xsum[half * 128 + row_in_tile] = l;
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    l += xsum[(half ^ 1) * 128 + row_in_tile];
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const int h = bh - b * p.heads;
     bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
 #pragma unroll 1
-    for (int c = 0; c < HD / 16; ++c) {
+    for (int c = oc0; c < oc1; ++c) {
       uint32_t r[16];
       tmem_ld16(tO + c * 16, r);
       tmem_ld_wait();
@@ -909,7 +811,7 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
       attr2_done = true;
     }
     dim3 grid2((p->seq + 2 * BM - 1) / (2 * BM), BH);
-    kern2<<<grid2, 320, C2::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
+    kern2<<<grid2, 576, C2::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
     LLMSEG_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return 0;
