@@ -735,6 +735,353 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
   }
 }
 
+// =============================================================================================
+// Window kernel: SAM 14x14 windowed attention (196 keys, hd 80, 32 rel-pos extension columns).
+//
+// The generic kernel spends most of a window CTA's life in its prologue (6400 two-tile CTAs per
+// layer at batch 8; ncu: 193 us, 216 TF/s).  Here ONE persistent CTA per SM loops over
+// (window, head) items; a whole window fits one 208-key score tile, so softmax is exact in a single
+// step (no online rescale) and the kernel keeps, per item:
+//   S_t = [q_t|qext_t].[k|kext]^T   two M=128 x N=208 MMAs (query rows 0..127 / 128..255)
+//   P_t  -> written over S_t columns [0,104);  O_t = P_t.V accumulates into S_t columns [112,192)
+//   TMEM: S_0 at columns [0,208), S_1 at [256,464)  (O aliases the dead tail of S)
+// K/V are double-buffered across items, the constant one-hot kext tile is loaded once per CTA,
+// Q of the next item streams in as soon as both score MMAs of the current item have been issued.
+//   warps: 0 TMA producer, 1 MMA issuer + TMEM alloc, 2..5 softmax rows of tile 0, 6..9 of tile 1
+// =============================================================================================
+struct WCfg {
+  static constexpr int KEYS = 208;
+  static constexpr int QT_BYTES = 16384 + 4096 + 8192;   // [128x64] SW128 + [128x16] SW32 + [128x32] SW64
+  static constexpr int E_BYTES = 208 * 64;               // [208x32] SW64
+  static constexpr int E_ALLOC = 14336;
+  static constexpr int K0_BYTES = 208 * 128;             // [208x64] SW128
+  static constexpr int K1_BYTES = 208 * 32;              // [208x16] SW32
+  static constexpr int K_ALLOC = 26624 + 7168;
+  static constexpr int V_CHUNK = 80 * 128;               // [80x64 keys] SW128
+  static constexpr int V_TAIL = 80 * 32;                 // [80x16 keys] SW32
+  static constexpr int V_ALLOC = 3 * 10240 + 3072;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_E = OFF_Q + 2 * QT_BYTES;
+  static constexpr int OFF_K = OFF_E + E_ALLOC;
+  static constexpr int OFF_V = OFF_K + 2 * K_ALLOC;
+  static constexpr int OFF_BAR = OFF_V + 2 * V_ALLOC;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int Q_TX = 2 * QT_BYTES;
+  static constexpr int K_TX = K0_BYTES + K1_BYTES;
+  static constexpr int V_TX = 3 * V_CHUNK + V_TAIL;
+  static constexpr int O_COL = 112;                      // O_t inside the S_t column range
+};
+
+__global__ void __launch_bounds__(320, 1)
+attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                const __grid_constant__ CUtensorMap tmQx, const __grid_constant__ CUtensorMap tmKa,
+                const __grid_constant__ CUtensorMap tmKb, const __grid_constant__ CUtensorMap tmE,
+                const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb,
+                const AttnDev p, const int n_items) {
+  using C = WCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* bar_e = bars + 0;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;
+  uint64_t* k_full = bars + 3;    // [2]
+  uint64_t* k_empty = bars + 5;   // [2]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* bar_s = bars + 11;    // [2] score tile t ready
+  uint64_t* bar_p = bars + 13;    // [2] P_t written          (4 elected arrivals)
+  uint64_t* bar_o = bars + 15;    // [2] O_t complete
+  uint64_t* o_free = bars + 17;   // [2] O_t/S_t columns released by the epilogue (4 elected arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQa);
+    tma_prefetch_desc(&tmKa);
+    tma_prefetch_desc(&tmVa);
+    for (int i = 0; i < 19; ++i) mbar_init(&bars[i], 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_p[t], 4);
+      mbar_init(&o_free[t], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(bar_e, C::E_BYTES);
+      tma_load_2d(smem + C::OFF_E, &tmE, bar_e, 0, 0);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t kvph = (it >> 1) & 1;
+        uint8_t* sk = smem + C::OFF_K + st * C::K_ALLOC;
+        uint8_t* sv = smem + C::OFF_V + st * C::V_ALLOC;
+        mbar_wait(&k_empty[st], kvph ^ 1);
+        mbar_expect_tx(&k_full[st], C::K_TX);
+        tma_load_3d(sk, &tmKa, &k_full[st], 0, 0, item);
+        tma_load_3d(sk + 26624, &tmKb, &k_full[st], 64, 0, item);
+        mbar_wait(&v_empty[st], kvph ^ 1);
+        mbar_expect_tx(&v_full[st], C::V_TX);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tma_load_3d(sv + c * C::V_CHUNK, &tmVa, &v_full[st], c * 64, 0, item);
+        tma_load_3d(sv + 3 * C::V_CHUNK, &tmVb, &v_full[st], 192, 0, item);
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, C::Q_TX);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint8_t* sq = smem + C::OFF_Q + t * C::QT_BYTES;
+          tma_load_3d(sq, &tmQa, q_full, 0, t * 128, item);
+          tma_load_3d(sq + 16384, &tmQb, q_full, 64, t * 128, item);
+          tma_load_3d(sq + 20480, &tmQx, q_full, 0, t * 128, item);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::KEYS);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 80);
+      const uint32_t sE = smem_u32(smem + C::OFF_E);
+      mbar_wait(bar_e, 0);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t ph = it & 1, kvph = (it >> 1) & 1;
+        const uint32_t sk = smem_u32(smem + C::OFF_K + st * C::K_ALLOC);
+        const uint32_t sv = smem_u32(smem + C::OFF_V + st * C::V_ALLOC);
+        mbar_wait(q_full, ph);
+        mbar_wait(&k_full[st], kvph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (it > 0) mbar_wait(&o_free[t], ph ^ 1);  // previous item's O_t / S_t columns drained
+          tc_fence_after();
+          const uint32_t sq = smem_u32(smem + C::OFF_Q + t * C::QT_BYTES);
+          const uint32_t tS = tmem_base + t * 256;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tS, umma_smem_desc(sq + k * 32, 1024, UMMA_SW128),
+                    umma_smem_desc(sk + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
+          umma_ss(tS, umma_smem_desc(sq + 16384, 256, UMMA_SW32), umma_smem_desc(sk + 26624, 256, UMMA_SW32),
+                  idesc_s, 1);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_ss(tS, umma_smem_desc(sq + 20480 + k * 32, 512, UMMA_SW64),
+                    umma_smem_desc(sE + k * 32, 512, UMMA_SW64), idesc_s, 1);
+          umma_commit(&bar_s[t]);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(q_empty);
+        mbar_wait(&v_full[st], kvph);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&bar_p[t], ph);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + t * 256;
+#pragma unroll
+          for (int k = 0; k < 12; ++k)
+            umma_ts(tS + C::O_COL, tS + k * 8,
+                    umma_smem_desc(sv + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128), idesc_o,
+                    k != 0);
+          umma_ts(tS + C::O_COL, tS + 96, umma_smem_desc(sv + 3 * C::V_CHUNK, 256, UMMA_SW32), idesc_o, 1);
+          umma_commit(&bar_o[t]);
+        }
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ================================ softmax: thread = one query row ================================
+    const int t = warp >= 6 ? 1 : 0;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = t * 128 + row_in_tile;
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+    const float c1 = p.c1;
+    const int seq = p.seq;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      mbar_wait(&bar_s[t], ph);
+      tc_fence_after();
+      // ---- pass 1: row max over the 196 valid keys ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
+        tmem_ld_wait();
+        float mc = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
+        mx = fmaxf(mx, mc);
+      }
+      {
+        uint32_t r[16];
+        tmem_ld16(tS + 192, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (192 + e < seq) mx = fmaxf(mx, __uint_as_float(r[e]));
+      }
+      const float moff = -mx * c1;  // c1 > 0
+      // ---- pass 2: P = exp2((s - max) * c1) -> packed bf16 over S columns [0,104) ----
+      float l = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[e]), c1, moff));
+          const float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), c1, moff));
+          l += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      {
+        uint32_t r[16];
+        tmem_ld16(tS + 192, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float p0 = (192 + e < seq) ? ex2(fmaf(__uint_as_float(r[e]), c1, moff)) : 0.f;
+          const float p1 = (192 + e + 1 < seq) ? ex2(fmaf(__uint_as_float(r[e + 1]), c1, moff)) : 0.f;
+          l += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+#pragma unroll
+        for (int e = 8; e < 16; ++e) pk[e] = 0;
+        tmem_st16(tS + 96, pk);  // columns [96,104) = keys 192..207, [104,112) scratch
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[t]);
+
+      // ---- epilogue: O / l -> out ----
+      mbar_wait(&bar_o[t], ph);
+      tc_fence_after();
+      const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+      const int b = item / p.heads, h = item - b * p.heads;
+      bf16* orow = p.out + ((size_t)b * seq + q_row) * p.ldo + h * 80;
+#pragma unroll 1
+      for (int c = 0; c < 5; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tS + C::O_COL + c * 16, r);
+        tmem_ld_wait();
+        if (q_row < seq) {
+          uint4 o0, o1;
+          o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+          o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+          o0.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+          o0.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+          o1.x = pack_bf16(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
+          o1.y = pack_bf16(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
+          o1.z = pack_bf16(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
+          o1.w = pack_bf16(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 16) = o0;
+          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// LLMSEG_ATTN_WIN=0 disables the window kernel (falls back to the generic one)
+bool use_attn_win() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_ATTN_WIN");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode == 1;
+}
+
+int num_sms_attn() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_attn_win(const llmseg_attn_params* p, cudaStream_t stream) {
+  using C = WCfg;
+  const int BH = p->batch * p->heads;
+  CUtensorMap tmQa, tmQb, tmQx, tmKa, tmKb, tmE, tmVa, tmVb;
+  {
+    uint64_t dims[3] = {80, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {160, (uint64_t)p->seq_pad * 160};
+    uint32_t qa[3] = {64, 128, 1}, qb[3] = {16, 128, 1}, ka[3] = {64, 208, 1}, kb[3] = {16, 208, 1};
+    if (int e = make_tmap_bf16(&tmQa, p->q, 3, dims, str, qa, 128)) return e;
+    if (int e = make_tmap_bf16(&tmQb, p->q, 3, dims, str, qb, 32)) return e;
+    if (int e = make_tmap_bf16(&tmKa, p->k, 3, dims, str, ka, 128)) return e;
+    if (int e = make_tmap_bf16(&tmKb, p->k, 3, dims, str, kb, 32)) return e;
+  }
+  {
+    uint64_t dims[3] = {32, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {64, (uint64_t)p->seq_pad * 64};
+    uint32_t box[3] = {32, 128, 1};
+    if (int e = make_tmap_bf16(&tmQx, p->qext, 3, dims, str, box, 64)) return e;
+    uint64_t edims[2] = {32, 256};
+    uint64_t estr[1] = {64};
+    uint32_t ebox[2] = {32, 208};
+    if (int e = make_tmap_bf16(&tmE, p->kext, 2, edims, estr, ebox, 64)) return e;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p->seq_pad, 80, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)p->seq_pad * 2, (uint64_t)p->seq_pad * 160};
+    uint32_t va[3] = {64, 80, 1}, vb[3] = {16, 80, 1};
+    if (int e = make_tmap_bf16(&tmVa, p->vt, 3, dims, str, va, 128)) return e;
+    if (int e = make_tmap_bf16(&tmVb, p->vt, 3, dims, str, vb, 32)) return e;
+  }
+  AttnDev d{};
+  d.out = static_cast<bf16*>(p->out);
+  d.ldo = p->ldo;
+  d.heads = p->heads;
+  d.seq = p->seq;
+  d.seq_pad = p->seq_pad;
+  d.c1 = p->scale * LOG2E;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(attn_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int sms = num_sms_attn();
+  const int grid = BH < sms ? BH : sms;
+  attn_win_kernel<<<grid, 320, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmQx, tmKa, tmKb, tmE, tmVa, tmVb, d, BH);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
 // LLMSEG_ATTN_V2=0|1: select the two-query-tile kernel
 bool use_attn_v2() {
   static int mode = -1;
@@ -858,6 +1205,8 @@ extern "C" int llmseg_attention(const llmseg_attn_params* p, void* stream_) {
   if (hd == 64 && ext == 0) return launch_attn<64, 0>(p, stream);
   if (hd == 128 && ext == 0) return launch_attn<128, 0>(p, stream);
   if (hd == 80 && ext == 0) return launch_attn<80, 0>(p, stream);
+  if (hd == 80 && ext == 32 && p->seq >= 192 && p->seq <= 208 && p->kv_len == nullptr && use_attn_win())
+    return launch_attn_win(p, stream);
   if (hd == 80 && ext == 32) return launch_attn<80, 1>(p, stream);
   if (hd == 80 && ext == 64) return launch_attn<80, 2>(p, stream);
   return set_error(LLMSEG_ESHAPE, "llmseg_attention: unsupported head_dim=%d ext_cols=%d", hd, ext);
