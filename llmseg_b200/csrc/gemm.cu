@@ -852,19 +852,8 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   const int sms = num_sms();
   int bn = 256;
   if (p->N < 256 || m_tiles * ((p->N + 255) / 256) < sms) bn = 128;
-  if (bn == 256 && use_pair_kernel(m_tiles)) {
-    // wave quantisation of the persistent pair kernel: 74 clusters; e.g. LLaMA o_proj/down at batch 8
-    // (20 row tiles x 16 column tiles = 160 pair-tiles = 2.16 waves, 72 % efficient) do better with
-    // 128-wide tiles (320 pair-tiles = 4.3 waves, 86 %) even at the lower per-tile efficiency.
-    const int clusters = sms / 2 > 0 ? sms / 2 : 1;
-    const int pairs = (m_tiles + 1) / 2;
-    auto eff = [&](int width) {
-      const int groups = pairs * ((p->N + width - 1) / width);
-      const int waves = (groups + clusters - 1) / clusters;
-      return (double)groups / ((double)waves * clusters);
-    };
-    if (eff(128) * 0.92 > eff(256)) bn = 128;
-  }
+  // (tried: 128-wide pair tiles when 256-wide ones quantise badly, e.g. LLaMA o_proj/down at batch 8 with
+  //  2.16 waves — slower: a 256x128 pair tile needs twice the L2->SM bytes per flop and becomes L2-bound.)
   d.num_m_tiles = m_tiles;
   d.num_n_tiles = (p->N + bn - 1) / bn;
   d.num_k_blocks = (p->K + BK - 1) / BK;
