@@ -232,9 +232,14 @@ def main():
     if attn_ms:
         achieved = GF_SAM_GLOBAL_ATTN * B / attn_ms            # GFLOP / ms == TFLOP/s
         peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if B == 8 and os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("attn_global_b8", {}).get("dram_bytes")
         roof = {"kernel": "attn_kernel<80,2> (SAM global attention, 64x64 tokens, rel-pos)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained",
                 "flops_per_launch": GF_SAM_GLOBAL_ATTN * B * 1e9, "avg_launch_ms": round(attn_ms, 4),
                 "launches_timed": len(attn_events)}
     line = {

@@ -1,0 +1,35 @@
+"""Epilogue cost micro-benchmark: same GEMM shape with different fused epilogues (CUDA events, B=8 shapes)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from llmseg_b200 import ops
+dev = "cuda"; torch.manual_seed(0)
+def t(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n * 1e3
+def mk(M, N, K):
+    return torch.randn(M, K, device=dev).bfloat16(), (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16(), torch.randn(N, device=dev).bfloat16()
+M = 32768
+a, w, b = mk(M, 5120, 1280); out = torch.empty(M, 5120, device=dev, dtype=torch.bfloat16)
+for name, kw in (("none", {}), ("bias", dict(bias=b)), ("bias+relu", dict(bias=b, act="relu")), ("bias+quick_gelu", dict(bias=b, act="quick_gelu")), ("bias+gelu", dict(bias=b, act="gelu"))):
+    bias = kw.pop("bias", None)
+    us = t(lambda: ops.gemm(a, w, bias, out=out, **kw)); print(f"mlp1 32768x5120x1280 {name:16s} {us:7.1f} us  {2*M*5120*1280/us/1e6:6.0f} TF/s", flush=True)
+a, w, b = mk(M, 1280, 5120); out = torch.empty(M, 1280, device=dev, dtype=torch.bfloat16); res = torch.randn(M, 1280, device=dev).bfloat16()
+for name, kw in (("bias", dict()), ("bias+residual", dict(residual=res))):
+    us = t(lambda: ops.gemm(a, w, b, out=out, **kw)); print(f"mlp2 32768x1280x5120 {name:16s} {us:7.1f} us  {2*M*5120*1280/us/1e6:6.0f} TF/s", flush=True)
+Mw = 39200
+a, w, b = mk(Mw, 1280, 1280); x = torch.randn(M, 1280, device=dev).bfloat16()
+rmap = torch.randperm(Mw, device=dev)[:Mw].to(torch.int32); rmap = torch.where(rmap < M, rmap, torch.full_like(rmap, -1)).contiguous()
+out = torch.empty(Mw, 1280, device=dev, dtype=torch.bfloat16)
+for name, fn in (("bias", lambda: ops.gemm(a, w, b, out=out)), ("bias+residual", lambda: ops.gemm(a, w, b, residual=out, out=out)),
+                 ("bias+res+rowmap(random)", lambda: ops.gemm(a, w, b, residual=x, out=x, out_row_map=rmap))):
+    us = t(fn); print(f"proj 39200x1280x1280 {name:24s} {us:7.1f} us  {2*Mw*1280*1280/us/1e6:6.0f} TF/s", flush=True)
+# QKV split cost
+H, hd, S, Sp = 16, 80, 196, 200; nb = Mw // S
+a, w, b = mk(Mw, 3840, 1280)
+q = torch.zeros(nb * H, Sp, hd, device=dev, dtype=torch.bfloat16); k = torch.zeros_like(q); vt = torch.zeros(nb * H, hd, Sp, device=dev, dtype=torch.bfloat16)
+out = torch.empty(Mw, 3840, device=dev, dtype=torch.bfloat16)
+us = t(lambda: ops.gemm(a, w, b, out=out)); print(f"qkv 39200x3840x1280 plain store      {us:7.1f} us  {2*Mw*3840*1280/us/1e6:6.0f} TF/s")
+us = t(lambda: ops.gemm_qkv(a, w, b, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=Sp)); print(f"qkv 39200x3840x1280 split q/k/vT     {us:7.1f} us  {2*Mw*3840*1280/us/1e6:6.0f} TF/s")

@@ -1,5 +1,3 @@
-KREGEX='regex:gemm_kernel|gemm2_kernel|attn_kernel|attn_win_kernel|norm_kernel|patchify|im2col|embed_splice|add_rows|maskpool|small_attn|select_kernel'
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench10.log 2>&1; echo exit=$? >> gpurun_out/bench10.log
-LLMSEG_ATTN_WIN=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench10_nowin.log 2>&1; echo exit=$? >> gpurun_out/bench10_nowin.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 1396 -c 700 --csv --log-file gpurun_out/launches_b8.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo exit=$? >> gpurun_out/ncu_bench.log
-tail -c 400 gpurun_out/bench10.log; tail -c 400 gpurun_out/bench10_nowin.log; grep -c . gpurun_out/launches_b8.csv
+timeout 300 python scripts/gpu_gemm_epi.py > gpurun_out/gemm_epi.log 2>&1; echo exit=$? >> gpurun_out/gemm_epi.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 1 -c 1 -o gpurun_out/prof_gemm2_mlp1 python scripts/profile_kernels.py gemm_mlp1 8 2 > gpurun_out/ncu_gemm2_mlp1.log 2>&1
+cat gpurun_out/gemm_epi.log
