@@ -1,3 +1,4 @@
-timeout 300 python scripts/gpu_gemm_epi.py > gpurun_out/gemm_epi.log 2>&1; echo exit=$? >> gpurun_out/gemm_epi.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 1 -c 1 -o gpurun_out/prof_gemm2_mlp1 python scripts/profile_kernels.py gemm_mlp1 8 2 > gpurun_out/ncu_gemm2_mlp1.log 2>&1
-cat gpurun_out/gemm_epi.log
+timeout 300 python scripts/gpu_gemm_epi.py > gpurun_out/gemm_epi2.log 2>&1; echo exit=$? >> gpurun_out/gemm_epi2.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu9.log 2>&1; echo exit=$? >> gpurun_out/pytest_gpu9.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench11.log 2>&1; echo exit=$? >> gpurun_out/bench11.log
+cat gpurun_out/gemm_epi2.log; tail -3 gpurun_out/pytest_gpu9.log; tail -c 500 gpurun_out/bench11.log
