@@ -18,10 +18,18 @@ namespace {
 
 constexpr int MAX_VEC = 16;  // 16 * 32 lanes * 8 elems = 4096 max dim
 
-// NV = 16-byte vectors held per lane (1,2,4,8,16): sized to the row so narrow rows keep few registers
-// and many warps (= many loads) in flight per SM.
+// NV = 16-byte vectors held per lane, sized EXACTLY to the row (1280 -> 5, 1024 -> 4, 4096 -> 16) so
+// narrow rows keep few registers and many warps — i.e. many loads — in flight per SM (measured: the
+// 8-vector version ran LayerNorm(1280) at 3.1 TB/s against a 6.4 TB/s copy, profiles/r01i_hbm.md).
+__device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 template <bool RMS, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NV <= 5 ? 5 : (NV <= 8 ? 4 : 2)))
 norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
             const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int rows, int dim, float eps,
             const int* __restrict__ src_map) {
@@ -43,7 +51,7 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
   for (int t = 0; t < NV; ++t) {
     const int i = lane + t * 32;
     if (i < nvec) {
-      v[t] = __ldg(irow + i);
+      v[t] = ld_stream16(irow + i);
       const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -131,7 +139,9 @@ int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* ga
       static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), rows, dim, eps, src_map)
   if (per_lane <= 1) LLMSEG_NORM_LAUNCH(1);
   else if (per_lane <= 2) LLMSEG_NORM_LAUNCH(2);
+  else if (per_lane <= 3) LLMSEG_NORM_LAUNCH(3);
   else if (per_lane <= 4) LLMSEG_NORM_LAUNCH(4);
+  else if (per_lane <= 5) LLMSEG_NORM_LAUNCH(5);
   else if (per_lane <= 8) LLMSEG_NORM_LAUNCH(8);
   else LLMSEG_NORM_LAUNCH(16);
 #undef LLMSEG_NORM_LAUNCH

@@ -76,15 +76,16 @@ maskpool_adjoint_kernel(const bf16* __restrict__ segs, float* __restrict__ wt,
 }
 
 // stage 2: out[k, c] = bf16( bf16(Σ_cell wt[k,cell]·E[img(k), cell, c]) / bf16(Σ_p w[k,p]) )
-// E is token-major [B, 4096, 256] bf16 (the SAM neck output in NHWC).  grid (ceil(n_masks/8));
-// block 256 threads (one per channel); 8 masks per block must belong to one image, so the host
-// guarantees per-image mask counts are padded/visited per image via mask_image[].
+// E is token-major [B, 4096, 256] bf16 (the SAM neck output in NHWC).  The 4096-cell contraction is
+// split 8 ways over blockIdx.y (512 cells each) into fp32 partials so 8x more blocks stream E;
+// stage 3 sums the partials in a fixed order (deterministic) and normalises.
+// grid (ceil(n_masks/8), 8); block 256 threads (one per channel).
 __global__ void __launch_bounds__(256)
-maskpool_apply_kernel(const float* __restrict__ wt, const float* __restrict__ part_sum,
-                      const bf16* __restrict__ emb, const int* __restrict__ mask_image,
-                      bf16* __restrict__ out, int n_masks) {
+maskpool_apply_kernel(const float* __restrict__ wt, const bf16* __restrict__ emb,
+                      const int* __restrict__ mask_image, float* __restrict__ partial, int n_masks) {
   const int c = threadIdx.x;
   const int k0 = blockIdx.x * 8;
+  const int cell0 = blockIdx.y * 512;
   __shared__ float ws[8][512];
   float acc[8];
   int img[8];
@@ -94,37 +95,44 @@ maskpool_apply_kernel(const float* __restrict__ wt, const float* __restrict__ pa
     img[i] = (k0 + i < n_masks) ? mask_image[k0 + i] : -1;
   }
   const bool same = (img[7] == img[0] || img[7] < 0);  // fast path: one image per block
-  for (int cell0 = 0; cell0 < 4096; cell0 += 512) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 512; i += 256) {
-      const int m = i >> 9, cc = i & 511;
-      ws[m][cc] = (k0 + m < n_masks) ? wt[(size_t)(k0 + m) * 4096 + cell0 + cc] : 0.f;
-    }
-    __syncthreads();
-    if (same) {
-      const bf16* e = emb + ((size_t)img[0] * 4096 + cell0) * 256 + c;
+  for (int i = threadIdx.x; i < 8 * 512; i += 256) {
+    const int m = i >> 9, cc = i & 511;
+    ws[m][cc] = (k0 + m < n_masks) ? wt[(size_t)(k0 + m) * 4096 + cell0 + cc] : 0.f;
+  }
+  __syncthreads();
+  if (same) {
+    const bf16* e = emb + ((size_t)img[0] * 4096 + cell0) * 256 + c;
 #pragma unroll 4
-      for (int cc = 0; cc < 512; ++cc) {
-        const float ev = __bfloat162float(e[(size_t)cc * 256]);
+    for (int cc = 0; cc < 512; ++cc) {
+      const float ev = __bfloat162float(e[(size_t)cc * 256]);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) acc[m] = fmaf(ws[m][cc], ev, acc[m]);
-      }
-    } else {
-      for (int m = 0; m < 8; ++m) {
-        if (img[m] < 0) continue;
-        const bf16* e = emb + ((size_t)img[m] * 4096 + cell0) * 256 + c;
-        for (int cc = 0; cc < 512; ++cc) acc[m] = fmaf(ws[m][cc], __bfloat162float(e[(size_t)cc * 256]), acc[m]);
-      }
+      for (int m = 0; m < 8; ++m) acc[m] = fmaf(ws[m][cc], ev, acc[m]);
+    }
+  } else {
+    for (int m = 0; m < 8; ++m) {
+      if (img[m] < 0) continue;
+      const bf16* e = emb + ((size_t)img[m] * 4096 + cell0) * 256 + c;
+      for (int cc = 0; cc < 512; ++cc) acc[m] = fmaf(ws[m][cc], __bfloat162float(e[(size_t)cc * 256]), acc[m]);
     }
   }
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    if (k0 + m >= n_masks) continue;
-    float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += part_sum[(k0 + m) * 8 + i];
-    const float den = bf16_round(bf16_round(s) + 1e-8f);  // bf16 sum, +1e-8 vanishes in bf16
-    out[(size_t)(k0 + m) * 256 + c] = __float2bfloat16_rn(bf16_round(acc[m]) / den);
+  for (int m = 0; m < 8; ++m)
+    if (k0 + m < n_masks) partial[((size_t)blockIdx.y * n_masks + k0 + m) * 256 + c] = acc[m];
+}
+
+// stage 3: fixed-order sum of the 8 partials, bf16 rounding points of the reference, normalise
+__global__ void __launch_bounds__(256)
+maskpool_final_kernel(const float* __restrict__ partial, const float* __restrict__ part_sum,
+                      bf16* __restrict__ out, int n_masks) {
+  const int k = blockIdx.x, c = threadIdx.x;
+  float acc = 0.f, s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc += partial[((size_t)i * n_masks + k) * 256 + c];
+    s += part_sum[k * 8 + i];
   }
+  const float den = bf16_round(bf16_round(s) + 1e-8f);  // bf16 sum, +1e-8 vanishes in bf16
+  out[(size_t)k * 256 + c] = __float2bfloat16_rn(bf16_round(acc) / den);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -363,7 +371,7 @@ __global__ void dice_bce_final_kernel(const float* __restrict__ part, int n, flo
 using namespace llmseg;
 
 extern "C" size_t llmseg_maskpool_workspace(int n_masks) {
-  return (size_t)n_masks * (4096 + 8) * sizeof(float);
+  return (size_t)n_masks * (4096 + 8 + 8 * 256) * sizeof(float);
 }
 
 extern "C" int llmseg_maskpool(const void* segs, const void* emb, const int32_t* mask_image,
@@ -376,10 +384,13 @@ extern "C" int llmseg_maskpool(const void* segs, const void* emb, const int32_t*
   float* ps = wt + (size_t)n_masks * 4096;
   maskpool_adjoint_kernel<<<dim3(8, n_masks), 256, 0, stream>>>(static_cast<const bf16*>(segs), wt, ps);
   LLMSEG_CUDA(cudaGetLastError());
-  maskpool_apply_kernel<<<(n_masks + 7) / 8, 256, 0, stream>>>(wt, ps, static_cast<const bf16*>(emb),
-                                                               mask_image, static_cast<bf16*>(out), n_masks);
+  float* partial = ps + (size_t)n_masks * 8;
+  maskpool_apply_kernel<<<dim3((n_masks + 7) / 8, 8), 256, 0, stream>>>(wt, static_cast<const bf16*>(emb),
+                                                                        mask_image, partial, n_masks);
   LLMSEG_CUDA(cudaGetLastError());
-  g_launches.fetch_add(2);
+  maskpool_final_kernel<<<n_masks, 256, 0, stream>>>(partial, ps, static_cast<bf16*>(out), n_masks);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(3);
   return 0;
 }
 
