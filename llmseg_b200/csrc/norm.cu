@@ -23,7 +23,7 @@ constexpr int MAX_VEC = 16;  // 16 * 32 lanes * 8 elems = 4096 max dim
 // 8-vector version ran LayerNorm(1280) at 3.1 TB/s against a 6.4 TB/s copy, profiles/r01i_hbm.md).
 __device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
