@@ -72,6 +72,9 @@ typedef struct {
   const int32_t* out_row_map; /* [M] or NULL: C/residual row of GEMM row r; negative = dropped */
   /* LLMSEG_GEMM_QKV: N = 3*heads*head_dim, columns ordered (which, head, d).  GEMM row r is
    * token s = r % seq_in of sequence b = r / seq_in.
+   * With out_row_map given, GEMM row r is instead token s = m % seq_in of sequence b = m / seq_in for
+   * m = out_row_map[r] (negative = dropped): the SAM window partition (image_encoder.py:263-288)
+   * folded into the projection, so the zero padding tokens are never multiplied.
    *   q, k : bf16 [(b*heads+h), seq_pad, head_dim]
    *   vt   : bf16 [(b*heads+h), head_dim, seq_pad]          (transposed for the PV tensor-core tile)
    * rope_cos/sin: bf16 [>=seq_in, head_dim/2] rotate-half RoPE applied to q and k (LLaMA) or NULL */
@@ -116,6 +119,8 @@ typedef struct {
   const void* qext;     /* bf16 [(b*heads+h), seq_pad, ext_cols] or NULL */
   const void* kext;     /* bf16 constant, see above, or NULL            */
   const void* row_bias; /* bf16 [(b*heads+h), seq_pad, 64] (ext_cols == 64) or NULL */
+  const int32_t* out_row_map; /* int32 [batch*seq] or NULL: output row of query (b, s); negative = not
+                                 written (SAM window un-partition + crop, image_encoder.py:291-318) */
 } llmseg_attn_params;
 int llmseg_attention(const llmseg_attn_params* p, void* stream);
 
@@ -170,6 +175,11 @@ int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* attention_mask,
                         void* stream);
 int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim, int group,
                           const int32_t* row_group, void* stream);
+/* Rows of K and Vᵀ whose token is window padding: the reference pads with zeros AFTER LayerNorm, so
+ * their k, v equal the projection bias (image_encoder.py:179-185,238-242).  rows: int32 [n_rows]
+ * positions m = b*seq_in + s; bias_qkv: bf16 [3*heads*head_dim] (q | k | v). */
+int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* rows, int n_rows,
+                        int heads, int head_dim, int seq_in, int seq_pad, void* stream);
 /* 3x3 / pad-1 im2col on token-major NHWC bf16: out[(b,y,x), (ky,kx,c)]; turns the SAM neck
  * conv3x3 (image_encoder.py:100-106) into one GEMM with the weight permuted to [out,(ky,kx,c)]. */
 int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width, int channels,

@@ -38,6 +38,7 @@ class AttnParams(C.Structure):
         ("scale", c_float), ("causal", c_int),
         ("kv_len", c_void_p),
         ("ext_cols", c_int), ("qext", c_void_p), ("kext", c_void_p), ("row_bias", c_void_p),
+        ("out_row_map", c_void_p),
     ]
 
 
@@ -64,6 +65,8 @@ def _declare(lib):
                                         c_int, c_void_p]
     lib.llmseg_add_rows_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_void_p, c_void_p]
+    lib.llmseg_fill_kv_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_int, c_void_p]
     lib.llmseg_im2col3x3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.llmseg_maskpool_workspace.argtypes = [c_int]
     lib.llmseg_maskpool_workspace.restype = C.c_size_t
@@ -83,7 +86,7 @@ def _declare(lib):
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
     "llmseg_gemm", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm",
-    "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_im2col3x3",
+    "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss",
 ]

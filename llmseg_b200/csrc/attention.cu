@@ -61,6 +61,7 @@ struct AttnDev {
   int causal;
   const int* kv_len;
   const bf16* row_bias;  // [(bh), seq_pad, 64] or null
+  const int* out_row_map;  // [(batch*seq)] output row of query (b, s), negative = not written; or null
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -379,7 +380,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
     l += xsum[(half ^ 1) * 128 + row_in_tile];
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const int h = bh - b * p.heads;
-    bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
+    long long out_r = (long long)b * p.seq + q_row;
+    if (p.out_row_map != nullptr) out_r = q_row < p.seq ? p.out_row_map[out_r] : -1;
+    bf16* orow = p.out + (size_t)(out_r < 0 ? 0 : out_r) * p.ldo + h * HD;
 #pragma unroll 1
     for (int c = oc0; c < oc1; ++c) {
       uint32_t r[16];
@@ -390,7 +393,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0;
       }
-      if (q_row < p.seq) {
+      if (q_row < p.seq && out_r >= 0) {
         uint4 o0, o1;
         o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
         o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
@@ -977,13 +980,15 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
       const int b = item / p.heads, h = item - b * p.heads;
-      bf16* orow = p.out + ((size_t)b * seq + q_row) * p.ldo + h * 80;
+      long long out_r = (long long)b * seq + q_row;
+      if (p.out_row_map != nullptr) out_r = q_row < seq ? p.out_row_map[out_r] : -1;
+      bf16* orow = p.out + (size_t)(out_r < 0 ? 0 : out_r) * p.ldo + h * 80;
 #pragma unroll 1
       for (int c = 0; c < 5; ++c) {
         uint32_t r[16];
         tmem_ld16(tS + C::O_COL + c * 16, r);
         tmem_ld_wait();
-        if (q_row < seq) {
+        if (q_row < seq && out_r >= 0) {
           uint4 o0, o1;
           o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
           o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
@@ -1069,6 +1074,7 @@ int launch_attn_win(const llmseg_attn_params* p, cudaStream_t stream) {
   d.seq = p->seq;
   d.seq_pad = p->seq_pad;
   d.c1 = p->scale * LOG2E;
+  d.out_row_map = p->out_row_map;
   static bool attr_done = false;
   if (!attr_done) {
     LLMSEG_CUDA(cudaFuncSetAttribute(attn_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1140,6 +1146,7 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   d.causal = p->causal;
   d.kv_len = p->kv_len;
   d.row_bias = static_cast<const bf16*>(p->row_bias);
+  d.out_row_map = p->out_row_map;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -1149,7 +1156,7 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
     d.dbg = dbg;
   }
 
-  if (use_attn_v2()) {
+  if (use_attn_v2() && p->out_row_map == nullptr) {
     using C2 = ACfg2<HD, EXT>;
     auto kern2 = attn2_kernel<HD, EXT>;
     static bool attr2_done = false;

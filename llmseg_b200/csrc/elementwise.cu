@@ -158,10 +158,38 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__
   }
 }
 
+// k[(b*H+h), s, :] = bias_k[h], vt[(b*H+h), :, s] = bias_v[h] for the listed (b, s) positions.
+__global__ void fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __restrict__ bias,
+                                    const int* __restrict__ rows, int heads, int hd, int seq_in, int seq_pad) {
+  const int m = rows[blockIdx.x];
+  const int b = m / seq_in, s = m - b * seq_in;
+  const int hw = heads * hd;
+  for (int c = threadIdx.x; c < hw; c += blockDim.x) {
+    const int h = c / hd, d = c - h * hd;
+    const size_t bh = (size_t)b * heads + h;
+    k[(bh * seq_pad + s) * hd + d] = bias[hw + c];
+    vt[(bh * hd + d) * seq_pad + s] = bias[2 * hw + c];
+  }
+}
+
 }  // namespace
 }  // namespace llmseg
 
 using namespace llmseg;
+
+extern "C" int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* rows, int n_rows,
+                                   int heads, int head_dim, int seq_in, int seq_pad, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(k && vt && bias_qkv && rows, LLMSEG_EARG, "llmseg_fill_kv_rows: null pointer");
+  LLMSEG_REQUIRE(n_rows > 0 && heads > 0 && head_dim > 0 && seq_pad >= seq_in, LLMSEG_ESHAPE,
+                 "llmseg_fill_kv_rows: n_rows=%d heads=%d head_dim=%d", n_rows, heads, head_dim);
+  fill_kv_rows_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(k), static_cast<bf16*>(vt), static_cast<const bf16*>(bias_qkv), rows, heads,
+      head_dim, seq_in, seq_pad);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
 
 extern "C" int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width,
                                 int channels, void* stream) {

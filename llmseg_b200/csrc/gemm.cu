@@ -375,7 +375,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
                                               int n_blk, int quarter, int chalf, int lane) {
   const int row = m_blk * BM + quarter * 32 + lane;
   int out_row = row;
-  if (MODE == LLMSEG_GEMM_PLAIN && p.out_row_map != nullptr && row < p.M) out_row = p.out_row_map[row];
+  if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
+    out_row = p.out_row_map[row];  // QKV: position of this token in the (sequence, slot) index space
   const bool live = row < p.M && out_row >= 0;
   if (MODE == MODE_RELPOS) {
     relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
@@ -388,7 +389,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
       tmem_ld_wait();
       const int col = n_blk * BN + c * 128 + half * 32;
-      if (live && col < p.N) epi_qkv_rope(p, lo, hi, row, col);
+      if (live && col < p.N) epi_qkv_rope(p, lo, hi, out_row, col);
     }
   } else {
 #pragma unroll 1
@@ -402,7 +403,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (live && n0 < p.N) {
         if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0, pf);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
-        else epi_qkv(p, r, row, n0, pf);
+        else epi_qkv(p, r, out_row, n0, pf);
       }
     }
   }
@@ -851,7 +852,7 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
     LLMSEG_REQUIRE(p->heads > 0 && p->head_dim % 8 == 0 && p->N == 3 * p->heads * p->head_dim,
                    LLMSEG_ESHAPE, "llmseg_gemm(QKV): N=%d != 3*%d*%d", p->N, p->heads, p->head_dim);
     LLMSEG_REQUIRE(p->seq_in > 0 && p->seq_pad >= p->seq_in && p->seq_pad % 8 == 0 &&
-                       p->M % p->seq_in == 0,
+                       (p->out_row_map != nullptr || p->M % p->seq_in == 0),
                    LLMSEG_ESHAPE, "llmseg_gemm(QKV): M=%d seq_in=%d seq_pad=%d inconsistent", p->M,
                    p->seq_in, p->seq_pad);
     rope = p->rope_cos != nullptr;

@@ -100,8 +100,14 @@ class SamEncoder:
             y, x = wy * ws + ty, wx * ws + tx
             tok = b * (g * g) + y * g + x
             tok = torch.where((y < g) & (x < g), tok, torch.full_like(tok, -1))
-            m = tok.reshape(-1).to(torch.int32).to(self.device)
-            self._maps[B] = (m, nw * nw)
+            m = tok.reshape(-1).to(torch.int32)
+            valid = m >= 0
+            pos = torch.arange(m.numel(), dtype=torch.int32)
+            tok2win = torch.empty(B * g * g, dtype=torch.int32)
+            tok2win[m[valid].long()] = pos[valid]          # token row -> (window, slot) position
+            pad_pos = pos[~valid].contiguous()             # positions holding zero padding tokens
+            dev = self.device
+            self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev), pad_pos.to(dev))
         return self._maps[B]
 
     def forward(self, images: Tensor) -> Tensor:
@@ -113,25 +119,32 @@ class SamEncoder:
         a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
         x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S)
         del a
-        win_map, n_win = self._window_maps(B)
+        win_map, n_win, tok2win, pad_pos = self._window_maps(B)
         scale = hd ** -0.5
         for blk in self.blocks:
             if blk["window"] > 0:
                 ws = blk["window"]
                 sw, sw_pad = ws * ws, (ws * ws + 7) // 8 * 8
                 nb = B * n_win
-                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps, src_row_map=win_map, rows_out=nb * sw)
+                # The 64x64 grid pads to 70x70 for 14x14 windows (image_encoder.py:263-288): 18% of the
+                # window rows are zero tokens.  They never enter a GEMM here: LN1 and the QKV projection run
+                # on the 4096 real tokens per image and scatter into (window, slot) order; the padding keys /
+                # values equal the projection bias exactly (zero input), their queries are cropped again
+                # (image_encoder.py:291-318), and attention writes straight back in token order.
+                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
                 q = self.scratch.zeros("q", nb * H, sw_pad, hd)
                 k = self.scratch.zeros("k", nb * H, sw_pad, hd)
                 vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
-                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
+                             seq_pad=sw_pad, row_map=tok2win)
+                ops.fill_kv_rows(k, vt, blk["b_qkv"], pad_pos, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
                 ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
                                 inv_scale=1.0 / scale, qext=qext)
                 o = h  # reuse the LN output buffer for the attention output (same shape)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
-                              qext=qext, kext=self.kext_win, ext_cols=32)
-                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x, out_row_map=win_map)
+                              qext=qext, kext=self.kext_win, ext_cols=32, out_row_map=win_map)
+                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
             else:
                 h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
                 q = self.scratch.zeros("qg", B * H, S, hd)

@@ -71,8 +71,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: torch.Tensor,
              k: torch.Tensor, vt: torch.Tensor, *, heads: int, head_dim: int, seq_in: int,
              seq_pad: int, rope_cos: Optional[torch.Tensor] = None,
-             rope_sin: Optional[torch.Tensor] = None) -> None:
-    """QKV projection writing q,k [(b*heads+h), seq_pad, hd] and vt [(b*heads+h), hd, seq_pad]."""
+             rope_sin: Optional[torch.Tensor] = None, row_map: Optional[torch.Tensor] = None) -> None:
+    """QKV projection writing q,k [(b*heads+h), seq_pad, hd] and vt [(b*heads+h), hd, seq_pad].
+    row_map (int32 [M]): GEMM row r lands at position m = row_map[r] -> (b, s) = divmod(m, seq_in)."""
     _req_bf16(a, w, bias, q, k, vt, rope_cos, rope_sin)
     M, K = a.shape
     p = GemmParams()
@@ -84,14 +85,23 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: 
     p.q, p.k, p.vt = q.data_ptr(), k.data_ptr(), vt.data_ptr()
     p.heads, p.head_dim, p.seq_in, p.seq_pad = heads, head_dim, seq_in, seq_pad
     p.rope_cos, p.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
+    p.out_row_map = _ptr(row_map)
     check(_lib.lib().llmseg_gemm(C.byref(p), _stream()), "gemm_qkv")
+
+
+def fill_kv_rows(k: torch.Tensor, vt: torch.Tensor, bias_qkv: torch.Tensor, rows: torch.Tensor, *, heads: int,
+                 head_dim: int, seq_in: int, seq_pad: int) -> None:
+    """k / vt rows of window-padding tokens <- projection bias (zero tokens after LayerNorm)."""
+    _req_bf16(k, vt, bias_qkv)
+    check(_lib.lib().llmseg_fill_kv_rows(k.data_ptr(), vt.data_ptr(), bias_qkv.data_ptr(), rows.data_ptr(),
+                                         rows.numel(), heads, head_dim, seq_in, seq_pad, _stream()), "fill_kv_rows")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, batch: int,
               heads: int, head_dim: int, seq: int, seq_pad: int, scale: float, causal: bool = False,
               kv_len: Optional[torch.Tensor] = None, qext: Optional[torch.Tensor] = None,
               kext: Optional[torch.Tensor] = None, row_bias: Optional[torch.Tensor] = None,
-              ext_cols: int = 0) -> torch.Tensor:
+              ext_cols: int = 0, out_row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused attention over the q/k/vt buffers of gemm_qkv; out is [batch*seq, heads*head_dim]."""
     _req_bf16(q, k, vt, out, qext, kext, row_bias)
     p = AttnParams()
@@ -101,6 +111,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     p.scale, p.causal = float(scale), int(causal)
     p.kv_len = _ptr(kv_len)
     p.ext_cols, p.qext, p.kext, p.row_bias = ext_cols, _ptr(qext), _ptr(kext), _ptr(row_bias)
+    p.out_row_map = _ptr(out_row_map)
     check(_lib.lib().llmseg_attention(C.byref(p), _stream()), "attention")
     return out
 

@@ -189,6 +189,59 @@ def test_sam_relpos_attention(cuda_lib, grid, nb):
     assert d.abs().mean().item() <= 4e-3
 
 
+def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
+    """SAM window partition / un-partition (reference image_encoder.py:263-318) as index maps on the QKV
+    epilogue and the attention output: must equal the explicit pad -> project -> attend -> crop flow
+    bit for bit (padding tokens are zeros after LayerNorm, so their k / v are the projection bias)."""
+    from llmseg_b200 import ops
+    from llmseg_b200.encoders import SamEncoder
+    from llmseg_b200.lisa import SamCfg
+    enc = SamEncoder.__new__(SamEncoder)
+    enc.cfg, enc.device, enc._maps = SamCfg(), DEV, {}
+    B, H, hd, ws = 1, 2, 80, 14
+    D, S, sw, sw_pad = H * hd, 4096, 196, 200
+    win_map, n_win, tok2win, pad_pos = enc._window_maps(B)
+    nb = B * n_win
+    g = torch.Generator().manual_seed(7)
+    x = _bf(torch.randn(B * S, D, generator=g))
+    w = _bf(torch.randn(3 * D, D, generator=g) / D ** 0.5)
+    bias = _bf(torch.randn(3 * D, generator=g) * 0.3)
+    rel = ops.make_rel_hw(_bf(torch.randn(27, hd, generator=g) * 0.2), _bf(torch.randn(27, hd, generator=g) * 0.2))
+    kext, scale = ops.make_kext(14, DEV), hd ** -0.5
+
+    def run(folded):
+        q = torch.zeros(nb * H, sw_pad, hd, device=DEV, dtype=torch.bfloat16)
+        k, vt = torch.zeros_like(q), torch.zeros(nb * H, hd, sw_pad, device=DEV, dtype=torch.bfloat16)
+        qext = torch.zeros(nb * H, sw_pad, 32, device=DEV, dtype=torch.bfloat16)
+        if folded:
+            ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad, row_map=tok2win)
+            ops.fill_kv_rows(k, vt, bias, pad_pos, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+        else:
+            xp = torch.zeros(nb * sw, D, device=DEV, dtype=torch.bfloat16)
+            valid = win_map >= 0
+            xp[valid] = x[win_map[valid].long()]
+            ops.gemm_qkv(xp, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+        ops.relpos_prep(q, rel, bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws, inv_scale=1 / scale, qext=qext)
+        if folded:
+            out = torch.full((B * S, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+            ops.attention(q, k, vt, out, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
+                          qext=qext, kext=kext, ext_cols=32, out_row_map=win_map)
+            return k, vt, out
+        o = torch.empty(nb * sw, D, device=DEV, dtype=torch.bfloat16)
+        ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
+                      qext=qext, kext=kext, ext_cols=32)
+        out = torch.empty(B * S, D, device=DEV, dtype=torch.bfloat16)
+        valid = win_map >= 0
+        out[win_map[valid].long()] = o[valid]
+        return k, vt, out
+
+    k0, vt0, o0 = run(False)
+    k1, vt1, o1 = run(True)
+    assert torch.equal(k0, k1) and torch.equal(vt0, vt1)
+    assert not torch.isnan(o1.float()).any()
+    assert torch.equal(o0, o1)
+
+
 def test_patchify_embed_splice_im2col(cuda_lib):
     from llmseg_b200 import ops
     g = torch.Generator().manual_seed(5)
