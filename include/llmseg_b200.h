@@ -53,7 +53,8 @@ uint64_t llmseg_launch_count(void);
  *   SAM  patch-embed + pos, neck     image_encoder.py:111-113,418-426,92-108
  *   CLIP / LLaMA linears             clip_encoder.py:53-57, llava_llama.py:93-102 (transformers)
  *   mm_projector, text_hidden_fcs    llava_arch.py:35,95; LISA.py:56-65,317-318
- * Rounding follows the bf16 reference: bf16(acc+bias) → bf16(act) → bf16(+residual).
+ * The epilogue (bias, activation, residual, RoPE, SwiGLU) runs in fp32 on the fp32 accumulators and rounds
+ * to bf16 once, at the store — at least as close to the fp32 reference as its bf16 autocast rounding chain.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int M, N, K;          /* K % 8 == 0 (pad with zeros otherwise)                              */
@@ -84,8 +85,27 @@ typedef struct {
   int heads, head_dim, seq_in, seq_pad;
   const void* rope_cos;
   const void* rope_sin;
+  /* Optional scratch (NULL / 0 = none): llmseg_gemm_workspace_bytes() bytes of device memory, 256-byte
+   * aligned, ZERO-FILLED once by the caller before its first use (the library leaves its flag area zeroed
+   * after every call) and never used by two GEMMs that may run concurrently (one buffer per stream).  With
+   * it, problems whose last wave of output tiles would leave most SMs idle split that wave along K across
+   * all SMs (stream-K tail: fp32 partial tiles + flags live in the workspace). */
+  void* workspace;
+  size_t workspace_bytes;
+  /* LayerNorm / RMSNorm of the A rows folded into the GEMM (NULL = off).  With Norm(x) = (x - mean)·rstd ⊙
+   * gamma + beta and y = Norm(x)·Wᵀ + b:   y = rstd · (x · W''ᵀ) + b'   where
+   *   W''[n,:] = W[n,:] ⊙ gamma - mean_k(W[n,k]·gamma[k])   (rows centred: x - mean is orthogonal to 1, so
+   *                                                          the mean term drops out; RMSNorm: not centred)
+   *   b'[n]    = b[n] + Σ_k beta[k]·W[n,k]
+   * Pass A = x (un-normalised), W = bf16(W''), bias = bf16(b') and
+   *   row_stats : float2 [M] (mean, rstd) per A row, from llmseg_norm_stats — only rstd is used here.
+   * The epilogue multiplies the fp32 accumulators by rstd before bias / activation / RoPE / SwiGLU / the
+   * Q-K-V split.  Replaces the separate norm pass over x (reference image_encoder.py:179,191;
+   * transformers CLIPEncoderLayer / LlamaDecoderLayer norms) by a statistics-only read. */
+  const void* row_stats;
 } llmseg_gemm_params;
 int llmseg_gemm(const llmseg_gemm_params* p, void* stream);
+size_t llmseg_gemm_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused attention  softmax(scale·QKᵀ + bias + mask)·V   (flash-style, tcgen05/TMEM, TMA-fed).
@@ -148,6 +168,10 @@ int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int
 int llmseg_layernorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
                      const void* beta, int rows_out, int dim, float eps,
                      const int32_t* src_row_map, void* stream);
+/* Row statistics only: stats[r] = (mean, rstd) of row r (rms != 0: (0, rsqrt(mean(x^2) + eps))), fp32
+ * float2 [rows]; same arithmetic as llmseg_layernorm / llmseg_rmsnorm.  Feeds llmseg_gemm's row_stats. */
+int llmseg_norm_stats(const void* in, int ld_in, int rows, int dim, float eps, int rms, void* stats,
+                      void* stream);
 int llmseg_rmsnorm(const void* in, int ld_in, void* out, int ld_out, const void* gamma,
                    int rows, int dim, float eps, const int32_t* src_row_map, void* stream);
 
@@ -175,10 +199,11 @@ int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* attention_mask,
                         void* stream);
 int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim, int group,
                           const int32_t* row_group, void* stream);
-/* Rows of K and Vᵀ whose token is window padding: the reference pads with zeros AFTER LayerNorm, so
- * their k, v equal the projection bias (image_encoder.py:179-185,238-242).  rows: int32 [n_rows]
- * positions m = b*seq_in + s; bias_qkv: bf16 [3*heads*head_dim] (q | k | v). */
-int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* rows, int n_rows,
+/* K and Vᵀ entries of window padding tokens: the reference pads with zeros AFTER LayerNorm, so their
+ * k, v equal the projection bias (image_encoder.py:179-185,238-242).  pos_map: int32 [batch*seq_in],
+ * negative = padding position (the same map llmseg_attention takes as out_row_map);
+ * bias_qkv: bf16 [3*heads*head_dim] (q | k | v). */
+int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map, int batch,
                         int heads, int head_dim, int seq_in, int seq_pad, void* stream);
 /* 3x3 / pad-1 im2col on token-major NHWC bf16: out[(b,y,x), (ky,kx,c)]; turns the SAM neck
  * conv3x3 (image_encoder.py:100-106) into one GEMM with the weight permuted to [out,(ky,kx,c)]. */

@@ -27,6 +27,8 @@ class GemmParams(C.Structure):
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p),
         ("heads", c_int), ("head_dim", c_int), ("seq_in", c_int), ("seq_pad", c_int),
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
+        ("row_stats", c_void_p),
     ]
 
 
@@ -52,11 +54,13 @@ def _declare(lib):
     for name in SYMBOLS:
         getattr(lib, name)  # raises AttributeError if the .so is stale
     lib.llmseg_gemm.argtypes = [C.POINTER(GemmParams), c_void_p]
+    lib.llmseg_gemm_workspace_bytes.restype = C.c_size_t
     lib.llmseg_attention.argtypes = [C.POINTER(AttnParams), c_void_p]
     lib.llmseg_relpos_prep.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_float, c_void_p, c_int, c_void_p, c_void_p]
     lib.llmseg_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                      c_int, c_float, c_void_p, c_void_p]
+    lib.llmseg_norm_stats.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     lib.llmseg_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                                    c_float, c_void_p, c_void_p]
     lib.llmseg_patchify.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
@@ -85,7 +89,7 @@ def _declare(lib):
 # every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
-    "llmseg_gemm", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm",
+    "llmseg_gemm", "llmseg_gemm_workspace_bytes", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm", "llmseg_norm_stats",
     "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss",

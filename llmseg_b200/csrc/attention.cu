@@ -104,16 +104,19 @@ template <bool MASK>
 __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float addm, int key0, int lim,
                                                   float& lsum, uint32_t* pk, int dbg = 0) {
   float mx = -INFINITY;
+  // both 32-column loads are issued before the single wait: one TMEM round trip per tile instead of two
+  uint32_t rr[64];
+  if (dbg == 2) {
+#pragma unroll
+    for (int e = 0; e < 64; ++e) rr[e] = __float_as_uint(0.001f * (float)e);
+  } else {
+    tmem_ld32(t_s, rr);
+    tmem_ld32(t_s + 32, rr + 32);
+    tmem_ld_wait();
+  }
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    if (dbg == 2) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(0.001f * (float)(e + c));
-    } else {
-      tmem_ld32(t_s + c * 32, r);
-      tmem_ld_wait();
-    }
+    const uint32_t* r = rr + c * 32;
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
@@ -916,90 +919,118 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
       const uint32_t ph = it & 1;
       mbar_wait(&bar_s[t], ph);
       tc_fence_after();
+      // TMEM loads cost a ~300-clk round trip each; issued one per wait they were 19 serial round trips per
+      // item and dominated the tile time.  Now: pass 1 in two bulk loads, pass 2 double-buffered (the next
+      // chunk is in flight while the current one goes through the MUFU), the O read in one batch.
       // ---- pass 1: row max over the 196 valid keys ----
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 6; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
+      {
+        uint32_t r[96];
+        tmem_ld32(tS, r);
+        tmem_ld32(tS + 32, r + 32);
+        tmem_ld32(tS + 64, r + 64);
         tmem_ld_wait();
-        float mc = -INFINITY;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mc = fmaxf(mc, __uint_as_float(r[e]));
-        mx = fmaxf(mx, mc);
+        for (int e = 0; e < 96; e += 4) {
+          m0 = fmaxf(m0, __uint_as_float(r[e]));
+          m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+          m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+          m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       {
-        uint32_t r[16];
-        tmem_ld16(tS + 192, r);
+        uint32_t r[112];
+        tmem_ld32(tS + 96, r);
+        tmem_ld32(tS + 128, r + 32);
+        tmem_ld32(tS + 160, r + 64);
+        tmem_ld16(tS + 192, r + 96);
         tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 96; e += 4) {
+          m0 = fmaxf(m0, __uint_as_float(r[e]));
+          m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+          m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+          m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e)
-          if (192 + e < seq) mx = fmaxf(mx, __uint_as_float(r[e]));
+          if (192 + e < seq) m0 = fmaxf(m0, __uint_as_float(r[96 + e]));
+        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
       const float moff = -mx * c1;  // c1 > 0
       // ---- pass 2: P = exp2((s - max) * c1) -> packed bf16 over S columns [0,104) ----
-      float l = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 6; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
-        tmem_ld_wait();
+      float l0 = 0.f, l1 = 0.f;
+      auto exp_chunk = [&](const uint32_t* r, int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float p0 = ex2(fmaf(__uint_as_float(r[e]), c1, moff));
           const float p1 = ex2(fmaf(__uint_as_float(r[e + 1]), c1, moff));
-          l += p0 + p1;
+          l0 += p0;
+          l1 += p1;
           pk[e >> 1] = pack_bf16(p0, p1);
         }
-        tmem_st16(tS + c * 16, pk);
-      }
+        tmem_st16(tS + c * 16, pk);  // P chunk c lies inside S chunk c/2, already in registers
+      };
       {
-        uint32_t r[16];
-        tmem_ld16(tS + 192, r);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tS, ra);
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) {
+          tmem_ld_wait();
+          tmem_ld32(tS + (c + 1) * 32, rb);
+          exp_chunk(ra, c);
+          tmem_ld_wait();
+          if (c + 2 < 6) tmem_ld32(tS + (c + 2) * 32, ra);
+          else tmem_ld16(tS + 192, ra);
+          exp_chunk(rb, c + 1);
+        }
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {
-          const float p0 = (192 + e < seq) ? ex2(fmaf(__uint_as_float(r[e]), c1, moff)) : 0.f;
-          const float p1 = (192 + e + 1 < seq) ? ex2(fmaf(__uint_as_float(r[e + 1]), c1, moff)) : 0.f;
-          l += p0 + p1;
+          const float p0 = (192 + e < seq) ? ex2(fmaf(__uint_as_float(ra[e]), c1, moff)) : 0.f;
+          const float p1 = (192 + e + 1 < seq) ? ex2(fmaf(__uint_as_float(ra[e + 1]), c1, moff)) : 0.f;
+          l0 += p0;
+          l1 += p1;
           pk[e >> 1] = pack_bf16(p0, p1);
         }
 #pragma unroll
         for (int e = 8; e < 16; ++e) pk[e] = 0;
         tmem_st16(tS + 96, pk);  // columns [96,104) = keys 192..207, [104,112) scratch
       }
+      const float l = l0 + l1;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[t]);
 
       // ---- epilogue: O / l -> out ----
-      mbar_wait(&bar_o[t], ph);
-      tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
       const int b = item / p.heads, h = item - b * p.heads;
       long long out_r = (long long)b * seq + q_row;
       if (p.out_row_map != nullptr) out_r = q_row < seq ? p.out_row_map[out_r] : -1;
       bf16* orow = p.out + (size_t)(out_r < 0 ? 0 : out_r) * p.ldo + h * 80;
-#pragma unroll 1
-      for (int c = 0; c < 5; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tS + C::O_COL + c * 16, r);
+      mbar_wait(&bar_o[t], ph);
+      tc_fence_after();
+      {
+        uint32_t r[80];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) tmem_ld16(tS + C::O_COL + c * 16, r + c * 16);
         tmem_ld_wait();
         if (q_row < seq && out_r >= 0) {
-          uint4 o0, o1;
-          o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
-          o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
-          o0.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
-          o0.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
-          o1.x = pack_bf16(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
-          o1.y = pack_bf16(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
-          o1.z = pack_bf16(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
-          o1.w = pack_bf16(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c * 16) = o0;
-          *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
+#pragma unroll
+          for (int c = 0; c < 10; ++c) {
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(r[8 * c + 0]) * inv_l, __uint_as_float(r[8 * c + 1]) * inv_l);
+            o.y = pack_bf16(__uint_as_float(r[8 * c + 2]) * inv_l, __uint_as_float(r[8 * c + 3]) * inv_l);
+            o.z = pack_bf16(__uint_as_float(r[8 * c + 4]) * inv_l, __uint_as_float(r[8 * c + 5]) * inv_l);
+            o.w = pack_bf16(__uint_as_float(r[8 * c + 6]) * inv_l, __uint_as_float(r[8 * c + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 8) = o;
+          }
         }
       }
       tc_fence_before();

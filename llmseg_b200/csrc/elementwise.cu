@@ -158,17 +158,35 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__
   }
 }
 
-// k[(b*H+h), s, :] = bias_k[h], vt[(b*H+h), :, s] = bias_v[h] for the listed (b, s) positions.
-__global__ void fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __restrict__ bias,
-                                    const int* __restrict__ rows, int heads, int hd, int seq_in, int seq_pad) {
-  const int m = rows[blockIdx.x];
-  const int b = m / seq_in, s = m - b * seq_in;
+// One block per sequence b: every position s with pos_map[b*seq_in + s] < 0 (a window padding token) gets
+// k[(b*H+h), s, :] = bias_k[h] and vt[(b*H+h), :, s] = bias_v[h] for all heads.  Sequences without padding
+// (16 of the 25 SAM windows) exit after the flag scan; k writes are 16-byte, vt writes run along s.
+__global__ void __launch_bounds__(512)
+fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __restrict__ bias,
+                    const int* __restrict__ pos_map, int heads, int hd, int seq_in, int seq_pad) {
+  extern __shared__ unsigned char s_pad[];  // [seq_in]
+  const int b = blockIdx.x;
+  int any = 0;
+  for (int s = threadIdx.x; s < seq_in; s += blockDim.x) {
+    const unsigned char f = pos_map[(size_t)b * seq_in + s] < 0;
+    s_pad[s] = f;
+    any |= f;
+  }
+  if (!__syncthreads_or(any)) return;
   const int hw = heads * hd;
-  for (int c = threadIdx.x; c < hw; c += blockDim.x) {
-    const int h = c / hd, d = c - h * hd;
-    const size_t bh = (size_t)b * heads + h;
-    k[(bh * seq_pad + s) * hd + d] = bias[hw + c];
-    vt[(bh * hd + d) * seq_pad + s] = bias[2 * hw + c];
+  const int vec = hd >> 3;
+  for (int idx = threadIdx.x; idx < heads * seq_in * vec; idx += blockDim.x) {
+    const int v = idx % vec;
+    const int s = (idx / vec) % seq_in;
+    const int h = idx / (vec * seq_in);
+    if (s_pad[s])
+      reinterpret_cast<uint4*>(k + (((size_t)b * heads + h) * seq_pad + s) * hd)[v] =
+          __ldg(reinterpret_cast<const uint4*>(bias + hw + h * hd) + v);
+  }
+  for (int idx = threadIdx.x; idx < hw * seq_in; idx += blockDim.x) {
+    const int s = idx % seq_in;
+    const int c = idx / seq_in;  // h * hd + d
+    if (s_pad[s]) vt[((size_t)b * hw + c) * seq_pad + s] = bias[2 * hw + c];
   }
 }
 
@@ -177,14 +195,16 @@ __global__ void fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt,
 
 using namespace llmseg;
 
-extern "C" int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* rows, int n_rows,
+extern "C" int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map, int batch,
                                    int heads, int head_dim, int seq_in, int seq_pad, void* stream) {
   if (int e = check_arch()) return e;
-  LLMSEG_REQUIRE(k && vt && bias_qkv && rows, LLMSEG_EARG, "llmseg_fill_kv_rows: null pointer");
-  LLMSEG_REQUIRE(n_rows > 0 && heads > 0 && head_dim > 0 && seq_pad >= seq_in, LLMSEG_ESHAPE,
-                 "llmseg_fill_kv_rows: n_rows=%d heads=%d head_dim=%d", n_rows, heads, head_dim);
-  fill_kv_rows_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<bf16*>(k), static_cast<bf16*>(vt), static_cast<const bf16*>(bias_qkv), rows, heads,
+  LLMSEG_REQUIRE(k && vt && bias_qkv && pos_map, LLMSEG_EARG, "llmseg_fill_kv_rows: null pointer");
+  LLMSEG_REQUIRE(batch > 0 && heads > 0 && heads < 65536 && head_dim > 0 && head_dim % 8 == 0 &&
+                     seq_pad >= seq_in && seq_in > 0 && seq_in <= 32768,
+                 LLMSEG_ESHAPE, "llmseg_fill_kv_rows: batch=%d heads=%d head_dim=%d seq_in=%d seq_pad=%d", batch,
+                 heads, head_dim, seq_in, seq_pad);
+  fill_kv_rows_kernel<<<batch, 512, seq_in, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(k), static_cast<bf16*>(vt), static_cast<const bf16*>(bias_qkv), pos_map, heads,
       head_dim, seq_in, seq_pad);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);

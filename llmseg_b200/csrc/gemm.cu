@@ -20,6 +20,8 @@
 
 namespace llmseg {
 extern std::atomic<uint64_t> g_launches;
+int launch_relpos_win(const void* q, const void* rel_hw, int rows, int seq, int seq_pad, float inv_scale,
+                      void* qext, cudaStream_t stream);  // relpos.cu
 
 namespace {
 
@@ -51,6 +53,13 @@ struct GemmDev {
   bf16* rp_rh;
   int cluster;    // CTAs per cluster along M (1, 2 or 4)
   int n_fastest;  // work-item order (see kernel)
+  // stream-K tail of the CTA-pair kernel (0 = off): the last, partial wave of tiles is cut along K into
+  // one contiguous range of sk_w k-blocks per CTA pair; see gemm2_kernel.
+  // LayerNorm / RMSNorm of the A rows folded into the epilogue (see include/llmseg_b200.h: row_stats)
+  const float2* row_stats;
+  int sk_w;
+  float* sk_ws;   // fp32 partial tiles: [pair][cta rank][BN/4][128 rows] float4
+  int* sk_flags;  // [pair][cta rank]: 1 = that pair's partial is complete
 };
 
 constexpr int MODE_RELPOS = 3;
@@ -78,25 +87,53 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the bf16 rounding that follows):
-// 2 MUFU + ~10 FMA/ALU instead of libdevice erff's ~30 instructions — the GELU epilogue of the SAM
-// MLP GEMM was epilogue-bound with erff (ncu: profiles/r01_ncu_summary.md).
-__device__ __forceinline__ float fast_erf(float x) {
-  const float ax = fabsf(x);
-  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = fast_ex2(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-poly, e, 1.0f), x);
+// Packed fp32 pairs: sm_100 issues FFMA2 / FMUL2 on a 64-bit register pair (two lanes per issue slot).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// Exact-erf GELU (nn.GELU(), reference image_encoder.py:170 / common.py MLPBlock) on two values:
+// erf(z) = z * P(z^2) on |z| <= 3, clamped beyond (1 - erf(3) = 2.2e-5); P is the degree-8 least-squares
+// fit on Chebyshev nodes, |erf error| < 2.7e-5, |GELU error| < 5.6e-5 absolute — below the bf16 rounding
+// that follows for every |GELU| > 0.015.  Pure FMA-pipe work (13 packed instructions per pair): the
+// A&S 7.1.26 form it replaces spent 2 MUFU per element and made the SAM MLP GEMM epilogue-bound
+// (profiles/r01h_gemm_epilogue_costs.md).
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 z = fmul2(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 zc = make_float2(fminf(fmaxf(z.x, -3.0f), 3.0f), fminf(fmaxf(z.y, -3.0f), 3.0f));
+  const float2 u = fmul2(zc, zc);
+  float2 q = make_float2(4.071986126e-08f, 4.071986126e-08f);
+  q = ffma2(q, u, make_float2(-1.945750910e-06f, -1.945750910e-06f));
+  q = ffma2(q, u, make_float2(4.110950977e-05f, 4.110950977e-05f));
+  q = ffma2(q, u, make_float2(-5.118074478e-04f, -5.118074478e-04f));
+  q = ffma2(q, u, make_float2(4.241328686e-03f, 4.241328686e-03f));
+  q = ffma2(q, u, make_float2(-2.512698807e-02f, -2.512698807e-02f));
+  q = ffma2(q, u, make_float2(1.111308783e-01f, 1.111308783e-01f));
+  q = ffma2(q, u, make_float2(-3.753655851e-01f, -3.753655851e-01f));
+  q = ffma2(q, u, make_float2(1.128284454e+00f, 1.128284454e+00f));
+  const float2 e = fmul2(zc, q);
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, e, hx);
 }
 __device__ __forceinline__ float fast_sigmoid(float x) {
   return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
 }
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == LLMSEG_ACT_GELU) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
   if (act == LLMSEG_ACT_QUICK_GELU) return x * fast_sigmoid(1.702f * x);
   if (act == LLMSEG_ACT_RELU) return fmaxf(x, 0.0f);
   return x;
@@ -148,11 +185,16 @@ __device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, i
         v[2 * e + 1] += f.y;
       }
     }
+    if (p.act == LLMSEG_ACT_GELU) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = bf16_round(v[e]);
-    if (p.act != LLMSEG_ACT_NONE) {
+      for (int e = 0; e < 8; e += 2) {
+        const float2 g = gelu2(make_float2(v[e], v[e + 1]));
+        v[e] = g.x;
+        v[e + 1] = g.y;
+      }
+    } else if (p.act != LLMSEG_ACT_NONE) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = bf16_round(apply_act(v[e], p.act));
+      for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e], p.act);
     }
     if (p.residual) {
       const uint4 b = pf.res[j >> 3];
@@ -182,10 +224,9 @@ __device__ __forceinline__ void epi_swiglu(const GemmDev& p, const uint32_t* r, 
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float g = bf16_round(__uint_as_float(r[j + 2 * e]));
-      const float u = bf16_round(__uint_as_float(r[j + 2 * e + 1]));
-      const float a = bf16_round(g * fast_sigmoid(g));
-      o[e] = a * u;
+      const float g = __uint_as_float(r[j + 2 * e]);
+      const float u = __uint_as_float(r[j + 2 * e + 1]);
+      o[e] = g * fast_sigmoid(g) * u;
     }
     uint4 w;
     w.x = pack_bf16(o[0], o[1]);
@@ -347,11 +388,11 @@ __device__ __forceinline__ void epi_qkv_rope(const GemmDev& p, const uint32_t* l
       const float cc[2] = {c.x, c.y}, ss[2] = {sn2.x, sn2.y};
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const float x1 = bf16_round(__uint_as_float(lo[j + 2 * e + t]));
-        const float x2 = bf16_round(__uint_as_float(hi[j + 2 * e + t]));
-        // q*cos + rotate_half(q)*sin with bf16 rounding of each product, as the bf16 reference does
-        ol[2 * e + t] = bf16_round(x1 * cc[t]) + bf16_round(-x2 * ss[t]);
-        oh[2 * e + t] = bf16_round(x2 * cc[t]) + bf16_round(x1 * ss[t]);
+        const float x1 = __uint_as_float(lo[j + 2 * e + t]);
+        const float x2 = __uint_as_float(hi[j + 2 * e + t]);
+        // q*cos + rotate_half(q)*sin in fp32, rounded once at the store
+        ol[2 * e + t] = fmaf(x1, cc[t], -x2 * ss[t]);
+        oh[2 * e + t] = fmaf(x2, cc[t], x1 * ss[t]);
       }
     }
     uint4 o;
@@ -368,16 +409,114 @@ __device__ __forceinline__ void epi_qkv_rope(const GemmDev& p, const uint32_t* l
   }
 }
 
+// ---- stream-K tail helpers (CTA-pair kernel) --------------------------------------------------
+// Work of one CTA pair = `full` whole tiles (grp = pair, pair + n_pairs, ...) followed, when sk_w > 0, by
+// the k-block range [pair*sk_w, (pair+1)*sk_w) of the linearised (tail tile, k-block) space.  A range
+// touches at most two tiles (sk_w < num_k_blocks): the end of one tile (a PARTIAL segment: its fp32
+// accumulators go to the workspace) and the start of the next (the OWNER segment: it adds the partials of
+// the pairs that follow and runs the real epilogue).  Producers never wait, owners wait only on
+// higher-numbered pairs, so the scheme cannot deadlock however the grid is scheduled.
+struct SkSeg {
+  int grp, k0, k1;
+  int n_peers;  // owner: number of partial segments to fold in (pairs pair+1 .. pair+n_peers)
+};
+struct SkWalk {
+  int full_end, pos, end, kb, w;
+  __device__ SkWalk(const GemmDev& p, int num_groups, int pair, int n_pairs) {
+    kb = p.num_k_blocks;
+    w = p.sk_w;
+    if (w > 0) {
+      full_end = (num_groups / n_pairs) * n_pairs;
+      const int total = (num_groups - full_end) * kb;
+      pos = pair * w < total ? pair * w : total;
+      end = pos + w < total ? pos + w : total;
+    } else {
+      full_end = num_groups;
+      pos = end = 0;
+    }
+  }
+  // next tail segment of this pair, false when done
+  __device__ bool next(SkSeg& sgm) {
+    if (pos >= end) return false;
+    const int t = pos / kb;
+    sgm.grp = full_end + t;
+    sgm.k0 = pos - t * kb;
+    const int left = end - pos;
+    sgm.k1 = sgm.k0 + left < kb ? sgm.k0 + left : kb;
+    sgm.n_peers = 0;
+    if (sgm.k0 == 0 && sgm.k1 < kb) sgm.n_peers = ((t + 1) * kb - 1) / w - pos / w;
+    pos += sgm.k1 - sgm.k0;
+    return true;
+  }
+};
+__device__ __forceinline__ float* sk_slot(const GemmDev& p, int bn, int pair, int cta_rank) {
+  return p.sk_ws + ((size_t)pair * 2 + cta_rank) * (size_t)(128 * bn);
+}
+// acc[0..32) += partial columns [c0, c0+32) of this thread's row, for every peer
+__device__ __forceinline__ void sk_accumulate(const GemmDev& p, int bn, uint32_t* r, int c0, int row_in_cta,
+                                              int pair, int cta_rank, int n_peers) {
+  // two peers per round: 16 independent 16-byte loads in flight hide most of the L2 round trip
+  for (int pr = 1; pr <= n_peers; pr += 2) {
+    const bool two = pr + 1 <= n_peers;
+    const float4* ws0 = reinterpret_cast<const float4*>(sk_slot(p, bn, pair + pr, cta_rank)) +
+                        (size_t)(c0 >> 2) * 128 + row_in_cta;
+    const float4* ws1 = reinterpret_cast<const float4*>(sk_slot(p, bn, pair + pr + (two ? 1 : 0), cta_rank)) +
+                        (size_t)(c0 >> 2) * 128 + row_in_cta;
+    float4 f0[8], f1[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) f0[v] = __ldcg(ws0 + v * 128);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) f1[v] = two ? __ldcg(ws1 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      r[4 * v + 0] = __float_as_uint(__uint_as_float(r[4 * v + 0]) + f0[v].x + f1[v].x);
+      r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + f0[v].y + f1[v].y);
+      r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + f0[v].z + f1[v].z);
+      r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + f0[v].w + f1[v].w);
+    }
+  }
+}
+// partial segment: this warp's share (32 rows x half the columns) of the fp32 accumulators -> workspace
+template <int BN>
+__device__ __forceinline__ void sk_dump(const GemmDev& p, uint32_t taddr, int quarter, int chalf, int lane,
+                                        int pair, int cta_rank) {
+  float4* ws = reinterpret_cast<float4*>(sk_slot(p, BN, pair, cta_rank)) + quarter * 32 + lane;
+#pragma unroll 1
+  for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+      ws[(size_t)(c * 8 + v) * 128] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                  __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+  }
+}
+// Row normalisation of A folded into the GEMM: acc is x·W''ᵀ for the un-normalised rows x, and
+// Norm(x)·Wᵀ = rstd · acc (+ bias') — see include/llmseg_b200.h (row_stats).
+__device__ __forceinline__ void row_scale(uint32_t* r, float rs) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * rs);
+}
+
+struct SkOwner {
+  int pair, cta_rank, n_peers;  // n_peers == 0: ordinary tile
+};
+
 // One warp's share of a finished 128 x BN accumulator tile: quarter = TMEM lane quarter (32 rows),
 // chalf = which half of the tile's columns.
 template <int BN, int MODE, bool ROPE>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage, uint32_t taddr, int m_blk,
-                                              int n_blk, int quarter, int chalf, int lane) {
+                                              int n_blk, int quarter, int chalf, int lane,
+                                              const SkOwner sk = SkOwner{0, 0, 0}) {
   const int row = m_blk * BM + quarter * 32 + lane;
   int out_row = row;
   if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
     out_row = p.out_row_map[row];  // QKV: position of this token in the (sequence, slot) index space
   const bool live = row < p.M && out_row >= 0;
+  float rs = 1.f;
+  const bool fold = MODE != MODE_RELPOS && p.row_stats != nullptr;
+  if (fold && row < p.M) rs = __ldg(p.row_stats + row).y;
   if (MODE == MODE_RELPOS) {
     relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
   } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
@@ -388,7 +527,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       tmem_ld32(taddr + c * 128 + half * 32, lo);
       tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
       tmem_ld_wait();
+      if (sk.n_peers > 0) {
+        sk_accumulate(p, BN, lo, c * 128 + half * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
+        sk_accumulate(p, BN, hi, c * 128 + half * 32 + 64, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
+      }
       const int col = n_blk * BN + c * 128 + half * 32;
+      if (fold) {
+        row_scale(lo, rs);
+        row_scale(hi, rs);
+      }
       if (live && col < p.N) epi_qkv_rope(p, lo, hi, out_row, col);
     }
   } else {
@@ -400,6 +547,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       EpiPrefetch pf;
       if (MODE != LLMSEG_GEMM_SWIGLU) epi_prefetch(p, pf, MODE == LLMSEG_GEMM_PLAIN ? out_row : 0, n0, live);
       tmem_ld_wait();
+      if (sk.n_peers > 0) sk_accumulate(p, BN, r, c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
+      if (fold) row_scale(r, rs);
       if (live && n0 < p.N) {
         if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0, pf);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
@@ -630,10 +779,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
-        const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * 2 + cta_rank;
-        const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      SkWalk walk(p, num_groups, cluster_id, num_clusters);
+      SkSeg sg;
+      for (int grp = cluster_id;; grp += num_clusters) {
+        int k0 = 0, k1 = p.num_k_blocks;
+        int g = grp;
+        if (grp >= walk.full_end) {
+          if (!walk.next(sg)) break;
+          g = sg.grp; k0 = sg.k0; k1 = sg.k1;
+        }
+        const int m_blk = (n_fastest ? g / p.num_n_tiles : g % m_groups) * 2 + cta_rank;
+        const int n_blk = n_fastest ? g % p.num_n_tiles : g / m_groups;
+        for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -655,11 +812,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      SkWalk walk(p, num_groups, cluster_id, num_clusters);
+      SkSeg sg;
+      for (int grp = cluster_id;; grp += num_clusters) {
+        int k0 = 0, k1 = p.num_k_blocks;
+        if (grp >= walk.full_end) {
+          if (!walk.next(sg)) break;
+          k0 = sg.k0; k1 = sg.k1;
+        }
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -668,10 +832,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * 32, 1024, UMMA_SW128);
             const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
-            umma2_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_ss(d_tmem, da, db, idesc, (kb != k0 || k != 0) ? 1u : 0u);
           }
           umma2_commit_mcast(&empty_bar[stage], 3);  // frees the slot in both CTAs
-          if (kb == p.num_k_blocks - 1) umma2_commit_mcast(&tmem_full[as], 3);
+          if (kb == k1 - 1) umma2_commit_mcast(&tmem_full[as], 3);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -688,13 +852,54 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int chalf = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
-      const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * 2 + cta_rank;
-      const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
+    SkWalk walk(p, num_groups, cluster_id, num_clusters);
+    SkSeg sg;
+    for (int grp = cluster_id;; grp += num_clusters) {
+      int g = grp;
+      bool partial = false;
+      SkOwner own{cluster_id, cta_rank, 0};
+      if (grp >= walk.full_end) {
+        if (!walk.next(sg)) break;
+        g = sg.grp;
+        partial = sg.k0 > 0;
+        own.n_peers = sg.n_peers;
+      }
+      const int m_blk = (n_fastest ? g / p.num_n_tiles : g % m_groups) * 2 + cta_rank;
+      const int n_blk = n_fastest ? g % p.num_n_tiles : g / m_groups;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      epilogue_tile<BN, MODE, ROPE>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane);
+      if (partial) {
+        // fp32 accumulators -> workspace, then publish (all 256 epilogue threads have fenced their stores)
+        sk_dump<BN>(p, taddr, quarter, chalf, lane, cluster_id, cta_rank);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 4 && lane == 0) {
+          int* flag = p.sk_flags + cluster_id * 2 + cta_rank;
+          asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+        }
+      } else {
+        if (own.n_peers > 0) {
+          if (warp == 4 && lane == 0) {
+            for (int pr = 1; pr <= own.n_peers; ++pr) {
+              const int* flag = p.sk_flags + (cluster_id + pr) * 2 + cta_rank;
+              int v = 0;
+              long long spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (++spins > (1ll << 22)) __trap();  // a lost producer must not hang the device
+              } while (v == 0);
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        epilogue_tile<BN, MODE, ROPE>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, own);
+        if (own.n_peers > 0) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // every reader of the partials is done
+          if (warp == 4 && lane == 0)
+            for (int pr = 1; pr <= own.n_peers; ++pr) p.sk_flags[(cluster_id + pr) * 2 + cta_rank] = 0;
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
@@ -806,6 +1011,28 @@ int pick_grid(int groups, int cl, int sms) {
   return clusters * cl;
 }
 
+// LLMSEG_GEMM_STREAMK=0 disables the stream-K tail (A/B measurements)
+bool streamk_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_GEMM_STREAMK");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
+// LLMSEG_RELPOS_WIN=0 routes the 14x14-window rel-pos prep through the generic GEMM kernel again
+bool relpos_win_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_RELPOS_WIN");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
+constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_MAX_PAIRS = 128;
+constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + SK_MAX_PAIRS * 2 * 128 * 256 * sizeof(float);
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -845,6 +1072,10 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   d.heads = p->heads; d.head_dim = p->head_dim; d.seq_in = p->seq_in; d.seq_pad = p->seq_pad;
   d.rope_cos = static_cast<const bf16*>(p->rope_cos);
   d.rope_sin = static_cast<const bf16*>(p->rope_sin);
+  d.row_stats = static_cast<const float2*>(p->row_stats);
+  if (p->row_stats != nullptr)
+    LLMSEG_REQUIRE((reinterpret_cast<uintptr_t>(p->row_stats) & 7) == 0, LLMSEG_EALIGN,
+                   "llmseg_gemm: row_stats must be 8-byte aligned (float2 per row)");
 
   bool rope = false;
   if (p->mode == LLMSEG_GEMM_QKV) {
@@ -903,7 +1134,26 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
 
   if (use_pair_kernel(m_tiles)) {
     d.cluster = 2;
-    const int pgrid = pick_grid(((m_tiles + 1) / 2) * d.num_n_tiles, 2, sms);
+    const int groups = ((m_tiles + 1) / 2) * d.num_n_tiles;
+    int pgrid = pick_grid(groups, 2, sms);
+    // stream-K tail: when the last wave holds `rem` < n_pairs tiles, cut it along K into one range of
+    // sk_w k-blocks per pair — worth it when that shortens the wave by >= 12 k-blocks (the fp32 partial
+    // round trip through L2 costs about 6-8) and the ranges stay >= 4 k-blocks long.
+    const int n_pairs = sms / 2;
+    if (streamk_enabled() && p->workspace != nullptr && p->workspace_bytes >= SK_WS_BYTES &&
+        (size_t)n_pairs <= SK_MAX_PAIRS && (reinterpret_cast<uintptr_t>(p->workspace) & 255) == 0) {
+      const int rem = groups % n_pairs;
+      const int kb = d.num_k_blocks;
+      // at most ~4 segments per tile: every extra partial is another 128 KB round trip for the owner
+      int w = (rem * kb + n_pairs - 1) / n_pairs;
+      if (w < (kb + 3) / 4) w = (kb + 3) / 4;
+      if (rem > 0 && kb >= 32 && kb - w >= 16) {
+        d.sk_w = w;
+        d.sk_flags = static_cast<int*>(p->workspace);
+        d.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(p->workspace) + SK_FLAG_BYTES);
+        pgrid = n_pairs * 2;
+      }
+    }
     uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     uint64_t str[1] = {(uint64_t)p->ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)(bn / 2)};
@@ -940,6 +1190,8 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
 #undef LLMSEG_GEMM_DISPATCH
 }
 
+extern "C" size_t llmseg_gemm_workspace_bytes(void) { return SK_WS_BYTES; }
+
 extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int seq,
                                   int seq_pad, int head_dim, int grid, float inv_scale, void* qext,
                                   int ext_cols, void* row_bias, void* stream_) {
@@ -953,6 +1205,8 @@ extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, 
   LLMSEG_REQUIRE((row_bias == nullptr && ext_cols == 32 && 2 * grid <= 32) ||
                      (row_bias != nullptr && ext_cols == 64 && grid <= 64),
                  LLMSEG_ESHAPE, "llmseg_relpos_prep: ext_cols=%d inconsistent with grid=%d", ext_cols, grid);
+  if (row_bias == nullptr && grid == 14 && head_dim == 80 && relpos_win_enabled())
+    return launch_relpos_win(q, rel_hw, bh * seq_pad, seq, seq_pad, inv_scale, qext, stream);
   GemmDev d{};
   d.M = bh * seq_pad; d.N = n_pad; d.K = head_dim;
   d.rp_grid = grid; d.rp_seq = seq; d.rp_seq_pad = seq_pad; d.rp_ext = ext_cols;

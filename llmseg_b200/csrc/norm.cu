@@ -32,7 +32,7 @@ template <bool RMS, int NV>
 __global__ void __launch_bounds__(256, (NV <= 5 ? 5 : (NV <= 8 ? 4 : 2)))
 norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
             const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int rows, int dim, float eps,
-            const int* __restrict__ src_map) {
+            const int* __restrict__ src_map, float2* __restrict__ stats) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -40,7 +40,7 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
   int src = warp;
   if (src_map) src = src_map[warp];
   uint4* orow = reinterpret_cast<uint4*>(out + (size_t)warp * ld_out);
-  if (src < 0) {
+  if (src < 0 && stats == nullptr) {
     for (int i = lane; i < nvec; i += 32) orow[i] = make_uint4(0, 0, 0, 0);
     return;
   }
@@ -87,6 +87,11 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
     sq = warp_sum(sq);
     rstd = rsqrtf(sq * inv_n + eps);
   }
+  if (stats != nullptr) {
+    // statistics only: the normalisation itself is folded into the consuming GEMM (llmseg_gemm row_stats)
+    if (lane == 0) stats[warp] = make_float2(mean, rstd);
+    return;
+  }
   const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
   const uint4* b4 = reinterpret_cast<const uint4*>(beta);
 #pragma unroll
@@ -120,9 +125,10 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
 
 template <bool RMS>
 int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* gamma, const void* beta,
-                int rows, int dim, float eps, const int32_t* src_map, cudaStream_t stream) {
+                int rows, int dim, float eps, const int32_t* src_map, cudaStream_t stream,
+                float2* stats = nullptr) {
   if (int e = check_arch()) return e;
-  LLMSEG_REQUIRE(in && out && gamma, LLMSEG_EARG, "norm: null pointer");
+  LLMSEG_REQUIRE(in && (stats || (out && gamma)), LLMSEG_EARG, "norm: null pointer");
   LLMSEG_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && dim <= MAX_VEC * 256, LLMSEG_ESHAPE,
                  "norm: rows=%d dim=%d unsupported (dim %% 8 == 0, dim <= %d)", rows, dim,
                  MAX_VEC * 256);
@@ -136,7 +142,7 @@ int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* ga
 #define LLMSEG_NORM_LAUNCH(NV_)                                                              \
   norm_kernel<RMS, NV_><<<blocks, warps_per_block * 32, 0, stream>>>(                        \
       static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out,                  \
-      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), rows, dim, eps, src_map)
+      static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), rows, dim, eps, src_map, stats)
   if (per_lane <= 1) LLMSEG_NORM_LAUNCH(1);
   else if (per_lane <= 2) LLMSEG_NORM_LAUNCH(2);
   else if (per_lane <= 3) LLMSEG_NORM_LAUNCH(3);
@@ -164,4 +170,16 @@ extern "C" int llmseg_rmsnorm(const void* in, int ld_in, void* out, int ld_out, 
                               int rows, int dim, float eps, const int32_t* src_row_map, void* stream) {
   return llmseg::launch_norm<true>(in, ld_in, out, ld_out, gamma, nullptr, rows, dim, eps,
                                    src_row_map, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int llmseg_norm_stats(const void* in, int ld_in, int rows, int dim, float eps, int rms, void* stats,
+                                 void* stream) {
+  LLMSEG_REQUIRE(stats != nullptr && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, LLMSEG_EARG,
+                 "llmseg_norm_stats: stats must be a non-null, 8-byte aligned float2 array");
+  float2* st = static_cast<float2*>(stats);
+  if (rms)
+    return llmseg::launch_norm<true>(in, ld_in, nullptr, 8, nullptr, nullptr, rows, dim, eps, nullptr,
+                                     static_cast<cudaStream_t>(stream), st);
+  return llmseg::launch_norm<false>(in, ld_in, nullptr, 8, nullptr, nullptr, rows, dim, eps, nullptr,
+                                    static_cast<cudaStream_t>(stream), st);
 }

@@ -19,8 +19,14 @@ import torch
 
 from . import ops
 
+import os
+
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
+# LayerNorm / RMSNorm in front of a projection is folded into that GEMM (ops.fold_norm + ops.norm_stats):
+# the norm pass over the residual stream becomes a statistics-only read.  LLMSEG_FOLD_NORM=0 keeps the
+# separate norm kernels (the reference's literal op order) for A/B runs.
+FOLD_NORM = os.environ.get("LLMSEG_FOLD_NORM", "1") != "0"
 
 
 def _dev(t: Tensor, device) -> Tensor:
@@ -40,6 +46,15 @@ class _Scratch:
         buf = self._bufs.get(key)
         if buf is None:
             buf = torch.zeros(shape, dtype=BF16, device=self.device)
+            self._bufs[key] = buf
+        return buf
+
+    def stats(self, rows: int) -> Tensor:
+        """fp32 [rows, 2] row-statistics buffer (ops.norm_stats -> ops.gemm(row_stats=...))."""
+        key = ("stats", rows)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.empty((rows, 2), dtype=torch.float32, device=self.device)
             self._bufs[key] = buf
         return buf
 
@@ -65,7 +80,7 @@ class SamEncoder:
         self.blocks = []
         for i in range(cfg.depth):
             bp = f"blocks.{i}."
-            self.blocks.append(dict(
+            blk = dict(
                 window=0 if i in cfg.global_attn_indexes else cfg.window_size,
                 ln1_w=d(bp + "norm1.weight"), ln1_b=d(bp + "norm1.bias"),
                 ln2_w=d(bp + "norm2.weight"), ln2_b=d(bp + "norm2.bias"),
@@ -74,7 +89,14 @@ class SamEncoder:
                 rel_hw=ops.make_rel_hw(d(bp + "attn.rel_pos_h"), d(bp + "attn.rel_pos_w")),
                 w1=d(bp + "mlp.lin1.weight"), b1=d(bp + "mlp.lin1.bias"),
                 w2=d(bp + "mlp.lin2.weight"), b2=d(bp + "mlp.lin2.bias"),
-            ))
+            )
+            if FOLD_NORM:
+                blk["f_qkv"] = ops.fold_norm(blk["w_qkv"], blk["ln1_w"], blk["ln1_b"], blk["b_qkv"])
+                blk["f_1"] = ops.fold_norm(blk["w1"], blk["ln2_w"], blk["ln2_b"], blk["b1"])
+                # the padding keys/values of a window are the projection of a zero token = the bias, in bf16
+                blk["b_qkv_pad"] = blk["b_qkv"]
+                del blk["w_qkv"], blk["w1"]
+            self.blocks.append(blk)
         self.w_neck1 = d("neck.0.weight").reshape(cfg.out_chans, D).contiguous()
         self.ln_n1 = (d("neck.1.weight"), d("neck.1.bias"))
         # conv3x3 weight [out, in, ky, kx] -> [out, (ky, kx, in)] to match im2col3x3's column order
@@ -105,9 +127,8 @@ class SamEncoder:
             pos = torch.arange(m.numel(), dtype=torch.int32)
             tok2win = torch.empty(B * g * g, dtype=torch.int32)
             tok2win[m[valid].long()] = pos[valid]          # token row -> (window, slot) position
-            pad_pos = pos[~valid].contiguous()             # positions holding zero padding tokens
             dev = self.device
-            self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev), pad_pos.to(dev))
+            self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev))
         return self._maps[B]
 
     def forward(self, images: Tensor) -> Tensor:
@@ -119,7 +140,7 @@ class SamEncoder:
         a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
         x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S)
         del a
-        win_map, n_win, tok2win, pad_pos = self._window_maps(B)
+        win_map, n_win, tok2win = self._window_maps(B)
         scale = hd ** -0.5
         for blk in self.blocks:
             if blk["window"] > 0:
@@ -131,38 +152,57 @@ class SamEncoder:
                 # on the 4096 real tokens per image and scatter into (window, slot) order; the padding keys /
                 # values equal the projection bias exactly (zero input), their queries are cropped again
                 # (image_encoder.py:291-318), and attention writes straight back in token order.
-                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
                 q = self.scratch.zeros("q", nb * H, sw_pad, hd)
                 k = self.scratch.zeros("k", nb * H, sw_pad, hd)
                 vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
-                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
-                             seq_pad=sw_pad, row_map=tok2win)
-                ops.fill_kv_rows(k, vt, blk["b_qkv"], pad_pos, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+                if FOLD_NORM:
+                    st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
+                    wq, bq = blk["f_qkv"]
+                    ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
+                                 row_map=tok2win, row_stats=st)
+                    o = self.scratch.zeros("o", B * S, D)
+                else:
+                    h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
+                    ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
+                                 seq_pad=sw_pad, row_map=tok2win)
+                    o = h  # reuse the LN output buffer for the attention output (same shape)
+                ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
                 ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
                                 inv_scale=1.0 / scale, qext=qext)
-                o = h  # reuse the LN output buffer for the attention output (same shape)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
                               qext=qext, kext=self.kext_win, ext_cols=32, out_row_map=win_map)
                 ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
             else:
-                h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
                 q = self.scratch.zeros("qg", B * H, S, hd)
                 k = self.scratch.zeros("kg", B * H, S, hd)
                 vt = self.scratch.zeros("vtg", B * H, hd, S)
                 qext = self.scratch.zeros("qext_g", B * H, S, 64)
                 rb = self.scratch.zeros("rb_g", B * H, S, 64)
-                ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S)
+                if FOLD_NORM:
+                    st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
+                    wq, bq = blk["f_qkv"]
+                    ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S, row_stats=st)
+                    o = self.scratch.zeros("o", B * S, D)
+                else:
+                    h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
+                    ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S)
+                    o = h
                 ops.relpos_prep(q, blk["rel_hw"], bh=B * H, seq=S, seq_pad=S, head_dim=hd, grid=g,
                                 inv_scale=1.0 / scale, qext=qext, row_bias=rb)
-                o = h
                 ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale,
                               qext=qext, kext=self.kext_glb, row_bias=rb, ext_cols=64)
                 ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
-            h = ops.layernorm(x, blk["ln2_w"], blk["ln2_b"], cfg.ln_eps)
-            m = ops.gemm(h, blk["w1"], blk["b1"], act="gelu")
+            if FOLD_NORM:
+                st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
+                w1, b1 = blk["f_1"]
+                m = ops.gemm(x, w1, b1, act="gelu", row_stats=st)
+            else:
+                h = ops.layernorm(x, blk["ln2_w"], blk["ln2_b"], cfg.ln_eps)
+                m = ops.gemm(h, blk["w1"], blk["b1"], act="gelu")
+                del h
             ops.gemm(m, blk["w2"], blk["b2"], residual=x, out=x)
-            del h, m
+            del m
         y = ops.gemm(x, self.w_neck1)
         y = ops.layernorm(y, self.ln_n1[0], self.ln_n1[1], 1e-6)
         y = ops.im2col3x3(y, B, g, g)
@@ -195,7 +235,7 @@ class ClipTower:
         self.layers = []
         for i in range(n_run):
             lp = f"encoder.layers.{i}."
-            self.layers.append(dict(
+            L = dict(
                 ln1=(d(lp + "layer_norm1.weight"), d(lp + "layer_norm1.bias")),
                 ln2=(d(lp + "layer_norm2.weight"), d(lp + "layer_norm2.bias")),
                 w_qkv=torch.cat([d(lp + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
@@ -203,7 +243,12 @@ class ClipTower:
                 w_o=d(lp + "self_attn.out_proj.weight"), b_o=d(lp + "self_attn.out_proj.bias"),
                 w1=d(lp + "mlp.fc1.weight"), b1=d(lp + "mlp.fc1.bias"),
                 w2=d(lp + "mlp.fc2.weight"), b2=d(lp + "mlp.fc2.bias"),
-            ))
+            )
+            if FOLD_NORM:
+                L["f_qkv"] = ops.fold_norm(L["w_qkv"], L["ln1"][0], L["ln1"][1], L["b_qkv"])
+                L["f_1"] = ops.fold_norm(L["w1"], L["ln2"][0], L["ln2"][1], L["b1"])
+                del L["w_qkv"], L["w1"]
+            self.layers.append(L)
         self.proj_w, self.proj_b = _dev(proj_w, device), _dev(proj_b, device)
         self.scratch = _Scratch(device)
         self._drop_cls: Dict[int, Tensor] = {}
@@ -230,12 +275,23 @@ class ClipTower:
         k = self.scratch.zeros("k", N * H, T_pad, hd)
         vt = self.scratch.zeros("vt", N * H, hd, T_pad)
         for L in self.layers:
-            h = ops.layernorm(x, L["ln1"][0], L["ln1"][1], cfg.eps)
-            ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
+            if FOLD_NORM:
+                st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T))
+                wq, bq = L["f_qkv"]
+                ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad, row_stats=st)
+                h = self.scratch.zeros("o", N * T, D)
+            else:
+                h = ops.layernorm(x, L["ln1"][0], L["ln1"][1], cfg.eps)
+                ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
             ops.attention(q, k, vt, h, batch=N, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
             ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x)
-            h = ops.layernorm(x, L["ln2"][0], L["ln2"][1], cfg.eps)
-            m = ops.gemm(h, L["w1"], L["b1"], act="quick_gelu")
+            if FOLD_NORM:
+                st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T))
+                w1, b1 = L["f_1"]
+                m = ops.gemm(x, w1, b1, act="quick_gelu", row_stats=st)
+            else:
+                h = ops.layernorm(x, L["ln2"][0], L["ln2"][1], cfg.eps)
+                m = ops.gemm(h, L["w1"], L["b1"], act="quick_gelu")
             ops.gemm(m, L["w2"], L["b2"], residual=x, out=x)
         feats = ops.gemm(x, self.proj_w, self.proj_b, out_row_map=self._drop_cls_map(N), out_rows=N * (T - 1))
         return feats.view(N, T - 1, -1)
@@ -256,15 +312,19 @@ class LlamaDecoder:
         for i in range(cfg.layers):
             lp = f"layers.{i}."
             gate, up = d(lp + "mlp.gate_proj.weight"), d(lp + "mlp.up_proj.weight")
-            self.layers.append(dict(
+            L = dict(
                 rms1=d(lp + "input_layernorm.weight"), rms2=d(lp + "post_attention_layernorm.weight"),
                 w_qkv=torch.cat([d(lp + f"self_attn.{n}_proj.weight") for n in "qkv"], 0).contiguous(),
                 w_o=d(lp + "self_attn.o_proj.weight"),
                 # rows interleaved (gate0, up0, gate1, up1, ...) for the SwiGLU epilogue
                 w_gu=torch.stack([gate, up], dim=1).reshape(2 * cfg.mlp, cfg.hidden).contiguous(),
                 w_down=d(lp + "mlp.down_proj.weight"),
-            ))
+            )
             del gate, up
+            if FOLD_NORM:  # RMSNorm: gamma folds into the weight, rstd is applied per row in the epilogue
+                L["w_qkv"] = ops.fold_norm(L["w_qkv"], L["rms1"], rms=True)[0]
+                L["w_gu"] = ops.fold_norm(L["w_gu"], L["rms2"], rms=True)[0]
+            self.layers.append(L)
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.float32) / cfg.head_dim))
         fr = torch.outer(torch.arange(max_seq, dtype=torch.float32), inv)
         self.rope_cos = fr.cos().to(BF16).to(device).contiguous()
@@ -287,14 +347,24 @@ class LlamaDecoder:
         x = embeds
         scale = 1.0 / math.sqrt(hd)
         for L in self.layers:
-            h = ops.rmsnorm(x, L["rms1"], cfg.eps)
-            ops.gemm_qkv(h, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
-                         rope_cos=self.rope_cos, rope_sin=self.rope_sin)
+            if FOLD_NORM:
+                st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T))
+                ops.gemm_qkv(x, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
+                             rope_cos=self.rope_cos, rope_sin=self.rope_sin, row_stats=st)
+                h = self.scratch.zeros("o", n_seq * T, cfg.hidden)
+            else:
+                h = ops.rmsnorm(x, L["rms1"], cfg.eps)
+                ops.gemm_qkv(h, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
+                             rope_cos=self.rope_cos, rope_sin=self.rope_sin)
             ops.attention(q, k, vt, h, batch=n_seq, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=scale,
                           causal=True, kv_len=kv_len)
             ops.gemm(h, L["w_o"], None, residual=x, out=x)
-            h = ops.rmsnorm(x, L["rms2"], cfg.eps)
-            m = ops.gemm(h, L["w_gu"], None, swiglu=True)
+            if FOLD_NORM:
+                st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T))
+                m = ops.gemm(x, L["w_gu"], None, swiglu=True, row_stats=st)
+            else:
+                h = ops.rmsnorm(x, L["rms2"], cfg.eps)
+                m = ops.gemm(h, L["w_gu"], None, swiglu=True)
             ops.gemm(m, L["w_down"], None, residual=x, out=x)
         if out_rows is not None:
             return ops.rmsnorm(x, self.norm, cfg.eps, src_row_map=out_rows, rows_out=out_rows.numel())

@@ -36,15 +36,73 @@ def _req_bf16(*ts):
                 raise ValueError("innermost dimension must be contiguous")
 
 
+_gemm_ws = {}
+USE_GEMM_WORKSPACE = True  # tests flip this to compare against the plain (no stream-K) schedule
+
+
+def _workspace(p: GemmParams, device) -> None:
+    """Stream-K scratch for llmseg_gemm: one zero-filled buffer per (device, stream) — GEMMs on one stream
+    never overlap, so they can share it (see include/llmseg_b200.h)."""
+    if not USE_GEMM_WORKSPACE:
+        return
+    key = (torch.device(device).index or 0, _stream())
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.lib().llmseg_gemm_workspace_bytes(), dtype=torch.uint8, device=device)
+        _gemm_ws[key] = ws
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+
+
+def _norm_fold_args(p: GemmParams, row_stats, M: int) -> None:
+    if row_stats is not None and not (row_stats.is_cuda and row_stats.dtype == torch.float32 and
+                                      row_stats.is_contiguous() and row_stats.numel() == 2 * M):
+        raise ValueError("row_stats must be a contiguous fp32 [M, 2] CUDA tensor")
+    p.row_stats = _ptr(row_stats)
+
+
+def fold_norm(w: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, rms: bool = False):
+    """Weight-side half of folding y = Norm(x) @ w.T + bias into the GEMM on the un-normalised x
+    (include/llmseg_b200.h, row_stats): returns (w2 bf16 [N,K], bias2 bf16 [N] or None) with
+    w2 = w * gamma, rows centred for LayerNorm (so the mean term vanishes), bias2 = bias + w @ beta.
+    One-off, at model load."""
+    wf = w.float() * gamma.float()[None, :]
+    if not rms:
+        wf = wf - wf.mean(dim=1, keepdim=True)
+    bias2 = None
+    if bias is not None or beta is not None:
+        b = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
+        if bias is not None:
+            b += bias.float()
+        if beta is not None:
+            b += w.float() @ beta.float()
+        bias2 = b.to(torch.bfloat16).contiguous()
+    return wf.to(torch.bfloat16).contiguous(), bias2
+
+
+def norm_stats(x: torch.Tensor, eps: float, *, rms: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, 2] = (mean, rstd) per row of x (rms: (0, rsqrt(mean(x^2)+eps))) for gemm(row_stats=...)."""
+    _req_bf16(x)
+    dim = x.shape[-1]
+    x2 = x.reshape(-1, dim) if x.dim() != 2 else x
+    if out is None:
+        out = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().llmseg_norm_stats(x2.data_ptr(), x2.stride(0), x2.shape[0], dim, float(eps), int(rms),
+                                       out.data_ptr(), _stream()), "norm_stats")
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          act: Optional[str] = None, residual: Optional[torch.Tensor] = None, res_mod: int = 0,
          out: Optional[torch.Tensor] = None, out_row_map: Optional[torch.Tensor] = None,
-         out_rows: Optional[int] = None, swiglu: bool = False) -> torch.Tensor:
+         out_rows: Optional[int] = None, swiglu: bool = False,
+         row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act(a @ w.T + bias) (+ residual).  a: [M,K] bf16, w: [N,K] bf16 (nn.Linear layout).
 
     out_row_map (int32 [M]) scatters GEMM row r to output row out_row_map[r] (negative = dropped);
     the residual is read at the same output row (modulo res_mod when given).
     swiglu: w rows are (gate0, up0, gate1, up1, ...) and out has N/2 columns.
+    row_stats: the row normalisation of `a` folded into the epilogue (w, bias from fold_norm).
     """
     _req_bf16(a, w, bias, residual, out)
     M, K = a.shape
@@ -64,6 +122,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     p.act = ACT[act]
     p.mode = GEMM_SWIGLU if swiglu else GEMM_PLAIN
     p.out_row_map = _ptr(out_row_map)
+    _norm_fold_args(p, row_stats, M)
+    _workspace(p, a.device)
     check(_lib.lib().llmseg_gemm(C.byref(p), _stream()), "gemm")
     return out
 
@@ -71,7 +131,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: torch.Tensor,
              k: torch.Tensor, vt: torch.Tensor, *, heads: int, head_dim: int, seq_in: int,
              seq_pad: int, rope_cos: Optional[torch.Tensor] = None,
-             rope_sin: Optional[torch.Tensor] = None, row_map: Optional[torch.Tensor] = None) -> None:
+             rope_sin: Optional[torch.Tensor] = None, row_map: Optional[torch.Tensor] = None,
+             row_stats: Optional[torch.Tensor] = None) -> None:
     """QKV projection writing q,k [(b*heads+h), seq_pad, hd] and vt [(b*heads+h), hd, seq_pad].
     row_map (int32 [M]): GEMM row r lands at position m = row_map[r] -> (b, s) = divmod(m, seq_in)."""
     _req_bf16(a, w, bias, q, k, vt, rope_cos, rope_sin)
@@ -86,15 +147,18 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: 
     p.heads, p.head_dim, p.seq_in, p.seq_pad = heads, head_dim, seq_in, seq_pad
     p.rope_cos, p.rope_sin = _ptr(rope_cos), _ptr(rope_sin)
     p.out_row_map = _ptr(row_map)
+    _norm_fold_args(p, row_stats, M)
+    _workspace(p, a.device)
     check(_lib.lib().llmseg_gemm(C.byref(p), _stream()), "gemm_qkv")
 
 
-def fill_kv_rows(k: torch.Tensor, vt: torch.Tensor, bias_qkv: torch.Tensor, rows: torch.Tensor, *, heads: int,
-                 head_dim: int, seq_in: int, seq_pad: int) -> None:
-    """k / vt rows of window-padding tokens <- projection bias (zero tokens after LayerNorm)."""
+def fill_kv_rows(k: torch.Tensor, vt: torch.Tensor, bias_qkv: torch.Tensor, pos_map: torch.Tensor, *, batch: int,
+                 heads: int, head_dim: int, seq_in: int, seq_pad: int) -> None:
+    """k / vt entries of window-padding positions (pos_map < 0) <- projection bias (zero tokens after LN)."""
     _req_bf16(k, vt, bias_qkv)
-    check(_lib.lib().llmseg_fill_kv_rows(k.data_ptr(), vt.data_ptr(), bias_qkv.data_ptr(), rows.data_ptr(),
-                                         rows.numel(), heads, head_dim, seq_in, seq_pad, _stream()), "fill_kv_rows")
+    assert pos_map.dtype == torch.int32 and pos_map.numel() == batch * seq_in
+    check(_lib.lib().llmseg_fill_kv_rows(k.data_ptr(), vt.data_ptr(), bias_qkv.data_ptr(), pos_map.data_ptr(),
+                                         batch, heads, head_dim, seq_in, seq_pad, _stream()), "fill_kv_rows")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, batch: int,

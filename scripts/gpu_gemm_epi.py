@@ -33,3 +33,27 @@ q = torch.zeros(nb * H, Sp, hd, device=dev, dtype=torch.bfloat16); k = torch.zer
 out = torch.empty(Mw, 3840, device=dev, dtype=torch.bfloat16)
 us = t(lambda: ops.gemm(a, w, b, out=out)); print(f"qkv 39200x3840x1280 plain store      {us:7.1f} us  {2*Mw*3840*1280/us/1e6:6.0f} TF/s")
 us = t(lambda: ops.gemm_qkv(a, w, b, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=Sp)); print(f"qkv 39200x3840x1280 split q/k/vT     {us:7.1f} us  {2*Mw*3840*1280/us/1e6:6.0f} TF/s")
+# LLaMA batch-8 shapes (M = 8 x 319 tokens): stream-K tail on/off
+Ml = 2552
+for name, N, K, kw in (("o_proj", 4096, 4096, "res"), ("down", 4096, 11008, "res"), ("gate_up", 22016, 4096, "swiglu"),
+                       ("qkv+rope", 12288, 4096, "qkv"), ("sam mlp2", 1280, 5120, "res32768")):
+    M_ = 32768 if kw == "res32768" else Ml
+    a, w, b = mk(M_, N, K)
+    res = torch.randn(M_, N, device=dev).bfloat16()
+    out = torch.empty(M_, N // 2 if kw == "swiglu" else N, device=dev, dtype=torch.bfloat16)
+    if kw == "qkv":
+        Hh = 32; q = torch.zeros(8 * Hh, 320, 128, device=dev, dtype=torch.bfloat16); k = torch.zeros_like(q)
+        vt = torch.zeros(8 * Hh, 128, 320, device=dev, dtype=torch.bfloat16)
+        cs = torch.randn(319, 64, device=dev).bfloat16()
+        fn = lambda: ops.gemm_qkv(a, w, None, q, k, vt, heads=Hh, head_dim=128, seq_in=319, seq_pad=320, rope_cos=cs, rope_sin=cs)
+    elif kw == "swiglu":
+        fn = lambda: ops.gemm(a, w, None, out=out, swiglu=True)
+    else:
+        fn = lambda: ops.gemm(a, w, None, residual=res, out=out)
+    r = [1e9, 1e9]
+    for rep in range(3):   # interleaved, best of 3: the two schedules see the same clocks
+        for i, use in enumerate((False, True)):
+            ops.USE_GEMM_WORKSPACE = use
+            r[i] = min(r[i], t(fn, 10))
+    ops.USE_GEMM_WORKSPACE = True
+    print(f"{name:9s} {M_}x{N}x{K}: plain {r[0]:7.1f} us ({2*M_*N*K/r[0]/1e6:5.0f} TF/s)   stream-K tail {r[1]:7.1f} us ({2*M_*N*K/r[1]/1e6:5.0f} TF/s)", flush=True)

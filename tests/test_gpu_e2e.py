@@ -71,7 +71,9 @@ def test_forward_reduced_depth_batched(cuda_lib):
     with torch.no_grad():
         out = model.forward(**inp)
     _check(out, _oracle(sd, ocfg, inp), 2)
-    # batched == independent single-image calls (reference inference is one image per forward)
+    # batched ~ independent single-image calls (reference inference is one image per forward).  Not bit
+    # equal: the GEMM's stream-K tail cuts K differently for different row counts, which moves fp32
+    # summation order (the same holds for the reference's cuBLAS split-K heuristics).
     from llmseg_b200 import synthetic
     for b in range(2):
         one = dict(inp)
@@ -81,8 +83,8 @@ def test_forward_reduced_depth_batched(cuda_lib):
         one["offset"] = torch.arange(2)
         with torch.no_grad():
             o1 = model.forward(**one)
-        assert torch.equal(o1["pred_similarity"][0], out["pred_similarity"][b])
-        assert torch.equal(o1["pred_iou"][0], out["pred_iou"][b])
+        assert (o1["pred_similarity"][0].float() - out["pred_similarity"][b].float()).abs().max().item() <= SIM_TOL
+        assert (o1["pred_iou"][0].float() - out["pred_iou"][b].float()).abs().max().item() <= SIM_TOL  # 1 bf16 ulp
 
 
 def test_forward_right_padded_prompt_and_ragged_k(cuda_lib):

@@ -54,6 +54,43 @@ def test_gemm_row_scatter_and_broadcast_residual(cuda_lib):
     assert (out.float() - ref).abs().max().item() <= _ulp_tol(ref)
 
 
+@pytest.mark.parametrize("M,N,K,mode", [(2552, 4096, 4096, "res"), (2552, 4096, 11008, "res"), (2552, 12288, 4096, "qkv"),
+                                        (1100, 1024, 4096, "res"), (2552, 2048, 2048, "swiglu")])
+def test_gemm_streamk_tail(cuda_lib, M, N, K, mode):
+    """Shapes whose last wave of tiles is mostly empty take the stream-K tail (fp32 partials through the
+    workspace): same result as the plain schedule up to fp32 summation order, and deterministic."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w = _bf(torch.randn(M, K, generator=g)), _bf(torch.randn(N, K, generator=g) / K ** 0.5)
+    r = _bf(torch.randn(M, N, generator=g))
+
+    def run():
+        if mode == "qkv":
+            H, hd, S = N // 384, 128, 319
+            q = torch.zeros(M // S * H, 320, hd, device=DEV, dtype=torch.bfloat16)
+            k, vt = torch.zeros_like(q), torch.zeros(M // S * H, hd, 320, device=DEV, dtype=torch.bfloat16)
+            ops.gemm_qkv(a, w, None, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=320)
+            return torch.cat([q.flatten(), k.flatten(), vt.flatten()])
+        if mode == "swiglu":
+            return ops.gemm(a, w, None, swiglu=True)
+        return ops.gemm(a, w, None, residual=r)
+
+    outs = []
+    for use in (False, True, True):
+        ops.USE_GEMM_WORKSPACE = use
+        try:
+            outs.append(run().float())
+        finally:
+            ops.USE_GEMM_WORKSPACE = True
+    plain, sk, sk2 = outs
+    assert torch.equal(sk, sk2)
+    d = (plain - sk).abs()
+    assert d.max().item() <= _ulp_tol(plain) and d.mean().item() <= 1e-4
+    if mode == "res":
+        ref = (a.float() @ w.float().T).bfloat16().float() + r.float()
+        assert (sk - ref).abs().max().item() <= _ulp_tol(ref)
+
+
 def test_gemm_swiglu(cuda_lib):
     from llmseg_b200 import ops
     g = torch.Generator().manual_seed(1)
@@ -108,13 +145,13 @@ def _qkv_setup(B, H, hd, S, g, rope=False):
     ref = x.float() @ w.float().T
     if bias is not None:
         ref = ref + bias.float()
-    ref = ref.bfloat16().float().reshape(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref = ref.reshape(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)   # epilogue is fp32 up to the store
     rq, rk, rv = ref[0], ref[1], ref[2]
     if rope:
         c = torch.cat([cos, cos], -1).float()[None, None]
         s_ = torch.cat([sin, sin], -1).float()[None, None]
         rot = lambda t: torch.cat([-t[..., hd // 2:], t[..., :hd // 2]], -1)
-        ap = lambda t: ((t * c).bfloat16().float() + (rot(t) * s_).bfloat16().float()).bfloat16().float()
+        ap = lambda t: t * c + rot(t) * s_
         rq, rk = ap(rq), ap(rk)
     return q, k, vt, rq, rk, rv, S_pad
 
@@ -189,6 +226,42 @@ def test_sam_relpos_attention(cuda_lib, grid, nb):
     assert d.abs().mean().item() <= 4e-3
 
 
+@pytest.mark.parametrize("rows,dim,N,rms", [(1000, 1280, 1024, False), (319, 4096, 512, True), (257, 1024, 768, False)])
+def test_norm_folded_into_gemm(cuda_lib, rows, dim, N, rms):
+    """y = act(Norm(x) @ W.T + b) with the norm folded into the GEMM (norm_stats + fold_norm + row_stats)
+    against fp32 torch, and against the two-kernel path (norm, then GEMM) it replaces."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(rows + N)
+    x = _bf(torch.randn(rows, dim, generator=g) * 3 + 1.5)     # non-zero mean: must cancel against the centred weights
+    x[:, 5] += 40.0                                            # a massive-activation channel
+    gm, bt = _bf(1 + 0.2 * torch.randn(dim, generator=g)), _bf(0.2 * torch.randn(dim, generator=g))
+    w = _bf(torch.randn(N, dim, generator=g) / dim ** 0.5)
+    b = None if rms else _bf(torch.randn(N, generator=g) * 0.1)
+    st = ops.norm_stats(x, 1e-6, rms=rms)
+    xf = x.float()
+    if rms:
+        ref_rstd = torch.rsqrt(xf.pow(2).mean(-1) + 1e-6)
+        assert (st[:, 0] == 0).all() and torch.allclose(st[:, 1], ref_rstd, rtol=1e-5)
+        normed = xf * ref_rstd[:, None] * gm.float()
+    else:
+        assert torch.allclose(st[:, 0], xf.mean(-1), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(st[:, 1], torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-5)
+        normed = torch.nn.functional.layer_norm(xf, (dim,), gm.float(), bt.float(), 1e-6)
+    wq, b2 = ops.fold_norm(w, gm, None if rms else bt, b, rms=rms)
+    assert (b2 is None) == rms
+    if not rms:   # centred rows: the mean of x drops out of x @ wq.T up to the bf16 rounding of wq
+        assert wq.float().sum(1).abs().max().item() <= 2 ** -8 * float(wq.float().abs().sum(1).max())
+    out = ops.gemm(x, wq, b2, act=None if rms else "gelu", row_stats=st)
+    ref = normed @ w.float().T
+    if not rms:
+        ref = torch.nn.functional.gelu(ref + b.float())
+    tol = _ulp_tol(ref) + 2 ** -8 * float(ref.abs().max())    # + bf16 rounding of the gamma-scaled weights
+    assert (out.float() - ref).abs().max().item() <= tol
+    h = ops.rmsnorm(x, gm, 1e-6) if rms else ops.layernorm(x, gm, bt, 1e-6)
+    two = ops.gemm(h, w, b, act=None if rms else "gelu")
+    assert (out.float() - ref).abs().mean().item() <= 1.5 * (two.float() - ref).abs().mean().item() + 1e-4
+
+
 def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
     """SAM window partition / un-partition (reference image_encoder.py:263-318) as index maps on the QKV
     epilogue and the attention output: must equal the explicit pad -> project -> attend -> crop flow
@@ -200,7 +273,7 @@ def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
     enc.cfg, enc.device, enc._maps = SamCfg(), DEV, {}
     B, H, hd, ws = 1, 2, 80, 14
     D, S, sw, sw_pad = H * hd, 4096, 196, 200
-    win_map, n_win, tok2win, pad_pos = enc._window_maps(B)
+    win_map, n_win, tok2win = enc._window_maps(B)
     nb = B * n_win
     g = torch.Generator().manual_seed(7)
     x = _bf(torch.randn(B * S, D, generator=g))
@@ -215,7 +288,7 @@ def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
         qext = torch.zeros(nb * H, sw_pad, 32, device=DEV, dtype=torch.bfloat16)
         if folded:
             ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad, row_map=tok2win)
-            ops.fill_kv_rows(k, vt, bias, pad_pos, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+            ops.fill_kv_rows(k, vt, bias, win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
         else:
             xp = torch.zeros(nb * sw, D, device=DEV, dtype=torch.bfloat16)
             valid = win_map >= 0
