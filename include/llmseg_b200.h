@@ -200,11 +200,13 @@ int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* attention_mask,
 int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim, int group,
                           const int32_t* row_group, void* stream);
 /* K and Vᵀ entries of window padding tokens: the reference pads with zeros AFTER LayerNorm, so their
- * k, v equal the projection bias (image_encoder.py:179-185,238-242).  pos_map: int32 [batch*seq_in],
- * negative = padding position (the same map llmseg_attention takes as out_row_map);
- * bias_qkv: bf16 [3*heads*head_dim] (q | k | v). */
-int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map, int batch,
-                        int heads, int head_dim, int seq_in, int seq_pad, void* stream);
+ * k, v equal the projection bias (image_encoder.py:179-185,238-242).  pos_map: int32 [*, seq_in],
+ * negative = padding position (the same map llmseg_attention takes as out_row_map); seq_ids: int32
+ * [n_seqs] sequences (windows) to visit — those that contain padding — or NULL for sequences
+ * 0..n_seqs-1; bias_qkv: bf16 [3*heads*head_dim] (q | k | v). */
+int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map,
+                        const int32_t* seq_ids, int n_seqs, int heads, int head_dim, int seq_in,
+                        int seq_pad, void* stream);
 /* 3x3 / pad-1 im2col on token-major NHWC bf16: out[(b,y,x), (ky,kx,c)]; turns the SAM neck
  * conv3x3 (image_encoder.py:100-106) into one GEMM with the weight permuted to [out,(ky,kx,c)]. */
 int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width, int channels,

@@ -69,8 +69,8 @@ def _declare(lib):
                                         c_int, c_void_p]
     lib.llmseg_add_rows_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_void_p, c_void_p]
-    lib.llmseg_fill_kv_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                        c_int, c_void_p]
+    lib.llmseg_fill_kv_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_void_p]
     lib.llmseg_im2col3x3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.llmseg_maskpool_workspace.argtypes = [c_int]
     lib.llmseg_maskpool_workspace.restype = C.c_size_t

@@ -209,7 +209,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (all 32 lanes walk the loop, one elected lane issues: uniform control flow keeps the operands in
+    //  uniform registers — see the MMA issuer below)
+    const bool issuer = elect_one();
+    if (issuer) {
       mbar_expect_tx(bar_q, C::Q_TX);
       tma_load_3d(smem + C::OFF_Q0, &tmQa, bar_q, 0, q0, bh);
       if (HD == 80) tma_load_3d(smem + C::OFF_Q1, &tmQb, bar_q, 64, q0, bh);
@@ -223,75 +226,91 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
         tma_load_3d(smem + C::OFF_QX, &tmQx, bar_q, 0, q0, bh);
         tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
       }
-      for (int j = 0; j < n_tiles; ++j) {
-        const uint32_t ph = j & 1;
-        const int key0 = j * BN;
-        mbar_wait(k_empty, ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t ph = j & 1;
+      const int key0 = j * BN;
+      mbar_wait(k_empty, ph ^ 1);
+      if (issuer) {
         mbar_expect_tx(k_full, C::K_TX);
         tma_load_3d(smem + C::OFF_K0, &tmKa, k_full, 0, key0, bh);
         if (HD == 80) tma_load_3d(smem + C::OFF_K1, &tmKb, k_full, 64, key0, bh);
         if (HD == 128) tma_load_3d(smem + C::OFF_K1, &tmKa, k_full, 64, key0, bh);
-        mbar_wait(v_empty, ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, ph ^ 1);
+      if (issuer) {
         mbar_expect_tx(v_full, C::V_TX);
         tma_load_3d(smem + C::OFF_V, &tmV, v_full, key0, 0, bh);
         tma_load_3d(smem + C::OFF_V + C::V_CHUNK, &tmV, v_full, key0 + 64, 0, bh);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The loop runs on all 32 lanes with the tcgen05 instructions under an elected-lane predicate.  With
+    // the loop inside `if (lane == 0)` ptxas wrapped each of the 17 MMAs of a tile in a ~20-instruction
+    // ELECT / R2UR loop, and the issuer thread — not the tensor pipe, the MUFU or TMEM — set the
+    // ~2300 clk tile time every variant in profiles/r01f_attention_investigation.md ran into.
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+      const bool issuer = elect_one();
       const uint32_t sQ0 = smem_u32(smem + C::OFF_Q0), sQ1 = smem_u32(smem + C::OFF_Q1);
       const uint32_t sQX = smem_u32(smem + C::OFF_QX), sE = smem_u32(smem + C::OFF_E);
       const uint32_t sK0 = smem_u32(smem + C::OFF_K0), sK1 = smem_u32(smem + C::OFF_K1);
       const uint32_t sV = smem_u32(smem + C::OFF_V);
       const uint32_t tS = tmem_base, tO = tmem_base + C::O_COL;
+      // every operand lives at a fixed shared-memory address: the descriptors are loop invariants
+      const uint64_t dQ0 = umma_smem_desc(sQ0, 1024, UMMA_SW128), dK0 = umma_smem_desc(sK0, 1024, UMMA_SW128);
+      const uint64_t dQ1s = umma_smem_desc(sQ1, 256, UMMA_SW32), dK1s = umma_smem_desc(sK1, 256, UMMA_SW32);
+      const uint64_t dQ1 = umma_smem_desc(sQ1, 1024, UMMA_SW128), dK1 = umma_smem_desc(sK1, 1024, UMMA_SW128);
+      const uint64_t dQXw = umma_smem_desc(sQX, 512, UMMA_SW64), dEw = umma_smem_desc(sE, 512, UMMA_SW64);
+      const uint64_t dQXg = umma_smem_desc(sQX, 1024, UMMA_SW128), dEg = umma_smem_desc(sE, 1024, UMMA_SW128);
+      const uint64_t dV0 = umma_smem_desc(sV, 1024, UMMA_SW128);
+      const uint64_t dV1 = umma_smem_desc(sV + C::V_CHUNK, 1024, UMMA_SW128);
       mbar_wait(bar_q, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t ph = j & 1;
         mbar_wait(k_full, ph);
         tc_fence_after();
-        // ---- S = [q|qext]·[k|kext]ᵀ ----
+        if (issuer) {
+          // ---- S = [q|qext]·[k|kext]ᵀ ----  (+32 bytes along K = +2 in the descriptor's address field)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, umma_smem_desc(sQ0 + k * 32, 1024, UMMA_SW128),
-                  umma_smem_desc(sK0 + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
-        if (HD == 80)
-          umma_ss(tS, umma_smem_desc(sQ1, 256, UMMA_SW32), umma_smem_desc(sK1, 256, UMMA_SW32),
-                  idesc_s, 1);
-        if (HD == 128) {
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
+          if (HD == 80) umma_ss(tS, dQ1s, dK1s, idesc_s, 1);
+          if (HD == 128) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_smem_desc(sQ1 + k * 32, 1024, UMMA_SW128),
-                    umma_smem_desc(sK1 + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dQ1 + 2 * k, dK1 + 2 * k, idesc_s, 1);
+          }
+          if (EXT == 1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_ss(tS, dQXw + 2 * k, dEw + (uint64_t)(j * 512 + 2 * k), idesc_s, 1);
+          }
+          if (EXT == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dQXg + 2 * k, dEg + 2 * k, idesc_s, 1);
+          }
+          umma_commit(k_empty);
+          umma_commit(bar_s);
         }
-        if (EXT == 1) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss(tS, umma_smem_desc(sQX + k * 32, 512, UMMA_SW64),
-                    umma_smem_desc(sE + j * 8192 + k * 32, 512, UMMA_SW64), idesc_s, 1);
-        }
-        if (EXT == 2) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_smem_desc(sQX + k * 32, 1024, UMMA_SW128),
-                    umma_smem_desc(sE + k * 32, 1024, UMMA_SW128), idesc_s, 1);
-        }
-        umma_commit(k_empty);
-        umma_commit(bar_s);
+        __syncwarp();
         // ---- O += P·V ----
         mbar_wait(bar_p, ph);
         mbar_wait(v_full, ph);
         tc_fence_after();
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // P(keys 0..63) sits at S columns [0,32), P(keys 64..127) at [64,96)
-          umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8,
-                  umma_smem_desc(sV + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128),
-                  idesc_o, (j | k) != 0);
-        umma_commit(v_empty);
+          for (int k = 0; k < 8; ++k)  // P(keys 0..63) sits at S columns [0,32), P(keys 64..127) at [64,96)
+            umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8, (k < 4 ? dV0 : dV1) + 2 * (k & 3), idesc_o,
+                    (j | k) != 0);
+          umma_commit(v_empty);
+        }
+        __syncwarp();
       }
-      umma_commit(bar_s);  // final: all PV done
+      if (issuer) umma_commit(bar_s);  // final: all PV done
+      __syncwarp();
     }
   } else {
     // ================================ softmax / correction / epilogue ================================
@@ -824,25 +843,36 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (warp-uniform loops, elected-lane issue: see attn_kernel)
+    const bool issuer = elect_one();
+    if (issuer) {
       mbar_expect_tx(bar_e, C::E_BYTES);
       tma_load_2d(smem + C::OFF_E, &tmE, bar_e, 0, 0);
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t kvph = (it >> 1) & 1;
-        uint8_t* sk = smem + C::OFF_K + st * C::K_ALLOC;
-        uint8_t* sv = smem + C::OFF_V + st * C::V_ALLOC;
-        mbar_wait(&k_empty[st], kvph ^ 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t kvph = (it >> 1) & 1;
+      uint8_t* sk = smem + C::OFF_K + st * C::K_ALLOC;
+      uint8_t* sv = smem + C::OFF_V + st * C::V_ALLOC;
+      mbar_wait(&k_empty[st], kvph ^ 1);
+      if (issuer) {
         mbar_expect_tx(&k_full[st], C::K_TX);
         tma_load_3d(sk, &tmKa, &k_full[st], 0, 0, item);
         tma_load_3d(sk + 26624, &tmKb, &k_full[st], 64, 0, item);
-        mbar_wait(&v_empty[st], kvph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], kvph ^ 1);
+      if (issuer) {
         mbar_expect_tx(&v_full[st], C::V_TX);
 #pragma unroll
         for (int c = 0; c < 3; ++c) tma_load_3d(sv + c * C::V_CHUNK, &tmVa, &v_full[st], c * 64, 0, item);
         tma_load_3d(sv + 3 * C::V_CHUNK, &tmVb, &v_full[st], 192, 0, item);
-        mbar_wait(q_empty, (it & 1) ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(q_empty, (it & 1) ^ 1);
+      if (issuer) {
         mbar_expect_tx(q_full, C::Q_TX);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -852,13 +882,16 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           tma_load_3d(sq + 20480, &tmQx, q_full, 0, t * 128, item);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, C::KEYS);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 80);
+      const bool issuer = elect_one();
       const uint32_t sE = smem_u32(smem + C::OFF_E);
+      const uint64_t dE = umma_smem_desc(sE, 512, UMMA_SW64);
       mbar_wait(bar_e, 0);
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -866,6 +899,8 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
         const uint32_t ph = it & 1, kvph = (it >> 1) & 1;
         const uint32_t sk = smem_u32(smem + C::OFF_K + st * C::K_ALLOC);
         const uint32_t sv = smem_u32(smem + C::OFF_V + st * C::V_ALLOC);
+        const uint64_t dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
+        const uint64_t dK1 = umma_smem_desc(sk + 26624, 256, UMMA_SW32);
         mbar_wait(q_full, ph);
         mbar_wait(&k_full[st], kvph);
 #pragma unroll
@@ -874,35 +909,44 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           tc_fence_after();
           const uint32_t sq = smem_u32(smem + C::OFF_Q + t * C::QT_BYTES);
           const uint32_t tS = tmem_base + t * 256;
+          const uint64_t dQ0 = umma_smem_desc(sq, 1024, UMMA_SW128);
+          const uint64_t dQ1 = umma_smem_desc(sq + 16384, 256, UMMA_SW32);
+          const uint64_t dQX = umma_smem_desc(sq + 20480, 512, UMMA_SW64);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_smem_desc(sq + k * 32, 1024, UMMA_SW128),
-                    umma_smem_desc(sk + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
-          umma_ss(tS, umma_smem_desc(sq + 16384, 256, UMMA_SW32), umma_smem_desc(sk + 26624, 256, UMMA_SW32),
-                  idesc_s, 1);
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
+            umma_ss(tS, dQ1, dK1, idesc_s, 1);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss(tS, umma_smem_desc(sq + 20480 + k * 32, 512, UMMA_SW64),
-                    umma_smem_desc(sE + k * 32, 512, UMMA_SW64), idesc_s, 1);
-          umma_commit(&bar_s[t]);
+            for (int k = 0; k < 2; ++k) umma_ss(tS, dQX + 2 * k, dE + 2 * k, idesc_s, 1);
+            umma_commit(&bar_s[t]);
+          }
+          __syncwarp();
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(q_empty);
+        if (issuer) {
+          umma_commit(&k_empty[st]);
+          umma_commit(q_empty);
+        }
+        __syncwarp();
         mbar_wait(&v_full[st], kvph);
+        const uint64_t dV = umma_smem_desc(sv, 1024, UMMA_SW128);
+        const uint64_t dVt = umma_smem_desc(sv + 3 * C::V_CHUNK, 256, UMMA_SW32);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           mbar_wait(&bar_p[t], ph);
           tc_fence_after();
           const uint32_t tS = tmem_base + t * 256;
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 12; ++k)
-            umma_ts(tS + C::O_COL, tS + k * 8,
-                    umma_smem_desc(sv + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128), idesc_o,
-                    k != 0);
-          umma_ts(tS + C::O_COL, tS + 96, umma_smem_desc(sv + 3 * C::V_CHUNK, 256, UMMA_SW32), idesc_o, 1);
-          umma_commit(&bar_o[t]);
+            for (int k = 0; k < 12; ++k)
+              umma_ts(tS + C::O_COL, tS + k * 8, dV + (uint64_t)((k >> 2) * (C::V_CHUNK >> 4) + (k & 3) * 2), idesc_o,
+                      k != 0);
+            umma_ts(tS + C::O_COL, tS + 96, dVt, idesc_o, 1);
+            umma_commit(&bar_o[t]);
+          }
+          __syncwarp();
         }
-        umma_commit(&v_empty[st]);
+        if (issuer) umma_commit(&v_empty[st]);
+        __syncwarp();
       }
     }
   } else {

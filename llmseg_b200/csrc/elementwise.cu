@@ -158,14 +158,17 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__
   }
 }
 
-// One block per sequence b: every position s with pos_map[b*seq_in + s] < 0 (a window padding token) gets
-// k[(b*H+h), s, :] = bias_k[h] and vt[(b*H+h), :, s] = bias_v[h] for all heads.  Sequences without padding
-// (16 of the 25 SAM windows) exit after the flag scan; k writes are 16-byte, vt writes run along s.
-__global__ void __launch_bounds__(512)
+// One block per (listed sequence b, head h): every position s with pos_map[b*seq_in + s] < 0 (a window
+// padding token) gets k[(b*H+h), s, :] = bias_k[h] and vt[(b*H+h), :, s] = bias_v[h].  seq_ids lists the
+// sequences that have padding at all (9 of the 25 SAM windows), so no block is launched just to find out
+// it has nothing to do; k writes are 16-byte, vt writes run along s.
+__global__ void __launch_bounds__(256)
 fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __restrict__ bias,
-                    const int* __restrict__ pos_map, int heads, int hd, int seq_in, int seq_pad) {
+                    const int* __restrict__ pos_map, const int* __restrict__ seq_ids, int heads, int hd,
+                    int seq_in, int seq_pad) {
   extern __shared__ unsigned char s_pad[];  // [seq_in]
-  const int b = blockIdx.x;
+  const int b = seq_ids ? seq_ids[blockIdx.x] : blockIdx.x;
+  const int h = blockIdx.y;
   int any = 0;
   for (int s = threadIdx.x; s < seq_in; s += blockDim.x) {
     const unsigned char f = pos_map[(size_t)b * seq_in + s] < 0;
@@ -174,19 +177,17 @@ fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __r
   }
   if (!__syncthreads_or(any)) return;
   const int hw = heads * hd;
+  const size_t bh = (size_t)b * heads + h;
   const int vec = hd >> 3;
-  for (int idx = threadIdx.x; idx < heads * seq_in * vec; idx += blockDim.x) {
-    const int v = idx % vec;
-    const int s = (idx / vec) % seq_in;
-    const int h = idx / (vec * seq_in);
-    if (s_pad[s])
-      reinterpret_cast<uint4*>(k + (((size_t)b * heads + h) * seq_pad + s) * hd)[v] =
-          __ldg(reinterpret_cast<const uint4*>(bias + hw + h * hd) + v);
+  const uint4* bk = reinterpret_cast<const uint4*>(bias + hw + h * hd);
+  for (int idx = threadIdx.x; idx < seq_in * vec; idx += blockDim.x) {
+    const int s = idx / vec, v = idx - s * vec;
+    if (s_pad[s]) reinterpret_cast<uint4*>(k + (bh * seq_pad + s) * hd)[v] = __ldg(bk + v);
   }
-  for (int idx = threadIdx.x; idx < hw * seq_in; idx += blockDim.x) {
-    const int s = idx % seq_in;
-    const int c = idx / seq_in;  // h * hd + d
-    if (s_pad[s]) vt[((size_t)b * hw + c) * seq_pad + s] = bias[2 * hw + c];
+  const bf16* bv = bias + 2 * hw + h * hd;
+  for (int idx = threadIdx.x; idx < hd * seq_in; idx += blockDim.x) {
+    const int d = idx / seq_in, s = idx - d * seq_in;
+    if (s_pad[s]) vt[(bh * hd + d) * seq_pad + s] = bv[d];
   }
 }
 
@@ -195,17 +196,19 @@ fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __r
 
 using namespace llmseg;
 
-extern "C" int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map, int batch,
-                                   int heads, int head_dim, int seq_in, int seq_pad, void* stream) {
+extern "C" int llmseg_fill_kv_rows(void* k, void* vt, const void* bias_qkv, const int32_t* pos_map,
+                                   const int32_t* seq_ids, int n_seqs, int heads, int head_dim, int seq_in,
+                                   int seq_pad, void* stream) {
+  const int batch = n_seqs;
   if (int e = check_arch()) return e;
   LLMSEG_REQUIRE(k && vt && bias_qkv && pos_map, LLMSEG_EARG, "llmseg_fill_kv_rows: null pointer");
   LLMSEG_REQUIRE(batch > 0 && heads > 0 && heads < 65536 && head_dim > 0 && head_dim % 8 == 0 &&
                      seq_pad >= seq_in && seq_in > 0 && seq_in <= 32768,
                  LLMSEG_ESHAPE, "llmseg_fill_kv_rows: batch=%d heads=%d head_dim=%d seq_in=%d seq_pad=%d", batch,
                  heads, head_dim, seq_in, seq_pad);
-  fill_kv_rows_kernel<<<batch, 512, seq_in, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<bf16*>(k), static_cast<bf16*>(vt), static_cast<const bf16*>(bias_qkv), pos_map, heads,
-      head_dim, seq_in, seq_pad);
+  fill_kv_rows_kernel<<<dim3(batch, heads), 256, seq_in, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(k), static_cast<bf16*>(vt), static_cast<const bf16*>(bias_qkv), pos_map, seq_ids,
+      heads, head_dim, seq_in, seq_pad);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -617,8 +617,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_clusters = gridDim.x / cl;
   const int slice_rows = BN / cl;
 
+  // producer / MMA warps: all 32 lanes walk the schedule, one elected lane issues (see gemm2_kernel)
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
@@ -628,14 +630,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-          if (cl == 1) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
-            tma_load_2d_mcast(sb + cta_rank * slice_rows * 128, &tmB, &full_bar[stage], kb * BK,
-                              n_blk * BN + cta_rank * slice_rows, cl_mask);
+          if (issuer) {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+            if (cl == 1) {
+              tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
+              tma_load_2d_mcast(sb + cta_rank * slice_rows * 128, &tmB, &full_bar[stage], kb * BK,
+                                n_blk * BN + cta_rank * slice_rows, cl_mask);
+            }
           }
+          __syncwarp();
           if (++stage == NST) {
             stage = 0;
             phase ^= 1;
@@ -644,12 +649,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
@@ -657,17 +664,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t da0 = umma_smem_desc(sa, 1024, UMMA_SW128);
+          const uint64_t db0 = umma_smem_desc(sa + A_STAGE_BYTES, 1024, UMMA_SW128);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * 32, 1024, UMMA_SW128);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (cl == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mcast(&empty_bar[stage], cl_mask);  // frees the slot in every CTA of the cluster
+            if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
           }
-          if (cl == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mcast(&empty_bar[stage], cl_mask);  // frees the slot in every CTA of the cluster
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[as]);
+          __syncwarp();
           if (++stage == NST) {
             stage = 0;
             phase ^= 1;
@@ -775,8 +783,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int num_clusters = gridDim.x >> 1;
   const bool n_fastest = p.n_fastest != 0;
 
+  // Producer and MMA warps walk their schedules with all 32 lanes (uniform control flow: addresses,
+  // descriptors and loop state live in uniform registers) and only the tcgen05 / TMA instructions sit
+  // under an elected-lane predicate.  With the whole loop inside `if (lane == 0)` ptxas treated every
+  // operand as divergent and wrapped each UTCHMMA in a ~20-instruction ELECT / R2UR loop: ~125
+  // instructions per k-block kept the tensor pipe waiting on its own issuer (ncu: 843 clk per k-block for
+  // 512 clk of MMA work, profiles/r01k_gemm_issue.md).
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       SkWalk walk(p, num_groups, cluster_id, num_clusters);
@@ -794,10 +809,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_pair(sa, &tmA, lbar, kb * BK, m_blk * BM);
-          tma_load_2d_pair(sb, &tmB, lbar, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+          if (issuer) {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, lbar, kb * BK, m_blk * BM);
+            tma_load_2d_pair(sb, &tmB, lbar, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+          }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -806,14 +824,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const bool issuer = elect_one();  // one lane issues every MMA and commit (commits track their issuer)
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       SkWalk walk(p, num_groups, cluster_id, num_clusters);
       SkSeg sg;
+      const uint32_t smem_base = smem_u32(smem);
       for (int grp = cluster_id;; grp += num_clusters) {
         int k0 = 0, k1 = p.num_k_blocks;
         if (grp >= walk.full_end) {
@@ -826,16 +846,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          // descriptors of the stage's first 16-column slice; the next slices are +32 bytes = +2 in the
+          // (address >> 4) field
+          const uint64_t da0 = umma_smem_desc(sa, 1024, UMMA_SW128);
+          const uint64_t db0 = umma_smem_desc(sa + A_STAGE_BYTES, 1024, UMMA_SW128);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * 32, 1024, UMMA_SW128);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 1024, UMMA_SW128);
-            umma2_ss(d_tmem, da, db, idesc, (kb != k0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma2_ss(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb != k0 || k != 0) ? 1u : 0u);
+            umma2_commit_mcast(&empty_bar[stage], 3);  // frees the slot in both CTAs
+            if (kb == k1 - 1) umma2_commit_mcast(&tmem_full[as], 3);
           }
-          umma2_commit_mcast(&empty_bar[stage], 3);  // frees the slot in both CTAs
-          if (kb == k1 - 1) umma2_commit_mcast(&tmem_full[as], 3);
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;

@@ -71,54 +71,62 @@ relpos_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // producer / MMA warps: warp-uniform loops, one elected lane issues (operands stay in uniform registers)
   if (warp == 0) {
-    if (lane == 0) {
+    const bool issuer = elect_one();
+    if (issuer) {
       mbar_expect_tx(r_full, C::R_BYTES);
       tma_load_2d(smem + C::OFF_R, &tmRa, r_full, 0, 0);
       tma_load_2d(smem + C::OFF_R + 8192, &tmRb, r_full, 64, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * C::A_BYTES;
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * C::A_BYTES;
+      if (issuer) {
         mbar_expect_tx(&full[stage], C::A_BYTES);
         tma_load_2d(sa, &tmQa, &full[stage], 0, tile * 128);
         tma_load_2d(sa + 16384, &tmQb, &full[stage], 64, tile * 128);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == C::STAGES) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      const uint32_t sr = smem_u32(smem + C::OFF_R);
-      mbar_wait(r_full, 0);
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[as], aphase ^ 1);
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::A_BYTES);
-        const uint32_t d_tmem = tmem_base + as * 64;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    const bool issuer = elect_one();
+    const uint32_t sr = smem_u32(smem + C::OFF_R);
+    const uint64_t dR0 = umma_smem_desc(sr, 1024, UMMA_SW128), dR1 = umma_smem_desc(sr + 8192, 256, UMMA_SW32);
+    const uint32_t smem_base = smem_u32(smem);
+    mbar_wait(r_full, 0);
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[as], aphase ^ 1);
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_base + stage * C::A_BYTES;
+      const uint32_t d_tmem = tmem_base + as * 64;
+      const uint64_t dA0 = umma_smem_desc(sa, 1024, UMMA_SW128), dA1 = umma_smem_desc(sa + 16384, 256, UMMA_SW32);
+      if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(d_tmem, umma_smem_desc(sa + k * 32, 1024, UMMA_SW128), umma_smem_desc(sr + k * 32, 1024, UMMA_SW128),
-                  idesc, k != 0);
-        umma_ss(d_tmem, umma_smem_desc(sa + 16384, 256, UMMA_SW32), umma_smem_desc(sr + 8192, 256, UMMA_SW32), idesc,
-                1);
+        for (int k = 0; k < 4; ++k) umma_ss(d_tmem, dA0 + 2 * k, dR0 + 2 * k, idesc, k != 0);
+        umma_ss(d_tmem, dA1, dR1, idesc, 1);
         umma_commit(&empty[stage]);
         umma_commit(&acc_full[as]);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-        if (++as == C::ACC) {
-          as = 0;
-          aphase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == C::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+      if (++as == C::ACC) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {

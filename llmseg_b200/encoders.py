@@ -127,8 +127,9 @@ class SamEncoder:
             pos = torch.arange(m.numel(), dtype=torch.int32)
             tok2win = torch.empty(B * g * g, dtype=torch.int32)
             tok2win[m[valid].long()] = pos[valid]          # token row -> (window, slot) position
+            pad_wins = (~valid).view(B * nw * nw, ws * ws).any(dim=1).nonzero().flatten().to(torch.int32)
             dev = self.device
-            self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev))
+            self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev), pad_wins.to(dev))
         return self._maps[B]
 
     def forward(self, images: Tensor) -> Tensor:
@@ -140,7 +141,7 @@ class SamEncoder:
         a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
         x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S)
         del a
-        win_map, n_win, tok2win = self._window_maps(B)
+        win_map, n_win, tok2win, pad_wins = self._window_maps(B)
         scale = hd ** -0.5
         for blk in self.blocks:
             if blk["window"] > 0:
@@ -167,7 +168,8 @@ class SamEncoder:
                     ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
                                  seq_pad=sw_pad, row_map=tok2win)
                     o = h  # reuse the LN output buffer for the attention output (same shape)
-                ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+                ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
+                                 seq_ids=pad_wins)
                 ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
                                 inv_scale=1.0 / scale, qext=qext)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,

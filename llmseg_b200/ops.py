@@ -153,12 +153,20 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: 
 
 
 def fill_kv_rows(k: torch.Tensor, vt: torch.Tensor, bias_qkv: torch.Tensor, pos_map: torch.Tensor, *, batch: int,
-                 heads: int, head_dim: int, seq_in: int, seq_pad: int) -> None:
-    """k / vt entries of window-padding positions (pos_map < 0) <- projection bias (zero tokens after LN)."""
+                 heads: int, head_dim: int, seq_in: int, seq_pad: int, seq_ids: Optional[torch.Tensor] = None) -> None:
+    """k / vt entries of window-padding positions (pos_map < 0) <- projection bias (zero tokens after LN).
+    seq_ids (int32): the sequences that contain padding; None visits all `batch` sequences."""
     _req_bf16(k, vt, bias_qkv)
     assert pos_map.dtype == torch.int32 and pos_map.numel() == batch * seq_in
+    n = batch
+    if seq_ids is not None:
+        assert seq_ids.dtype == torch.int32 and seq_ids.is_cuda
+        n = seq_ids.numel()
+        if n == 0:
+            return
     check(_lib.lib().llmseg_fill_kv_rows(k.data_ptr(), vt.data_ptr(), bias_qkv.data_ptr(), pos_map.data_ptr(),
-                                         batch, heads, head_dim, seq_in, seq_pad, _stream()), "fill_kv_rows")
+                                         _ptr(seq_ids), n, heads, head_dim, seq_in, seq_pad, _stream()),
+          "fill_kv_rows")
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, *, batch: int,

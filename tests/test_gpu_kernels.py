@@ -273,7 +273,7 @@ def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
     enc.cfg, enc.device, enc._maps = SamCfg(), DEV, {}
     B, H, hd, ws = 1, 2, 80, 14
     D, S, sw, sw_pad = H * hd, 4096, 196, 200
-    win_map, n_win, tok2win = enc._window_maps(B)
+    win_map, n_win, tok2win, pad_wins = enc._window_maps(B)
     nb = B * n_win
     g = torch.Generator().manual_seed(7)
     x = _bf(torch.randn(B * S, D, generator=g))
@@ -288,7 +288,8 @@ def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
         qext = torch.zeros(nb * H, sw_pad, 32, device=DEV, dtype=torch.bfloat16)
         if folded:
             ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad, row_map=tok2win)
-            ops.fill_kv_rows(k, vt, bias, win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad)
+            ops.fill_kv_rows(k, vt, bias, win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
+                             seq_ids=pad_wins if folded == "listed" else None)
         else:
             xp = torch.zeros(nb * sw, D, device=DEV, dtype=torch.bfloat16)
             valid = win_map >= 0
@@ -308,11 +309,13 @@ def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
         out[win_map[valid].long()] = o[valid]
         return k, vt, out
 
+    assert pad_wins.numel() == 9      # right column, bottom row and the corner of the 5x5 window grid
     k0, vt0, o0 = run(False)
-    k1, vt1, o1 = run(True)
-    assert torch.equal(k0, k1) and torch.equal(vt0, vt1)
-    assert not torch.isnan(o1.float()).any()
-    assert torch.equal(o0, o1)
+    for mode in (True, "listed"):
+        k1, vt1, o1 = run(mode)
+        assert torch.equal(k0, k1) and torch.equal(vt0, vt1)
+        assert not torch.isnan(o1.float()).any()
+        assert torch.equal(o0, o1)
 
 
 def test_patchify_embed_splice_im2col(cuda_lib):
