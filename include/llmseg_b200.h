@@ -88,7 +88,7 @@ typedef struct {
   /* Optional scratch (NULL / 0 = none): llmseg_gemm_workspace_bytes() bytes of device memory, 256-byte
    * aligned, ZERO-FILLED once by the caller before its first use (the library leaves its flag area zeroed
    * after every call) and never used by two GEMMs that may run concurrently (one buffer per stream).  With
-   * it, problems whose last wave of output tiles would leave most SMs idle split that wave along K across
+   * it (a) row statistics can be finished in-kernel (stats_final) and (b) problems whose last wave of output tiles would leave most SMs idle split that wave along K across
    * all SMs (stream-K tail: fp32 partial tiles + flags live in the workspace). */
   void* workspace;
   size_t workspace_bytes;
@@ -103,9 +103,29 @@ typedef struct {
    * Q-K-V split.  Replaces the separate norm pass over x (reference image_encoder.py:179,191;
    * transformers CLIPEncoderLayer / LlamaDecoderLayer norms) by a statistics-only read. */
   const void* row_stats;
+  /* row_stats_parts > 0: row_stats is instead [M][row_stats_parts] float2 partial (sum, sum of squares) of
+   * each A row — what a previous llmseg_gemm wrote through stats_out — and the epilogue derives
+   * mean = Σsum/norm_dim, rstd = rsqrt(Σsq/norm_dim - mean² + norm_eps)  (norm_rms: rsqrt(Σsq/norm_dim + eps)). */
+  int row_stats_parts;
+  int norm_dim;
+  float norm_eps;
+  int norm_rms;
+  /* LLMSEG_GEMM_PLAIN producer side: float2 [out rows][llmseg_gemm_stats_parts(M, N)] — every epilogue warp
+   * writes the (sum, sum of squares) of its share of each output row (fp32 values before the bf16 store), so
+   * the norm that follows needs no pass over C at all.  NULL = off. */
+  void* stats_out;
+  /* With stats_final (float2 [M], needs stats_out, the workspace and no out_row_map) the partials are also
+   * finished inside the kernel: the last tile to complete a 128-row block reduces that block's partials (in
+   * index order — deterministic) into (mean, rstd) with stats_dim / stats_eps / stats_rms, ready to be passed
+   * as the next GEMM's row_stats with row_stats_parts = 0. */
+  void* stats_final;
+  int stats_dim;
+  float stats_eps;
+  int stats_rms;
 } llmseg_gemm_params;
 int llmseg_gemm(const llmseg_gemm_params* p, void* stream);
 size_t llmseg_gemm_workspace_bytes(void);
+int llmseg_gemm_stats_parts(int M, int N);
 
 /* ------------------------------------------------------------------------------------------
  * Fused attention  softmax(scale·QKᵀ + bias + mask)·V   (flash-style, tcgen05/TMEM, TMA-fed).

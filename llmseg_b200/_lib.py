@@ -29,6 +29,9 @@ class GemmParams(C.Structure):
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
         ("row_stats", c_void_p),
+        ("row_stats_parts", c_int), ("norm_dim", c_int), ("norm_eps", c_float), ("norm_rms", c_int),
+        ("stats_out", c_void_p),
+        ("stats_final", c_void_p), ("stats_dim", c_int), ("stats_eps", c_float), ("stats_rms", c_int),
     ]
 
 
@@ -55,6 +58,7 @@ def _declare(lib):
         getattr(lib, name)  # raises AttributeError if the .so is stale
     lib.llmseg_gemm.argtypes = [C.POINTER(GemmParams), c_void_p]
     lib.llmseg_gemm_workspace_bytes.restype = C.c_size_t
+    lib.llmseg_gemm_stats_parts.argtypes = [c_int, c_int]
     lib.llmseg_attention.argtypes = [C.POINTER(AttnParams), c_void_p]
     lib.llmseg_relpos_prep.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_float, c_void_p, c_int, c_void_p, c_void_p]
@@ -89,7 +93,7 @@ def _declare(lib):
 # every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
-    "llmseg_gemm", "llmseg_gemm_workspace_bytes", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm", "llmseg_norm_stats",
+    "llmseg_gemm", "llmseg_gemm_workspace_bytes", "llmseg_gemm_stats_parts", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm", "llmseg_norm_stats",
     "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss",

@@ -57,6 +57,16 @@ struct GemmDev {
   // one contiguous range of sk_w k-blocks per CTA pair; see gemm2_kernel.
   // LayerNorm / RMSNorm of the A rows folded into the epilogue (see include/llmseg_b200.h: row_stats)
   const float2* row_stats;
+  int stats_parts_in;    // 0: row_stats = (mean, rstd) per row; > 0: that many (sum, sum of squares) partials per row
+  float norm_inv_dim, norm_eps;
+  int norm_rms;
+  int tma_store;         // PLAIN, no row map: C leaves through shared memory + TMA tile stores (pair kernel)
+  float2* stats_out;     // PLAIN: per-row (sum, sum of squares) partials of this GEMM's output, or null
+  int stats_parts_out;   // partials per row = num_n_tiles * 2 (one per epilogue warp sharing a row)
+  float2* stats_final;   // (mean, rstd) per output row, finished in-kernel by the last tile of a row block
+  int* stats_counters;   // [num_m_tiles] arrivals per 128-row block (zero before and after the launch)
+  float so_inv_dim, so_eps;
+  int so_rms;
   int sk_w;
   float* sk_ws;   // fp32 partial tiles: [pair][cta rank][BN/4][128 rows] float4
   int* sk_flags;  // [pair][cta rank]: 1 = that pair's partial is complete
@@ -166,8 +176,11 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev& p, EpiPrefetch& pf, 
     }
   }
 }
+// stage_row != nullptr: the packed bf16 groups go to this row of the warp's 128B-swizzled [32 x 64] staging
+// tile (16-byte chunk index chunk0 + j/8, XOR row&7) instead of global memory; a TMA store follows.
 __device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, int out_row, int n0,
-                                          const EpiPrefetch& pf) {
+                                          const EpiPrefetch& pf, float& st_s, float& st_ss,
+                                          uint8_t* stage_row = nullptr, int chunk0 = 0, int swz = 0) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int col = n0 + j;
@@ -206,12 +219,22 @@ __device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, i
         v[2 * e + 1] += f.y;
       }
     }
+    if (p.stats_out != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        st_s += v[e];
+        st_ss = fmaf(v[e], v[e], st_ss);
+      }
+    }
     uint4 o;
     o.x = pack_bf16(v[0], v[1]);
     o.y = pack_bf16(v[2], v[3]);
     o.z = pack_bf16(v[4], v[5]);
     o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(p.C + (size_t)out_row * p.ldc + col) = o;
+    if (stage_row != nullptr)
+      *reinterpret_cast<uint4*>(stage_row + (((chunk0 + (j >> 3)) ^ swz) << 4)) = o;
+    else
+      *reinterpret_cast<uint4*>(p.C + (size_t)out_row * p.ldc + col) = o;
   }
 }
 
@@ -455,34 +478,28 @@ __device__ __forceinline__ float* sk_slot(const GemmDev& p, int bn, int pair, in
 // acc[0..32) += partial columns [c0, c0+32) of this thread's row, for every peer
 __device__ __forceinline__ void sk_accumulate(const GemmDev& p, int bn, uint32_t* r, int c0, int row_in_cta,
                                               int pair, int cta_rank, int n_peers) {
-  // two peers per round: 16 independent 16-byte loads in flight hide most of the L2 round trip
-  for (int pr = 1; pr <= n_peers; pr += 2) {
-    const bool two = pr + 1 <= n_peers;
-    const float4* ws0 = reinterpret_cast<const float4*>(sk_slot(p, bn, pair + pr, cta_rank)) +
-                        (size_t)(c0 >> 2) * 128 + row_in_cta;
-    const float4* ws1 = reinterpret_cast<const float4*>(sk_slot(p, bn, pair + pr + (two ? 1 : 0), cta_rank)) +
-                        (size_t)(c0 >> 2) * 128 + row_in_cta;
-    float4 f0[8], f1[8];
+  for (int pr = 1; pr <= n_peers; ++pr) {
+    const float4* ws = reinterpret_cast<const float4*>(sk_slot(p, bn, pair + pr, cta_rank)) +
+                       (size_t)(c0 >> 2) * 128 + row_in_cta;
+    float4 f[8];
 #pragma unroll
-    for (int v = 0; v < 8; ++v) f0[v] = __ldcg(ws0 + v * 128);
-#pragma unroll
-    for (int v = 0; v < 8; ++v) f1[v] = two ? __ldcg(ws1 + v * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = 0; v < 8; ++v) f[v] = __ldcg(ws + v * 128);
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
-      r[4 * v + 0] = __float_as_uint(__uint_as_float(r[4 * v + 0]) + f0[v].x + f1[v].x);
-      r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + f0[v].y + f1[v].y);
-      r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + f0[v].z + f1[v].z);
-      r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + f0[v].w + f1[v].w);
+      r[4 * v + 0] = __float_as_uint(__uint_as_float(r[4 * v + 0]) + f[v].x);
+      r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + f[v].y);
+      r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + f[v].z);
+      r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + f[v].w);
     }
   }
 }
 // partial segment: this warp's share (32 rows x half the columns) of the fp32 accumulators -> workspace
-template <int BN>
+template <int BN, int NP>
 __device__ __forceinline__ void sk_dump(const GemmDev& p, uint32_t taddr, int quarter, int chalf, int lane,
                                         int pair, int cta_rank) {
   float4* ws = reinterpret_cast<float4*>(sk_slot(p, BN, pair, cta_rank)) + quarter * 32 + lane;
 #pragma unroll 1
-  for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+  for (int c = chalf * (BN / 32 / NP); c < (chalf + 1) * (BN / 32 / NP); ++c) {
     uint32_t r[32];
     tmem_ld32(taddr + c * 32, r);
     tmem_ld_wait();
@@ -503,26 +520,87 @@ struct SkOwner {
   int pair, cta_rank, n_peers;  // n_peers == 0: ordinary tile
 };
 
+// rstd of A row `row` for the folded norm: either stored directly or reduced from the (sum, sum of squares)
+// partials the producing GEMM's epilogue wrote (stats_out).  Called BEFORE the wait for the accumulators.
+__device__ __forceinline__ float row_rstd(const GemmDev& p, int row) {
+  if (p.row_stats == nullptr || row >= p.M) return 1.f;
+  if (p.stats_parts_in == 0) return __ldg(p.row_stats + row).y;
+  const float2* st = p.row_stats + (size_t)row * p.stats_parts_in;
+  float s = 0.f, ss = 0.f;
+  for (int i0 = 0; i0 < p.stats_parts_in; i0 += 8) {  // 8 independent loads per round trip
+    float2 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = i0 + j < p.stats_parts_in ? __ldcg(st + i0 + j) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s += v[j].x;
+      ss += v[j].y;
+    }
+  }
+  const float mean = p.norm_rms ? 0.f : s * p.norm_inv_dim;
+  const float var = fmaxf(fmaf(-mean, mean, ss * p.norm_inv_dim), 0.f);
+  return rsqrtf(var + p.norm_eps);
+}
+
+// After a tile's epilogue (all 8 epilogue warps of the CTA): count the tile in for its 128-row block; the
+// CTA that brings the count to num_n_tiles reduces the block's partials — in index order, so the result
+// does not depend on which CTA that is — into (mean, rstd) and re-arms the counter.
+__device__ __forceinline__ void stats_finish(const GemmDev& p, int m_blk, int warp, int lane, volatile int* s_flag) {
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (warp == 4 && lane == 0) {
+    const int old = atomicAdd(p.stats_counters + m_blk, 1);
+    const int last = old == p.num_n_tiles - 1;
+    if (last) p.stats_counters[m_blk] = 0;
+    *s_flag = last;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (*s_flag) {
+    __threadfence();
+    const int t = (warp - 4) * 32 + lane;
+    const int row = m_blk * BM + t;
+    if (t < BM && row < p.M) {
+      const float2* st = p.stats_out + (size_t)row * p.stats_parts_out;
+      float s = 0.f, ss = 0.f;
+      for (int i0 = 0; i0 < p.stats_parts_out; i0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = i0 + j < p.stats_parts_out ? __ldcg(st + i0 + j) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s += v[j].x;
+          ss += v[j].y;
+        }
+      }
+      const float mean = p.so_rms ? 0.f : s * p.so_inv_dim;
+      const float var = fmaxf(fmaf(-mean, mean, ss * p.so_inv_dim), 0.f);
+      p.stats_final[row] = make_float2(mean, rsqrtf(var + p.so_eps));
+    }
+  }
+}
+
 // One warp's share of a finished 128 x BN accumulator tile: quarter = TMEM lane quarter (32 rows),
-// chalf = which half of the tile's columns.
-template <int BN, int MODE, bool ROPE>
+// chalf = which of the NP column parts of the tile (NP warps share a lane quarter).
+template <int BN, int MODE, bool ROPE, int NP = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage, uint32_t taddr, int m_blk,
-                                              int n_blk, int quarter, int chalf, int lane,
-                                              const SkOwner sk = SkOwner{0, 0, 0}) {
+                                              int n_blk, int quarter, int chalf, int lane, float rs,
+                                              const SkOwner sk = SkOwner{0, 0, 0}, uint8_t* epi_stage = nullptr,
+                                              const CUtensorMap* tmC = nullptr) {
   const int row = m_blk * BM + quarter * 32 + lane;
   int out_row = row;
   if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
     out_row = p.out_row_map[row];  // QKV: position of this token in the (sequence, slot) index space
   const bool live = row < p.M && out_row >= 0;
-  float rs = 1.f;
   const bool fold = MODE != MODE_RELPOS && p.row_stats != nullptr;
-  if (fold && row < p.M) rs = __ldg(p.row_stats + row).y;
+  float st_s = 0.f, st_ss = 0.f;
   if (MODE == MODE_RELPOS) {
     relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
   } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
+    // (128-column group c, 32-column offset `half`) pairs: BN/64 of them, dealt out to the NP warps
 #pragma unroll 1
-    for (int c = 0; c < BN / 128; ++c) {
-      const int half = chalf;
+    for (int u = chalf; u < BN / 64; u += NP) {
+      const int c = u >> 1;
+      const int half = u & 1;
       uint32_t lo[32], hi[32];
       tmem_ld32(taddr + c * 128 + half * 32, lo);
       tmem_ld32(taddr + c * 128 + half * 32 + 64, hi);
@@ -540,7 +618,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
     }
   } else {
 #pragma unroll 1
-    for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+    for (int c = chalf * (BN / 32 / NP); c < (chalf + 1) * (BN / 32 / NP); ++c) {
       uint32_t r[32];
       const int n0 = n_blk * BN + c * 32;
       tmem_ld32(taddr + c * 32, r);
@@ -549,12 +627,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       tmem_ld_wait();
       if (sk.n_peers > 0) sk_accumulate(p, BN, r, c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
       if (fold) row_scale(r, rs);
+      const bool staged = MODE == LLMSEG_GEMM_PLAIN && epi_stage != nullptr && p.tma_store;
+      if (staged && (c & 1) == 0) {
+        // the previous tile store of this warp must have drained the staging tile before it is rewritten
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
       if (live && n0 < p.N) {
-        if (MODE == LLMSEG_GEMM_PLAIN) epi_plain(p, r, out_row, n0, pf);
+        if (MODE == LLMSEG_GEMM_PLAIN)
+          epi_plain(p, r, out_row, n0, pf, st_s, st_ss, staged ? epi_stage + lane * 128 : nullptr, (c & 1) * 4,
+                    lane & 7);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
         else epi_qkv(p, r, out_row, n0, pf);
       }
+      if (staged && (c & 1) == 1) {
+        // 64 columns x 32 rows staged: hand them to the TMA (full 128-byte lines; rows >= M and
+        // columns >= N are clipped by the tensor map)
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, epi_stage, n_blk * BN + (c - 1) * 32, m_blk * BM + quarter * 32);
+          bulk_commit();
+        }
+      }
     }
+    if (MODE == LLMSEG_GEMM_PLAIN && p.stats_out != nullptr && live)
+      p.stats_out[(size_t)out_row * p.stats_parts_out + n_blk * NP + chalf] = make_float2(st_s, st_ss);
   }
 }
 
@@ -696,12 +794,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
       const int m_blk = (n_fastest ? grp / p.num_n_tiles : grp % m_groups) * cl + cta_rank;
       const int n_blk = n_fastest ? grp % p.num_n_tiles : grp / m_groups;
+      const float rs = MODE == MODE_RELPOS ? 1.f : row_rstd(p, m_blk * BM + quarter * 32 + lane);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-      epilogue_tile<BN, MODE, ROPE>(p, rp_stage, taddr, m_blk, n_blk, quarter, chalf, lane);
+      epilogue_tile<BN, MODE, ROPE>(p, rp_stage, taddr, m_blk, n_blk, quarter, chalf, lane, rs);
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
+      if (MODE == LLMSEG_GEMM_PLAIN && p.stats_final != nullptr)
+        stats_finish(p, m_blk, warp, lane, reinterpret_cast<volatile int*>(tmem_ptr + 1));
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -733,22 +834,32 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_HALF_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // epilogue staging: one [32 rows x 64 cols] bf16 tile (4 KB, 128B-swizzled) per epilogue warp
+  static constexpr int EPI_TILE_BYTES = 32 * 128;
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + 8 * EPI_TILE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 256;
 };
 
+// Epilogue warps per CTA (G2_EPI_WARPS/4 per TMEM lane quarter, each BN*4/G2_EPI_WARPS columns).  16 warps
+// (640 threads, 96 registers each) measured 8 % SLOWER than 8 on the SAM lin1 shape: the epilogue spills
+// and the extra warps do not buy latency hiding that matters.
+constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_THREADS = 128 + G2_EPI_WARPS * 32;
 template <int BN, int MODE, bool ROPE>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const GemmDev p) {
+             const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* stats_bar = tmem_empty + 3;  // [4]: epilogue warps -> statistics warp, one phase per tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -766,8 +877,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 16);  // leader's copy: 8 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[i], 2 * G2_EPI_WARPS);  // leader's copy: epilogue warps x 2 CTAs
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&stats_bar[i], G2_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_ptr, C::TMEM_COLS);
@@ -870,11 +982,74 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
+  } else if (warp == 3) {
+    // ---- statistics warp: finishes the per-row (sum, sum of squares) partials off the critical path.  It
+    //      walks the same schedule; for every finished tile it counts the tile in for its 128-row block and,
+    //      when it was the last of the block's N-tiles (any CTA), reduces the partials — in index order, so
+    //      the result does not depend on who is last — into (mean, rstd) and re-arms the counter. ----
+    if (MODE == LLMSEG_GEMM_PLAIN && p.stats_final != nullptr) {
+      int st_it = 0;
+      SkWalk walk(p, num_groups, cluster_id, num_clusters);
+      SkSeg sg;
+      for (int grp = cluster_id;; grp += num_clusters) {
+        int g = grp;
+        if (grp >= walk.full_end) {
+          if (!walk.next(sg)) break;
+          if (sg.k0 > 0) continue;  // partial segment: no epilogue, no statistics
+          g = sg.grp;
+        }
+        const int m_blk = (n_fastest ? g / p.num_n_tiles : g % m_groups) * 2 + cta_rank;
+        mbar_wait(&stats_bar[st_it & 3], (st_it >> 2) & 1);
+        ++st_it;
+        __threadfence();
+        int last = 0;
+        if (lane == 0) {
+          const int old = atomicAdd(p.stats_counters + m_blk, 1);
+          last = old == p.num_n_tiles - 1;
+          if (last) p.stats_counters[m_blk] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          // lane handles rows lane, lane+32, lane+64, lane+96 of the block; all 4 x 8 loads of a round are in
+          // flight together (this reduction is the kernel's tail when the block finishes last)
+          float sm[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int i0 = 0; i0 < p.stats_parts_out; i0 += 8) {
+            float2 v[4][8];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              const int row = m_blk * BM + lane + 32 * rr;
+              const float2* st = p.stats_out + (size_t)(row < p.M ? row : 0) * p.stats_parts_out;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[rr][j] = (row < p.M && i0 + j < p.stats_parts_out) ? __ldcg(st + i0 + j) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                sm[rr] += v[rr][j].x;
+                ss[rr] += v[rr][j].y;
+              }
+          }
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int row = m_blk * BM + lane + 32 * rr;
+            if (row < p.M) {
+              const float mean = p.so_rms ? 0.f : sm[rr] * p.so_inv_dim;
+              const float var = fmaxf(fmaf(-mean, mean, ss[rr] * p.so_inv_dim), 0.f);
+              p.stats_final[row] = make_float2(mean, rsqrtf(var + p.so_eps));
+            }
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     const int quarter = warp & 3;
     const int chalf = (warp - 4) >> 2;
     int as = 0;
     uint32_t aphase = 0;
+    int st_it = 0;
     SkWalk walk(p, num_groups, cluster_id, num_clusters);
     SkSeg sg;
     for (int grp = cluster_id;; grp += num_clusters) {
@@ -889,14 +1064,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       const int m_blk = (n_fastest ? g / p.num_n_tiles : g % m_groups) * 2 + cta_rank;
       const int n_blk = n_fastest ? g % p.num_n_tiles : g / m_groups;
+      const float rs = partial ? 1.f : row_rstd(p, m_blk * BM + quarter * 32 + lane);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
       if (partial) {
         // fp32 accumulators -> workspace, then publish (all 256 epilogue threads have fenced their stores)
-        sk_dump<BN>(p, taddr, quarter, chalf, lane, cluster_id, cta_rank);
+        sk_dump<BN, G2_EPI_WARPS / 4>(p, taddr, quarter, chalf, lane, cluster_id, cta_rank);
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");
         if (warp == 4 && lane == 0) {
           int* flag = p.sk_flags + cluster_id * 2 + cta_rank;
           asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -914,11 +1090,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               } while (v == 0);
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");
         }
-        epilogue_tile<BN, MODE, ROPE>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, own);
+        epilogue_tile<BN, MODE, ROPE, G2_EPI_WARPS / 4>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
+                                                        smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC);
         if (own.n_peers > 0) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");  // every reader of the partials is done
+          asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");  // every reader of the partials is done
           if (warp == 4 && lane == 0)
             for (int pr = 1; pr <= own.n_peers; ++pr) p.sk_flags[(cluster_id + pr) * 2 + cta_rank] = 0;
         }
@@ -926,11 +1103,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[as]), 0));
+      if (MODE == LLMSEG_GEMM_PLAIN && p.stats_final != nullptr && !partial) {
+        // partials of this tile are written: tell the statistics warp (release at CTA scope; it adds the
+        // GPU-scope fence) and move on — nothing here waits on other CTAs
+        if (lane == 0) mbar_arrive(&stats_bar[st_it & 3]);
+        ++st_it;
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
       }
     }
+    if (lane == 0) bulk_wait0();  // this warp's TMA stores have landed before the CTA may exit
   }
 
   tc_fence_before();
@@ -943,7 +1127,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 template <int BN, int MODE, bool ROPE>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int grid,
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmDev& d, int grid,
             cudaStream_t stream) {
   auto kern = gemm2_kernel<BN, MODE, ROPE>;
   static bool attr_done = false;
@@ -953,7 +1137,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, in
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(G2_THREADS);
   cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -963,7 +1147,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, d));
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, d));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -1034,6 +1218,15 @@ int pick_grid(int groups, int cl, int sms) {
   return clusters * cl;
 }
 
+// LLMSEG_GEMM_TMA_STORE=0: the pair kernel's PLAIN epilogue writes C with per-lane 16-byte stores again
+bool tma_store_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_GEMM_TMA_STORE");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0;
+}
 // LLMSEG_GEMM_STREAMK=0 disables the stream-K tail (A/B measurements)
 bool streamk_enabled() {
   static int mode = -1;
@@ -1052,7 +1245,9 @@ bool relpos_win_enabled() {
   }
   return mode != 0;
 }
-constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_FLAG_BYTES = 16384;   // [0, 2048): stream-K flags; [2048, 16384): stats row-block counters
+constexpr size_t SK_COUNTER_OFF = 2048;
+constexpr int SK_MAX_COUNTERS = (16384 - 2048) / 4;
 constexpr size_t SK_MAX_PAIRS = 128;
 constexpr size_t SK_WS_BYTES = SK_FLAG_BYTES + SK_MAX_PAIRS * 2 * 128 * 256 * sizeof(float);
 
@@ -1096,9 +1291,31 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   d.rope_cos = static_cast<const bf16*>(p->rope_cos);
   d.rope_sin = static_cast<const bf16*>(p->rope_sin);
   d.row_stats = static_cast<const float2*>(p->row_stats);
+  d.stats_parts_in = p->row_stats_parts;
+  d.norm_inv_dim = p->norm_dim > 0 ? 1.0f / (float)p->norm_dim : 0.f;
+  d.norm_eps = p->norm_eps;
+  d.norm_rms = p->norm_rms;
+  d.stats_out = static_cast<float2*>(p->stats_out);
   if (p->row_stats != nullptr)
-    LLMSEG_REQUIRE((reinterpret_cast<uintptr_t>(p->row_stats) & 7) == 0, LLMSEG_EALIGN,
-                   "llmseg_gemm: row_stats must be 8-byte aligned (float2 per row)");
+    LLMSEG_REQUIRE((reinterpret_cast<uintptr_t>(p->row_stats) & 7) == 0 && p->row_stats_parts >= 0 &&
+                       (p->row_stats_parts == 0 || p->norm_dim > 0),
+                   LLMSEG_EARG, "llmseg_gemm: row_stats must be 8-byte aligned; partials need norm_dim > 0");
+  if (p->stats_out != nullptr)
+    LLMSEG_REQUIRE(p->mode == LLMSEG_GEMM_PLAIN && (reinterpret_cast<uintptr_t>(p->stats_out) & 7) == 0,
+                   LLMSEG_EARG, "llmseg_gemm: stats_out needs PLAIN mode and 8-byte alignment");
+  if (p->stats_final != nullptr) {
+    LLMSEG_REQUIRE(p->stats_out != nullptr && p->out_row_map == nullptr && p->stats_dim > 0 &&
+                       (reinterpret_cast<uintptr_t>(p->stats_final) & 7) == 0,
+                   LLMSEG_EARG, "llmseg_gemm: stats_final needs stats_out, no out_row_map and stats_dim > 0");
+    LLMSEG_REQUIRE(p->workspace != nullptr && p->workspace_bytes >= SK_WS_BYTES &&
+                       (p->M + BM - 1) / BM <= SK_MAX_COUNTERS,
+                   LLMSEG_EARG, "llmseg_gemm: stats_final needs the workspace and M <= %d", SK_MAX_COUNTERS * BM);
+    d.stats_final = static_cast<float2*>(p->stats_final);
+    d.stats_counters = reinterpret_cast<int*>(static_cast<uint8_t*>(p->workspace) + SK_COUNTER_OFF);
+    d.so_inv_dim = 1.0f / (float)p->stats_dim;
+    d.so_eps = p->stats_eps;
+    d.so_rms = p->stats_rms;
+  }
 
   bool rope = false;
   if (p->mode == LLMSEG_GEMM_QKV) {
@@ -1136,6 +1353,7 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   //  2.16 waves — slower: a 256x128 pair tile needs twice the L2->SM bytes per flop and becomes L2-bound.)
   d.num_m_tiles = m_tiles;
   d.num_n_tiles = (p->N + bn - 1) / bn;
+  d.stats_parts_out = d.num_n_tiles * 2;
   d.num_k_blocks = (p->K + BK - 1) / BK;
   d.cluster = pick_cluster(m_tiles);
   d.n_fastest = p->M > p->N ? 1 : 0;
@@ -1181,13 +1399,23 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
     uint64_t str[1] = {(uint64_t)p->ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)(bn / 2)};
     if (int e = make_tmap_bf16(&tmB, p->W, 2, dims, str, box, 128)) return e;
+    // C through TMA tile stores: plain row-major output, rows not scattered (LLMSEG_GEMM_TMA_STORE=0: off)
+    CUtensorMap tmC = tmA;
+    d.tma_store = 0;
+    if (p->mode == LLMSEG_GEMM_PLAIN && p->out_row_map == nullptr && tma_store_enabled()) {
+      uint64_t cdims[2] = {(uint64_t)p->N, (uint64_t)p->M};
+      uint64_t cstr[1] = {(uint64_t)p->ldc * 2};
+      uint32_t cbox[2] = {64, 32};
+      if (int e = make_tmap_bf16(&tmC, p->C, 2, cdims, cstr, cbox, 128)) return e;
+      d.tma_store = 1;
+    }
 #define LLMSEG_GEMM2_DISPATCH(BN_)                                                              \
   switch (p->mode) {                                                                            \
-    case LLMSEG_GEMM_PLAIN: return launch2<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, d, pgrid, stream);   \
-    case LLMSEG_GEMM_SWIGLU: return launch2<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, d, pgrid, stream); \
+    case LLMSEG_GEMM_PLAIN: return launch2<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, tmC, d, pgrid, stream);   \
+    case LLMSEG_GEMM_SWIGLU: return launch2<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, tmC, d, pgrid, stream); \
     default:                                                                                    \
-      return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, d, pgrid, stream)              \
-                  : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, d, pgrid, stream);            \
+      return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, tmC, d, pgrid, stream)              \
+                  : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, tmC, d, pgrid, stream);            \
   }
     if (bn == 256) {
       LLMSEG_GEMM2_DISPATCH(256)
@@ -1214,6 +1442,16 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
 }
 
 extern "C" size_t llmseg_gemm_workspace_bytes(void) { return SK_WS_BYTES; }
+
+// partials per output row that llmseg_gemm writes to stats_out for an (M, N) PLAIN problem — must mirror the
+// tile-shape choice in llmseg_gemm (two epilogue warps share a row of every N-tile)
+extern "C" int llmseg_gemm_stats_parts(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  const int m_tiles = (M + BM - 1) / BM;
+  int bn = 256;
+  if (N < 256 || m_tiles * ((N + 255) / 256) < num_sms()) bn = 128;
+  return ((N + bn - 1) / bn) * 2;
+}
 
 extern "C" int llmseg_relpos_prep(const void* q, const void* rel_hw, int n_pad, int bh, int seq,
                                   int seq_pad, int head_dim, int grid, float inv_scale, void* qext,

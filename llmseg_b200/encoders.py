@@ -49,14 +49,19 @@ class _Scratch:
             self._bufs[key] = buf
         return buf
 
-    def stats(self, rows: int) -> Tensor:
-        """fp32 [rows, 2] row-statistics buffer (ops.norm_stats -> ops.gemm(row_stats=...))."""
-        key = ("stats", rows)
+    def stats(self, rows: int, parts: int = 1, tag: str = "a") -> Tensor:
+        """fp32 row-statistics buffer: [rows, 2] for ops.norm_stats, [rows, parts, 2] for GEMM-epilogue partials."""
+        key = ("stats", tag, rows, parts)
         buf = self._bufs.get(key)
         if buf is None:
-            buf = torch.empty((rows, 2), dtype=torch.float32, device=self.device)
+            buf = torch.empty((rows, parts, 2), dtype=torch.float32, device=self.device)
             self._bufs[key] = buf
         return buf
+
+    def gemm_stats(self, M: int, N: int, eps: float, tag: str, rms: bool = False):
+        """ops.RowStats buffer for gemm(stats_out=...) of an [M, *] x [N, *] problem (cached)."""
+        parts = ops.gemm_stats_parts(M, N)
+        return ops.gemm_stats_buffer(M, N, M, eps, rms=rms, out=self.stats(M, parts + 1, tag))
 
 
 # ==============================================================================================
@@ -139,7 +144,11 @@ class SamEncoder:
         g, D, H, hd = cfg.grid, cfg.embed_dim, self.heads, self.hd
         S = g * g
         a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
-        x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S)
+        # stA / stB: per-row (sum, sum of squares) partials of the residual stream, written by the epilogue of
+        # whichever GEMM produced it (patch embed / lin2 -> stA for norm1, proj -> stB for norm2)
+        stA = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "a") if FOLD_NORM else None
+        stB = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "b") if FOLD_NORM else None
+        x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S, stats_out=stA)
         del a
         win_map, n_win, tok2win, pad_wins = self._window_maps(B)
         scale = hd ** -0.5
@@ -158,10 +167,9 @@ class SamEncoder:
                 vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
                 if FOLD_NORM:
-                    st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
                     wq, bq = blk["f_qkv"]
                     ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
-                                 row_map=tok2win, row_stats=st)
+                                 row_map=tok2win, row_stats=stA)
                     o = self.scratch.zeros("o", B * S, D)
                 else:
                     h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
@@ -174,7 +182,7 @@ class SamEncoder:
                                 inv_scale=1.0 / scale, qext=qext)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
                               qext=qext, kext=self.kext_win, ext_cols=32, out_row_map=win_map)
-                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
+                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x, stats_out=stB)
             else:
                 q = self.scratch.zeros("qg", B * H, S, hd)
                 k = self.scratch.zeros("kg", B * H, S, hd)
@@ -182,9 +190,8 @@ class SamEncoder:
                 qext = self.scratch.zeros("qext_g", B * H, S, 64)
                 rb = self.scratch.zeros("rb_g", B * H, S, 64)
                 if FOLD_NORM:
-                    st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
                     wq, bq = blk["f_qkv"]
-                    ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S, row_stats=st)
+                    ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S, row_stats=stA)
                     o = self.scratch.zeros("o", B * S, D)
                 else:
                     h = ops.layernorm(x, blk["ln1_w"], blk["ln1_b"], cfg.ln_eps)
@@ -194,16 +201,15 @@ class SamEncoder:
                                 inv_scale=1.0 / scale, qext=qext, row_bias=rb)
                 ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale,
                               qext=qext, kext=self.kext_glb, row_bias=rb, ext_cols=64)
-                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x)
+                ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x, stats_out=stB)
             if FOLD_NORM:
-                st = ops.norm_stats(x, cfg.ln_eps, out=self.scratch.stats(B * S))
                 w1, b1 = blk["f_1"]
-                m = ops.gemm(x, w1, b1, act="gelu", row_stats=st)
+                m = ops.gemm(x, w1, b1, act="gelu", row_stats=stB)
             else:
                 h = ops.layernorm(x, blk["ln2_w"], blk["ln2_b"], cfg.ln_eps)
                 m = ops.gemm(h, blk["w1"], blk["b1"], act="gelu")
                 del h
-            ops.gemm(m, blk["w2"], blk["b2"], residual=x, out=x)
+            ops.gemm(m, blk["w2"], blk["b2"], residual=x, out=x, stats_out=stA)
             del m
         y = ops.gemm(x, self.w_neck1)
         y = ops.layernorm(y, self.ln_n1[0], self.ln_n1[1], 1e-6)
@@ -276,9 +282,12 @@ class ClipTower:
         q = self.scratch.zeros("q", N * H, T_pad, hd)
         k = self.scratch.zeros("k", N * H, T_pad, hd)
         vt = self.scratch.zeros("vt", N * H, hd, T_pad)
+        stB = self.scratch.gemm_stats(N * T, D, cfg.eps, "b") if FOLD_NORM else None
+        st = None
         for L in self.layers:
             if FOLD_NORM:
-                st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T))
+                if st is None:  # first layer: x comes out of pre_layrnorm, not out of a GEMM
+                    st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T, 1, "n"))
                 wq, bq = L["f_qkv"]
                 ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad, row_stats=st)
                 h = self.scratch.zeros("o", N * T, D)
@@ -286,15 +295,15 @@ class ClipTower:
                 h = ops.layernorm(x, L["ln1"][0], L["ln1"][1], cfg.eps)
                 ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
             ops.attention(q, k, vt, h, batch=N, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
-            ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x)
+            ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x, stats_out=stB)
             if FOLD_NORM:
-                st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T))
                 w1, b1 = L["f_1"]
-                m = ops.gemm(x, w1, b1, act="quick_gelu", row_stats=st)
+                m = ops.gemm(x, w1, b1, act="quick_gelu", row_stats=stB)
+                st = self.scratch.gemm_stats(N * T, D, cfg.eps, "a")
             else:
                 h = ops.layernorm(x, L["ln2"][0], L["ln2"][1], cfg.eps)
                 m = ops.gemm(h, L["w1"], L["b1"], act="quick_gelu")
-            ops.gemm(m, L["w2"], L["b2"], residual=x, out=x)
+            ops.gemm(m, L["w2"], L["b2"], residual=x, out=x, stats_out=st)
         feats = ops.gemm(x, self.proj_w, self.proj_b, out_row_map=self._drop_cls_map(N), out_rows=N * (T - 1))
         return feats.view(N, T - 1, -1)
 
@@ -348,9 +357,12 @@ class LlamaDecoder:
         vt = self.scratch.zeros("vt", n_seq * H, hd, T_pad)
         x = embeds
         scale = 1.0 / math.sqrt(hd)
+        stB = self.scratch.gemm_stats(n_seq * T, cfg.hidden, cfg.eps, "b", rms=True) if FOLD_NORM else None
+        st = None
         for L in self.layers:
             if FOLD_NORM:
-                st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T))
+                if st is None:  # first layer: x is the spliced embedding sequence, not a GEMM output
+                    st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T, 1, "n"))
                 ops.gemm_qkv(x, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
                              rope_cos=self.rope_cos, rope_sin=self.rope_sin, row_stats=st)
                 h = self.scratch.zeros("o", n_seq * T, cfg.hidden)
@@ -360,14 +372,14 @@ class LlamaDecoder:
                              rope_cos=self.rope_cos, rope_sin=self.rope_sin)
             ops.attention(q, k, vt, h, batch=n_seq, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=scale,
                           causal=True, kv_len=kv_len)
-            ops.gemm(h, L["w_o"], None, residual=x, out=x)
+            ops.gemm(h, L["w_o"], None, residual=x, out=x, stats_out=stB)
             if FOLD_NORM:
-                st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T))
-                m = ops.gemm(x, L["w_gu"], None, swiglu=True, row_stats=st)
+                m = ops.gemm(x, L["w_gu"], None, swiglu=True, row_stats=stB)
+                st = self.scratch.gemm_stats(n_seq * T, cfg.hidden, cfg.eps, "a", rms=True)
             else:
                 h = ops.rmsnorm(x, L["rms2"], cfg.eps)
                 m = ops.gemm(h, L["w_gu"], None, swiglu=True)
-            ops.gemm(m, L["w_down"], None, residual=x, out=x)
+            ops.gemm(m, L["w_down"], None, residual=x, out=x, stats_out=st)
         if out_rows is not None:
             return ops.rmsnorm(x, self.norm, cfg.eps, src_row_map=out_rows, rows_out=out_rows.numel())
         return ops.rmsnorm(x, self.norm, cfg.eps)

@@ -53,11 +53,46 @@ def _workspace(p: GemmParams, device) -> None:
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
 
 
-def _norm_fold_args(p: GemmParams, row_stats, M: int) -> None:
-    if row_stats is not None and not (row_stats.is_cuda and row_stats.dtype == torch.float32 and
-                                      row_stats.is_contiguous() and row_stats.numel() == 2 * M):
-        raise ValueError("row_stats must be a contiguous fp32 [M, 2] CUDA tensor")
-    p.row_stats = _ptr(row_stats)
+class RowStats:
+    """Per-row normalisation statistics for gemm(row_stats=...): either (mean, rstd) pairs from norm_stats
+    (parts == 0, t = fp32 [rows, 2]) or the (sum, sum of squares) partials a previous gemm(stats_out=...)
+    wrote from its epilogue (t = fp32 [rows, parts, 2]) together with what is needed to finish them."""
+    __slots__ = ("t", "parts", "dim", "eps", "rms", "final")
+
+    def __init__(self, t: torch.Tensor, parts: int, dim: int, eps: float, rms: bool,
+                 final: Optional[torch.Tensor] = None):
+        self.t, self.parts, self.dim, self.eps, self.rms = t, parts, dim, float(eps), bool(rms)
+        self.final = final   # fp32 [rows, 2] (mean, rstd) finished in-kernel by the producing GEMM, or None
+
+
+def gemm_stats_buffer(M: int, N: int, rows_out: int, eps: float, *, rms: bool = False, device="cuda",
+                      out: Optional[torch.Tensor] = None) -> RowStats:
+    """Buffer for gemm(..., stats_out=...) of an [M, K] x [N, K] PLAIN problem writing `rows_out` rows of
+    width N: the norm that follows (over those N columns) reads its statistics from here."""
+    parts = _lib.lib().llmseg_gemm_stats_parts(M, N)
+    if out is None:
+        out = torch.empty((rows_out, parts + 1, 2), dtype=torch.float32, device=device)
+    assert out.dtype == torch.float32 and out.numel() == rows_out * (parts + 1) * 2
+    flat = out.view(-1)
+    part_t = flat[:rows_out * parts * 2].view(rows_out, parts, 2)
+    final = flat[rows_out * parts * 2:].view(rows_out, 2) if rows_out == M else None
+    return RowStats(part_t, parts, N, eps, rms, final)
+
+
+def gemm_stats_parts(M: int, N: int) -> int:
+    return _lib.lib().llmseg_gemm_stats_parts(M, N)
+
+
+def _norm_fold_args(p: GemmParams, row_stats: Optional[RowStats], M: int) -> None:
+    if row_stats is None:
+        return
+    t, parts = row_stats.t, row_stats.parts
+    if row_stats.final is not None:   # finished by the producing GEMM: read (mean, rstd) directly
+        t, parts = row_stats.final, 0
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == 2 * M * max(parts, 1)):
+        raise ValueError("row_stats must hold fp32 [M, 2] or [M, parts, 2] on the GPU")
+    p.row_stats = t.data_ptr()
+    p.row_stats_parts, p.norm_dim, p.norm_eps, p.norm_rms = parts, row_stats.dim, row_stats.eps, int(row_stats.rms)
 
 
 def fold_norm(w: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor] = None,
@@ -80,8 +115,8 @@ def fold_norm(w: torch.Tensor, gamma: torch.Tensor, beta: Optional[torch.Tensor]
     return wf.to(torch.bfloat16).contiguous(), bias2
 
 
-def norm_stats(x: torch.Tensor, eps: float, *, rms: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 [rows, 2] = (mean, rstd) per row of x (rms: (0, rsqrt(mean(x^2)+eps))) for gemm(row_stats=...)."""
+def norm_stats(x: torch.Tensor, eps: float, *, rms: bool = False, out: Optional[torch.Tensor] = None) -> RowStats:
+    """(mean, rstd) per row of x (rms: (0, rsqrt(mean(x^2)+eps))) as a RowStats for gemm(row_stats=...)."""
     _req_bf16(x)
     dim = x.shape[-1]
     x2 = x.reshape(-1, dim) if x.dim() != 2 else x
@@ -89,20 +124,21 @@ def norm_stats(x: torch.Tensor, eps: float, *, rms: bool = False, out: Optional[
         out = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
     check(_lib.lib().llmseg_norm_stats(x2.data_ptr(), x2.stride(0), x2.shape[0], dim, float(eps), int(rms),
                                        out.data_ptr(), _stream()), "norm_stats")
-    return out
+    return RowStats(out, 0, dim, eps, rms)
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          act: Optional[str] = None, residual: Optional[torch.Tensor] = None, res_mod: int = 0,
          out: Optional[torch.Tensor] = None, out_row_map: Optional[torch.Tensor] = None,
          out_rows: Optional[int] = None, swiglu: bool = False,
-         row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         row_stats: Optional[RowStats] = None, stats_out: Optional[RowStats] = None) -> torch.Tensor:
     """out = act(a @ w.T + bias) (+ residual).  a: [M,K] bf16, w: [N,K] bf16 (nn.Linear layout).
 
     out_row_map (int32 [M]) scatters GEMM row r to output row out_row_map[r] (negative = dropped);
     the residual is read at the same output row (modulo res_mod when given).
     swiglu: w rows are (gate0, up0, gate1, up1, ...) and out has N/2 columns.
     row_stats: the row normalisation of `a` folded into the epilogue (w, bias from fold_norm).
+    stats_out: gemm_stats_buffer(M, N, ...) to fill with this GEMM's per-row output statistics.
     """
     _req_bf16(a, w, bias, residual, out)
     M, K = a.shape
@@ -123,6 +159,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     p.mode = GEMM_SWIGLU if swiglu else GEMM_PLAIN
     p.out_row_map = _ptr(out_row_map)
     _norm_fold_args(p, row_stats, M)
+    if stats_out is not None:
+        if swiglu or stats_out.parts != _lib.lib().llmseg_gemm_stats_parts(M, N) or stats_out.dim != N:
+            raise ValueError("stats_out must come from gemm_stats_buffer(M, N, ...) of this (plain) problem")
+        p.stats_out = stats_out.t.data_ptr()
+        if stats_out.final is not None:
+            if out_row_map is not None or not USE_GEMM_WORKSPACE:
+                raise ValueError("in-kernel statistics need the workspace and unscattered output rows")
+            p.stats_final = stats_out.final.data_ptr()
+            p.stats_dim, p.stats_eps, p.stats_rms = stats_out.dim, stats_out.eps, int(stats_out.rms)
     _workspace(p, a.device)
     check(_lib.lib().llmseg_gemm(C.byref(p), _stream()), "gemm")
     return out
@@ -132,7 +177,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q: 
              k: torch.Tensor, vt: torch.Tensor, *, heads: int, head_dim: int, seq_in: int,
              seq_pad: int, rope_cos: Optional[torch.Tensor] = None,
              rope_sin: Optional[torch.Tensor] = None, row_map: Optional[torch.Tensor] = None,
-             row_stats: Optional[torch.Tensor] = None) -> None:
+             row_stats: Optional[RowStats] = None) -> None:
     """QKV projection writing q,k [(b*heads+h), seq_pad, hd] and vt [(b*heads+h), hd, seq_pad].
     row_map (int32 [M]): GEMM row r lands at position m = row_map[r] -> (b, s) = divmod(m, seq_in)."""
     _req_bf16(a, w, bias, q, k, vt, rope_cos, rope_sin)

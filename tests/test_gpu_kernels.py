@@ -241,11 +241,11 @@ def test_norm_folded_into_gemm(cuda_lib, rows, dim, N, rms):
     xf = x.float()
     if rms:
         ref_rstd = torch.rsqrt(xf.pow(2).mean(-1) + 1e-6)
-        assert (st[:, 0] == 0).all() and torch.allclose(st[:, 1], ref_rstd, rtol=1e-5)
+        assert (st.t[:, 0] == 0).all() and torch.allclose(st.t[:, 1], ref_rstd, rtol=1e-5)
         normed = xf * ref_rstd[:, None] * gm.float()
     else:
-        assert torch.allclose(st[:, 0], xf.mean(-1), rtol=1e-5, atol=1e-5)
-        assert torch.allclose(st[:, 1], torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-5)
+        assert torch.allclose(st.t[:, 0], xf.mean(-1), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(st.t[:, 1], torch.rsqrt(xf.var(-1, unbiased=False) + 1e-6), rtol=1e-5)
         normed = torch.nn.functional.layer_norm(xf, (dim,), gm.float(), bt.float(), 1e-6)
     wq, b2 = ops.fold_norm(w, gm, None if rms else bt, b, rms=rms)
     assert (b2 is None) == rms
@@ -260,6 +260,43 @@ def test_norm_folded_into_gemm(cuda_lib, rows, dim, N, rms):
     h = ops.rmsnorm(x, gm, 1e-6) if rms else ops.layernorm(x, gm, bt, 1e-6)
     two = ops.gemm(h, w, b, act=None if rms else "gelu")
     assert (out.float() - ref).abs().mean().item() <= 1.5 * (two.float() - ref).abs().mean().item() + 1e-4
+
+
+@pytest.mark.parametrize("M,D,rms", [(4096, 1280, False), (319, 4096, True), (2056, 1024, False)])
+def test_gemm_epilogue_row_statistics(cuda_lib, M, D, rms):
+    """gemm(stats_out=...) leaves (sum, sum of squares) partials of every output row; a following
+    gemm(row_stats=...) that finishes them must match the one that reads ops.norm_stats of the same rows."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(M + D)
+    a, w = _bf(torch.randn(M, 512, generator=g)), _bf(torch.randn(D, 512, generator=g) / 512 ** 0.5)
+    res = _bf(torch.randn(M, D, generator=g) * 2 + 0.7)
+    st = ops.gemm_stats_buffer(M, D, M, 1e-5, rms=rms)
+    st.t.fill_(float("nan"))
+    x = ops.gemm(a, w, None, residual=res, stats_out=st)
+    ref_x = (a.float() @ w.float().T) + res.float()
+    tot = st.t.sum(1)
+    assert not torch.isnan(tot).any()
+    assert torch.allclose(tot[:, 0], ref_x.sum(-1), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(tot[:, 1], ref_x.pow(2).sum(-1), rtol=1e-4, atol=2e-2)
+    # ... and the last tile of every 128-row block finished them into (mean, rstd)
+    assert st.final is not None and not torch.isnan(st.final).any()
+    mean = torch.zeros(M, device=DEV) if rms else ref_x.mean(-1)
+    rstd = torch.rsqrt(ref_x.pow(2).mean(-1) - mean * mean + 1e-5)
+    assert torch.allclose(st.final[:, 0], mean, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(st.final[:, 1], rstd, rtol=1e-4)
+    w2 = _bf(torch.randn(256, D, generator=g) / D ** 0.5)
+    gm = _bf(1 + 0.1 * torch.randn(D, generator=g))
+    wq, _ = ops.fold_norm(w2, gm, rms=rms)
+    y_final = ops.gemm(x, wq, None, row_stats=st)
+    y_parts = ops.gemm(x, wq, None, row_stats=ops.RowStats(st.t, st.parts, st.dim, st.eps, st.rms))
+    y_stats = ops.gemm(x, wq, None, row_stats=ops.norm_stats(x, 1e-5, rms=rms))
+    for y in (y_final, y_parts):
+        d = (y.float() - y_stats.float()).abs()
+        assert d.max().item() <= _ulp_tol(y_stats.float()) and d.mean().item() <= 2e-3
+    # the row-block counters re-arm themselves: a second launch gives the same statistics
+    first = st.final.clone()
+    ops.gemm(a, w, None, residual=res, stats_out=st)
+    assert torch.equal(first, st.final)
 
 
 def test_window_partition_folded_into_qkv_and_attention(cuda_lib):
