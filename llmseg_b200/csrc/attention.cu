@@ -523,7 +523,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (warp-uniform loops, elected-lane issue: see attn_kernel)
+    const bool issuer = elect_one();
+    if (issuer) {
       mbar_expect_tx(bar_q, C::Q_TX);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -539,28 +541,36 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
         tma_load_2d(smem + C::OFF_E + 8192, &tmE, bar_q, 0, 128);
       }
       if (EXT == 2) tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int key0 = j * BN;
-        uint8_t* sk = smem + C::OFF_K + st * C::K_BYTES;
-        uint8_t* sv = smem + C::OFF_V + st * C::V_BYTES;
-        mbar_wait(&k_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int key0 = j * BN;
+      uint8_t* sk = smem + C::OFF_K + st * C::K_BYTES;
+      uint8_t* sv = smem + C::OFF_V + st * C::V_BYTES;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (issuer) {
         mbar_expect_tx(&k_full[st], C::K_BYTES);
         tma_load_3d(sk, &tmKa, &k_full[st], 0, key0, bh);
         if (HD == 80) tma_load_3d(sk + C::Q0_BYTES, &tmKb, &k_full[st], 64, key0, bh);
         if (HD == 128) tma_load_3d(sk + C::Q0_BYTES, &tmKa, &k_full[st], 64, key0, bh);
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (issuer) {
         mbar_expect_tx(&v_full[st], C::V_BYTES);
         tma_load_3d(sv, &tmV, &v_full[st], key0, 0, bh);
         tma_load_3d(sv + C::V_CHUNK, &tmV, &v_full[st], key0 + 64, 0, bh);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+      const bool issuer = elect_one();
       const uint32_t sE = smem_u32(smem + C::OFF_E);
       // S_g(j) = [q_g|qext_g] . [k_j|kext]^T   into TMEM columns [128g, 128g+128)
       auto issue_s = [&](int g, int j) {
@@ -568,32 +578,32 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
         const uint32_t sq = smem_u32(smem + C::OFF_Q + g * C::QT_BYTES);
         const uint32_t sk = smem_u32(smem + C::OFF_K + (j & 1) * C::K_BYTES);
         const uint32_t tS = tmem_base + g * 128;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tS, umma_smem_desc(sq + k * 32, 1024, UMMA_SW128),
-                  umma_smem_desc(sk + k * 32, 1024, UMMA_SW128), idesc_s, k != 0);
-        if (HD == 80)
-          umma_ss(tS, umma_smem_desc(sq + C::Q0_BYTES, 256, UMMA_SW32),
-                  umma_smem_desc(sk + C::Q0_BYTES, 256, UMMA_SW32), idesc_s, 1);
-        if (HD == 128) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_smem_desc(sq + C::Q0_BYTES + k * 32, 1024, UMMA_SW128),
-                    umma_smem_desc(sk + C::Q0_BYTES + k * 32, 1024, UMMA_SW128), idesc_s, 1);
-        }
         const uint32_t sqx = sq + C::Q0_BYTES + C::Q1_BYTES;
-        if (EXT == 1) {
+        const uint64_t dQ0 = umma_smem_desc(sq, 1024, UMMA_SW128), dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
+        const uint64_t dQ1s = umma_smem_desc(sq + C::Q0_BYTES, 256, UMMA_SW32);
+        const uint64_t dK1s = umma_smem_desc(sk + C::Q0_BYTES, 256, UMMA_SW32);
+        const uint64_t dQ1 = umma_smem_desc(sq + C::Q0_BYTES, 1024, UMMA_SW128);
+        const uint64_t dK1 = umma_smem_desc(sk + C::Q0_BYTES, 1024, UMMA_SW128);
+        const uint64_t dQXw = umma_smem_desc(sqx, 512, UMMA_SW64), dEw = umma_smem_desc(sE + j * 8192, 512, UMMA_SW64);
+        const uint64_t dQXg = umma_smem_desc(sqx, 1024, UMMA_SW128), dEg = umma_smem_desc(sE, 1024, UMMA_SW128);
+        if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_ss(tS, umma_smem_desc(sqx + k * 32, 512, UMMA_SW64),
-                    umma_smem_desc(sE + j * 8192 + k * 32, 512, UMMA_SW64), idesc_s, 1);
-        }
-        if (EXT == 2) {
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
+          if (HD == 80) umma_ss(tS, dQ1s, dK1s, idesc_s, 1);
+          if (HD == 128) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tS, umma_smem_desc(sqx + k * 32, 1024, UMMA_SW128),
-                    umma_smem_desc(sE + k * 32, 1024, UMMA_SW128), idesc_s, 1);
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dQ1 + 2 * k, dK1 + 2 * k, idesc_s, 1);
+          }
+          if (EXT == 1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_ss(tS, dQXw + 2 * k, dEw + 2 * k, idesc_s, 1);
+          }
+          if (EXT == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss(tS, dQXg + 2 * k, dEg + 2 * k, idesc_s, 1);
+          }
         }
+        __syncwarp();
       };
       // O_g += P_g(j) . V_j ; P_g sits at S_g columns [0,32) (keys 0..63) and [64,96) (keys 64..127)
       auto issue_pv = [&](int g, int j) {
@@ -601,20 +611,27 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
         const uint32_t sv = smem_u32(smem + C::OFF_V + (j & 1) * C::V_BYTES);
         const uint32_t tS = tmem_base + g * 128;
         const uint32_t tO = tmem_base + 256 + g * 128;
+        const uint64_t dV0 = umma_smem_desc(sv, 1024, UMMA_SW128);
+        const uint64_t dV1 = umma_smem_desc(sv + C::V_CHUNK, 1024, UMMA_SW128);
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8,
-                  umma_smem_desc(sv + (k >> 2) * C::V_CHUNK + (k & 3) * 32, 1024, UMMA_SW128), idesc_o,
-                  (j | k) != 0);
+          for (int k = 0; k < 8; ++k)
+            umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8, (k < 4 ? dV0 : dV1) + 2 * (k & 3), idesc_o, (j | k) != 0);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (issuer) umma_commit(bar);
+        __syncwarp();
       };
       mbar_wait(bar_q, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
-      umma_commit(&bar_s[0]);
+      commit(&bar_s[0]);
       issue_s(1, 0);
-      umma_commit(&bar_s[1]);
-      umma_commit(&k_empty[0]);
+      commit(&bar_s[1]);
+      commit(&k_empty[0]);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         const uint32_t ph = j & 1;            // bar_p / bar_s complete once per tile
@@ -630,17 +647,17 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
           tc_fence_after();
           issue_s(0, j + 1);
         }
-        umma_commit(&bar_s[0]);  // S0(j+1) ready — or, after the last tile, O0 complete
+        commit(&bar_s[0]);  // S0(j+1) ready — or, after the last tile, O0 complete
         // ---- query tile 1 ----
         mbar_wait(&bar_p[1], ph);
         tc_fence_after();
         issue_pv(1, j);
-        umma_commit(&v_empty[st]);
+        commit(&v_empty[st]);
         if (more) {
           issue_s(1, j + 1);
-          umma_commit(&k_empty[st ^ 1]);
+          commit(&k_empty[st ^ 1]);
         }
-        umma_commit(&bar_s[1]);
+        commit(&bar_s[1]);
       }
     }
   } else {

@@ -57,3 +57,14 @@ for name, N, K, kw in (("o_proj", 4096, 4096, "res"), ("down", 4096, 11008, "res
             r[i] = min(r[i], t(fn, 10))
     ops.USE_GEMM_WORKSPACE = True
     print(f"{name:9s} {M_}x{N}x{K}: plain {r[0]:7.1f} us ({2*M_*N*K/r[0]/1e6:5.0f} TF/s)   stream-K tail {r[1]:7.1f} us ({2*M_*N*K/r[1]/1e6:5.0f} TF/s)", flush=True)
+# cost of the row-statistics epilogue (partials only / partials + in-kernel finish)
+for name, M_, N, K in (("proj", 32768, 1280, 1280), ("mlp2", 32768, 1280, 5120), ("o_proj", 2552, 4096, 4096), ("down", 2552, 4096, 11008)):
+    a, w, b = mk(M_, N, K)
+    res = torch.randn(M_, N, device=dev).bfloat16(); out = torch.empty_like(res)
+    st = ops.gemm_stats_buffer(M_, N, M_, 1e-6)
+    st_p = ops.RowStats(st.t, st.parts, st.dim, st.eps, st.rms)
+    r = [1e9, 1e9, 1e9]
+    for rep in range(3):
+        for i, so in enumerate((None, st_p, st)):
+            r[i] = min(r[i], t(lambda: ops.gemm(a, w, None, residual=res, out=out, stats_out=so), 10))
+    print(f"{name:7s} {M_}x{N}x{K}: no stats {r[0]:7.1f} us   partials {r[1]:7.1f} us   partials+finish {r[2]:7.1f} us", flush=True)
