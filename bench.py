@@ -193,31 +193,60 @@ def main():
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
-    # dominant-kernel timing: the same steps launched eagerly (graph nodes cannot carry timing events)
-    # with CUDA events around every SAM global-attention launch, on the launching stream.
-    attn_events = []
-    orig_attention = ops.attention
+    # dominant-kernel timing: the same steps launched eagerly (graph nodes cannot carry timing events) with
+    # CUDA events, on the launching stream, around every GEMM launch (the tcgen05 GEMM kernel is ~75 % of
+    # the step) and every SAM global-attention launch.
+    probes = []   # (group key, algorithmic flops, start event, end event)
+    orig = {n: getattr(ops, n) for n in ("attention", "gemm", "gemm_qkv")}
 
-    def attention_probe(*a, **kw):
-        if kw.get("ext_cols", 0) == 64:
+    def probed(name, key_fn):
+        fn = orig[name]
+
+        def inner(*a, **kw):
+            key = key_fn(a, kw)
+            if key is None:
+                return fn(*a, **kw)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            r = orig_attention(*a, **kw)
+            r = fn(*a, **kw)
             e.record()
-            attn_events.append((s, e))
+            probes.append((key[0], key[1], s, e))
             return r
-        return orig_attention(*a, **kw)
+        return inner
+
+    def gemm_key(a, kw):
+        M, K = a[0].shape
+        N = a[1].shape[0]
+        tag = "+".join(t for t, on in (("bias", a[2] is not None if len(a) > 2 else kw.get("bias") is not None),
+                                       (str(kw.get("act")), kw.get("act") is not None),
+                                       ("residual", kw.get("residual") is not None), ("swiglu", kw.get("swiglu", False)),
+                                       ("folded norm", kw.get("row_stats") is not None)) if on)
+        return (f"gemm {M}x{N}x{K} {tag}".strip(), 2.0 * M * N * K)
+
+    def qkv_key(a, kw):
+        M, K = a[0].shape
+        N = a[1].shape[0]
+        return (f"gemm_qkv {M}x{N}x{K}" + (" rope" if kw.get("rope_cos") is not None else ""), 2.0 * M * N * K)
+
+    def attn_key(a, kw):
+        return ("attn_global", GF_SAM_GLOBAL_ATTN * B * 1e9) if kw.get("ext_cols", 0) == 64 else None
 
     model.use_cuda_graph = False
-    ops.attention = attention_probe
+    ops.attention, ops.gemm, ops.gemm_qkv = probed("attention", attn_key), probed("gemm", gemm_key), probed("gemm_qkv", qkv_key)
     try:
         for _ in range(min(args.steps, 3)):
             model.model_forward(**inp)
         torch.cuda.synchronize()
     finally:
-        ops.attention = orig_attention
+        for n, f in orig.items():
+            setattr(ops, n, f)
         model.use_cuda_graph = True
-    attn_ms = statistics.mean(s.elapsed_time(e) for s, e in attn_events) if attn_events else None
+    groups = {}
+    for key, fl, s, e in probes:
+        g = groups.setdefault(key, [0, 0.0, 0.0])
+        g[0] += 1
+        g[1] += fl
+        g[2] += s.elapsed_time(e)
 
     if world > 1:
         dist.barrier()
@@ -228,20 +257,35 @@ def main():
     imgs = B * world * args.steps
     value = imgs / (total_ms / 1e3)
     e2e_value = imgs / (e2e_ms / 1e3)
-    roof = None
-    if attn_ms:
-        achieved = GF_SAM_GLOBAL_ATTN * B / attn_ms            # GFLOP / ms == TFLOP/s
-        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if B == 8 and os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get("attn_global_b8", {}).get("dram_bytes")
-        roof = {"kernel": "attn_kernel<80,2> (SAM global attention, 64x64 tokens, rel-pos)", "bound": "tensor",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src + " bf16_tflops_sustained",
-                "flops_per_launch": GF_SAM_GLOBAL_ATTN * B * 1e9, "avg_launch_ms": round(attn_ms, 4),
-                "launches_timed": len(attn_events)}
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    traffic_db = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic_db = json.load(f)
+
+    def roof_of(key, kernel, traffic_key):
+        n, fl, ms = groups[key]
+        achieved = fl / ms / 1e9                                # FLOP / ms / 1e9 == TFLOP/s
+        return {"kernel": kernel, "bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": traffic_db.get(traffic_key, {}).get("dram_bytes") if B == 8 else None,
+                "peak_source": peak_src + " bf16_tflops_sustained", "flops_per_launch": fl / n,
+                "avg_launch_ms": round(ms / n, 4), "launches_timed": n}
+
+    roof = roof_attn = gemm_all = None
+    gemm_groups = {k: v for k, v in groups.items() if k.startswith("gemm")}
+    if gemm_groups:
+        # dominant (kernel, shape): the GEMM group with the largest share of the step
+        top = max(gemm_groups, key=lambda k: gemm_groups[k][2])
+        roof = roof_of(top, f"gemm2_kernel (tcgen05 CTA-pair GEMM): {top}", "gemm_mlp1_b8" if "5120x1280" in top else "")
+        fl = sum(v[1] for v in gemm_groups.values())
+        ms = sum(v[2] for v in gemm_groups.values())
+        steps_probed = max(1, min(args.steps, 3))
+        gemm_all = {"achieved": round(fl / ms / 1e9, 1), "unit": "TFLOP/s", "frac": round(fl / ms / 1e9 / peak, 4),
+                    "ms_per_step": round(ms / steps_probed, 2), "launches_per_step": sum(v[0] for v in gemm_groups.values()) // steps_probed}
+    if "attn_global" in groups:
+        roof_attn = roof_of("attn_global", "attn_kernel<80,2> (SAM global attention, 64x64 tokens, rel-pos)", "attn_global_b8")
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
@@ -255,6 +299,8 @@ def main():
                 "d2h_bytes_per_step": int(world * b_max * (2 * k_max + 2) * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "roofline_all_gemms": gemm_all,
+        "roofline_attn": roof_attn,
     }
     if not args.no_cpu_baseline:
         from oracle.cpu_baseline import cpu_forward_sample

@@ -185,9 +185,20 @@ fill_kv_rows_kernel(bf16* __restrict__ k, bf16* __restrict__ vt, const bf16* __r
     if (s_pad[s]) reinterpret_cast<uint4*>(k + (bh * seq_pad + s) * hd)[v] = __ldg(bk + v);
   }
   const bf16* bv = bias + 2 * hw + h * hd;
-  for (int idx = threadIdx.x; idx < hd * seq_in; idx += blockDim.x) {
-    const int d = idx / seq_in, s = idx - d * seq_in;
-    if (s_pad[s]) vt[(bh * hd + d) * seq_pad + s] = bv[d];
+  // pairs of positions (seq_pad is even, so an even s is 4-byte aligned in every vt row): padding comes in
+  // runs along s, most pairs are one 4-byte store
+  const int half = (seq_in + 1) >> 1;
+  for (int idx = threadIdx.x; idx < hd * half; idx += blockDim.x) {
+    const int d = idx / half, s = (idx - d * half) * 2;
+    const bool p0 = s_pad[s] != 0, p1 = s + 1 < seq_in && s_pad[s + 1] != 0;
+    bf16* dst = vt + (bh * hd + d) * seq_pad + s;
+    const bf16 v = bv[d];
+    if (p0 && p1 && (seq_pad & 1) == 0) {
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __halves2bfloat162(v, v);
+    } else {
+      if (p0) dst[0] = v;
+      if (p1) dst[1] = v;
+    }
   }
 }
 
