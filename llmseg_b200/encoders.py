@@ -5,6 +5,7 @@ for the kernels (bf16, fused QKV / interleaved gate-up, conv weights flattened f
 and exposes a forward that only enqueues llmseg_* kernels.
 
   SamEncoder   reference model/segment_anything/modeling/image_encoder.py:110-125 (ViT-H/16 @1024)
+  Dinov2Encoder reference model/LISA.py:186-199,244-245 (hub dinov2_vitl14 @896 + lisa_dino_conv)
   ClipTower    reference model/llava/model/multimodal_encoder/clip_encoder.py:31-60 + mm_projector
                (llava_arch.py:93-96); arithmetic = transformers CLIPVisionTransformer
   LlamaDecoder reference model/llava/model/language_model/llava_llama.py:93-102; arithmetic =
@@ -217,6 +218,150 @@ class SamEncoder:
         y = ops.gemm(y, self.w_neck2)
         y = ops.layernorm(y, self.ln_n2[0], self.ln_n2[1], 1e-6)
         return y.view(B, S, cfg.out_chans)
+
+
+# ==============================================================================================
+# DINOv2 ViT-L/14 image encoder + lisa_dino_conv ("variant B": the branch the checked-in
+# reference model_forward takes, model/LISA.py:186-199,244-245)
+# ==============================================================================================
+def _resample_pos_embed(pos: Tensor, grid: int, offset: float) -> Tensor:
+    """Bicubic resampling of DINOv2's stored position table to a grid x grid image
+    (DinoVisionTransformer.interpolate_pos_encoding; `offset` = its interpolate_offset, 0.1 on the hub
+    default).  A one-off weight transform at load, in fp32."""
+    n = pos.shape[1] - 1
+    m = int(round(math.sqrt(n)))
+    if m * m != n:
+        raise ValueError(f"pos_embed holds {n} patch positions, not a square grid")
+    pos = pos.float()
+    if m == grid:
+        return pos[0]
+    D = pos.shape[-1]
+    tbl = pos[:, 1:].reshape(1, m, m, D).permute(0, 3, 1, 2)
+    kw = dict(scale_factor=(float(grid + offset) / m,) * 2) if offset else dict(size=(grid, grid))
+    tbl = torch.nn.functional.interpolate(tbl, mode="bicubic", align_corners=False, **kw)
+    if tbl.shape[-2:] != (grid, grid):
+        raise ValueError(f"pos_embed resampling produced {tuple(tbl.shape[-2:])}, wanted {grid}x{grid}")
+    return torch.cat([pos[0, :1], tbl.permute(0, 2, 3, 1).reshape(grid * grid, D)], dim=0)
+
+
+class Dinov2Encoder:
+    """hub `dinov2_vitl14.forward_features(...)['x_norm_patchtokens']` followed by the 1x1
+    `lisa_dino_conv`, on the same kernels as the CLIP tower (head_dim 64, no rel-pos):
+
+      * patch conv bias and cls_token are folded into the (resampled) position table, which the patch
+        GEMM adds as a per-token residual
+      * LayerScale is folded into the weights of the projection it scales (`ls*(W a + b)`)
+      * norm1/norm2 and the final norm are folded into the consuming GEMM (ops.fold_norm); the final norm
+        + the 1x1 conv are ONE GEMM whose epilogue drops the CLS row
+    """
+
+    def __init__(self, sd: Dict[str, Tensor], cfg, device, conv_w: Tensor, conv_b: Tensor, prefix: str = ""):
+        self.cfg, self.device = cfg, device
+        D, p = cfg.embed_dim, cfg.patch_size
+        self.heads, self.hd = cfg.num_heads, cfg.embed_dim // cfg.num_heads
+        if self.hd != 64:
+            raise ValueError(f"DINOv2 attention kernel is instantiated for head_dim 64 (ViT-L), got {self.hd}")
+        d = lambda k: _dev(sd[prefix + k], device)
+        f32 = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+        K = 3 * p * p
+        self.k_pad = (K + 1 + 7) // 8 * 8
+        w = torch.zeros(D, self.k_pad, dtype=BF16, device=device)
+        w[:, :K] = d("patch_embed.proj.weight").reshape(D, K)
+        self.w_patch = w          # column K (the CLS marker column of ops.patchify) stays zero
+        pos = _resample_pos_embed(f32("pos_embed"), cfg.grid, cfg.interpolate_offset)
+        pos[0] += f32("cls_token").reshape(D)
+        pos[1:] += f32("patch_embed.proj.bias")
+        self.pos = pos.to(BF16).contiguous()
+        self.layers = []
+        for i in range(cfg.depth):
+            bp = f"blocks.{i}."
+            ls1, ls2 = f32(bp + "ls1.gamma"), f32(bp + "ls2.gamma")
+            scaled = lambda name, ls: ((f32(name + ".weight") * ls[:, None]).to(BF16).contiguous(),
+                                       (f32(name + ".bias") * ls).to(BF16).contiguous())
+            L = dict(ln1=(d(bp + "norm1.weight"), d(bp + "norm1.bias")), ln2=(d(bp + "norm2.weight"), d(bp + "norm2.bias")),
+                     w_qkv=d(bp + "attn.qkv.weight"), b_qkv=d(bp + "attn.qkv.bias"),
+                     w1=d(bp + "mlp.fc1.weight"), b1=d(bp + "mlp.fc1.bias"))
+            L["w_o"], L["b_o"] = scaled(bp + "attn.proj", ls1)
+            L["w2"], L["b2"] = scaled(bp + "mlp.fc2", ls2)
+            if FOLD_NORM:
+                L["f_qkv"] = ops.fold_norm(L["w_qkv"], L["ln1"][0], L["ln1"][1], L["b_qkv"])
+                L["f_1"] = ops.fold_norm(L["w1"], L["ln2"][0], L["ln2"][1], L["b1"])
+                del L["w_qkv"], L["w1"]
+            self.layers.append(L)
+        self.norm = (d("norm.weight"), d("norm.bias"))
+        self.w_conv = _dev(conv_w, device).reshape(conv_w.shape[0], D).contiguous()
+        self.b_conv = _dev(conv_b, device)
+        if FOLD_NORM:
+            self.f_conv = ops.fold_norm(self.w_conv, self.norm[0], self.norm[1], self.b_conv)
+        self.scratch = _Scratch(device)
+        self._drop_cls: Dict[int, Tensor] = {}
+
+    def _drop_cls_map(self, B: int, as_src: bool = False) -> Tensor:
+        key = (B, as_src)
+        if key not in self._drop_cls:
+            T = self.cfg.grid ** 2 + 1
+            if as_src:   # output row -> source row (for the gathering norm kernel)
+                r = torch.arange(B * (T - 1))
+                m = (r // (T - 1)) * T + r % (T - 1) + 1
+            else:        # source row -> output row, CLS rows dropped (for the GEMM epilogue)
+                t = torch.arange(B * T)
+                n, s = t // T, t % T
+                m = torch.where(s > 0, n * (T - 1) + s - 1, torch.full_like(t, -1))
+            self._drop_cls[key] = m.to(torch.int32).to(self.device)
+        return self._drop_cls[key]
+
+    def _blocks(self, images: Tensor):
+        cfg = self.cfg
+        B = images.shape[0]
+        T, D, H, hd = cfg.grid ** 2 + 1, cfg.embed_dim, self.heads, self.hd
+        if images.shape[-1] != cfg.img_size or images.shape[-2] != cfg.img_size:
+            raise ValueError(f"DINOv2 encoder is laid out for {cfg.img_size}x{cfg.img_size} images, got {tuple(images.shape)}")
+        T_pad = (T + 7) // 8 * 8
+        a = ops.patchify(images.contiguous(), cfg.patch_size, self.k_pad, cls_rows=1)
+        stA = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "a") if FOLD_NORM else None
+        stB = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "b") if FOLD_NORM else None
+        x = ops.gemm(a, self.w_patch, None, residual=self.pos, res_mod=T, stats_out=stA)
+        del a
+        q = self.scratch.zeros("q", B * H, T_pad, hd)
+        k = self.scratch.zeros("k", B * H, T_pad, hd)
+        vt = self.scratch.zeros("vt", B * H, hd, T_pad)
+        for L in self.layers:
+            if FOLD_NORM:
+                wq, bq = L["f_qkv"]
+                ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad, row_stats=stA)
+                h = self.scratch.zeros("o", B * T, D)
+            else:
+                h = ops.layernorm(x, L["ln1"][0], L["ln1"][1], cfg.ln_eps)
+                ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
+            ops.attention(q, k, vt, h, batch=B, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
+            ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x, stats_out=stB)
+            if FOLD_NORM:
+                w1, b1 = L["f_1"]
+                m = ops.gemm(x, w1, b1, act="gelu", row_stats=stB)
+            else:
+                h = ops.layernorm(x, L["ln2"][0], L["ln2"][1], cfg.ln_eps)
+                m = ops.gemm(h, L["w1"], L["b1"], act="gelu")
+            ops.gemm(m, L["w2"], L["b2"], residual=x, out=x, stats_out=stA)
+            del m
+        return x, stA, B, T
+
+    def patch_tokens(self, images: Tensor) -> Tensor:
+        """`x_norm_patchtokens` [B, g*g, embed_dim] bf16 (what get_dinov2_visual_embs reshapes, LISA.py:192-195)."""
+        x, _, B, T = self._blocks(images)
+        y = ops.layernorm(x, self.norm[0], self.norm[1], self.cfg.ln_eps, src_row_map=self._drop_cls_map(B, True),
+                          rows_out=B * (T - 1))
+        return y.view(B, T - 1, -1)
+
+    def forward(self, images: Tensor) -> Tensor:
+        """[B,3,S,S] bf16 -> token-major `lisa_dino_conv` output [B, g*g, out_chans] bf16 (NHWC)."""
+        x, stA, B, T = self._blocks(images)
+        if FOLD_NORM:
+            w, b = self.f_conv
+            y = ops.gemm(x, w, b, row_stats=stA, out_row_map=self._drop_cls_map(B), out_rows=B * (T - 1))
+        else:
+            y = ops.layernorm(x, self.norm[0], self.norm[1], self.cfg.ln_eps)
+            y = ops.gemm(y, self.w_conv, self.b_conv, out_row_map=self._drop_cls_map(B), out_rows=B * (T - 1))
+        return y.view(B, T - 1, -1)
 
 
 # ==============================================================================================

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .encoders import BF16, ClipTower, LlamaDecoder, SamEncoder
+from .encoders import BF16, ClipTower, Dinov2Encoder, LlamaDecoder, SamEncoder
 from .selector import Selector
 
 Tensor = torch.Tensor
@@ -42,6 +42,25 @@ class SamCfg:
     window_size: int = 14
     global_attn_indexes: tuple = (7, 15, 23, 31)
     ln_eps: float = 1e-6
+
+    @property
+    def grid(self) -> int:
+        return self.img_size // self.patch_size
+
+
+@dataclass
+class DinoCfg:
+    """hub `dinov2_vitl14` evaluated on 896x896 images (64x64 patches, reference LISA.py:186-199)."""
+    img_size: int = 896
+    patch_size: int = 14
+    embed_dim: int = 1024
+    depth: int = 24
+    num_heads: int = 16
+    mlp_ratio: float = 4.0
+    train_grid: int = 37
+    ln_eps: float = 1e-6
+    out_chans: int = 256
+    interpolate_offset: float = 0.1
 
     @property
     def grid(self) -> int:
@@ -84,6 +103,11 @@ class LisaCfg:
     sam: SamCfg = field(default_factory=SamCfg)
     clip: ClipCfg = field(default_factory=ClipCfg)
     llama: LlamaCfg = field(default_factory=LlamaCfg)
+    dino: DinoCfg = field(default_factory=DinoCfg)
+    # "sam": image features from SAM ViT-H (`get_visual_embs`, LISA.py:173-184 — the encoder north_star names);
+    # "dinov2": DINOv2 ViT-L/14 + lisa_dino_conv (`get_dinov2_visual_embs`, LISA.py:186-199,244-245 — the
+    # branch the checked-in reference and its released checkpoints use)
+    image_encoder: str = "sam"
     seg_token_idx: int = DEFAULT_SEG_TOKEN_IDX
     out_dim: int = 256
 
@@ -127,7 +151,15 @@ class LISAForCausalLM:
         self.seg_token_idx = self.cfg.seg_token_idx
         self.device = torch.device(device)
         sd = strip_peft_prefix(state_dict)
-        self.sam = SamEncoder(_sub(sd, "model.visual_model.image_encoder."), self.cfg.sam, self.device)
+        if self.cfg.image_encoder == "sam":
+            self.sam = SamEncoder(_sub(sd, "model.visual_model.image_encoder."), self.cfg.sam, self.device)
+            self.image_encoder, self.image_size = self.sam, self.cfg.sam.img_size
+        elif self.cfg.image_encoder == "dinov2":
+            self.dino = Dinov2Encoder(_sub(sd, "model.visual_model_dinov2."), self.cfg.dino, self.device,
+                                      sd["model.lisa_dino_conv.weight"], sd["model.lisa_dino_conv.bias"])
+            self.image_encoder, self.image_size = self.dino, self.cfg.dino.img_size
+        else:
+            raise ValueError(f"image_encoder must be 'sam' or 'dinov2', got {self.cfg.image_encoder!r}")
         self.clip = ClipTower(_sub(sd, "model.vision_tower.vision_tower."), self.cfg.clip, self.device,
                               sd["model.mm_projector.weight"], sd["model.mm_projector.bias"])
         self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq)
@@ -146,8 +178,19 @@ class LISAForCausalLM:
 
     def get_visual_embs(self, pixel_values: Tensor) -> Tensor:
         """SAM ViT-H features, returned NCHW [B,256,64,64] like reference LISA.py:173-184."""
+        if self.cfg.image_encoder != "sam":
+            raise RuntimeError("this model was built with image_encoder='dinov2'; use get_dinov2_visual_embs")
         tok = self.sam.forward(pixel_values.to(self.device, BF16))
         g = self.cfg.sam.grid
+        return tok.view(tok.shape[0], g, g, -1).permute(0, 3, 1, 2)
+
+    def get_dinov2_visual_embs(self, pixel_values: Tensor) -> Tensor:
+        """DINOv2 `x_norm_patchtokens`, returned NCHW [B,1024,64,64] like reference LISA.py:186-199
+        (before `lisa_dino_conv`; the forward itself runs norm + conv as one GEMM)."""
+        if self.cfg.image_encoder != "dinov2":
+            raise RuntimeError("this model was built with image_encoder='sam'; use get_visual_embs")
+        tok = self.dino.patch_tokens(pixel_values.to(self.device, BF16))
+        g = self.cfg.dino.grid
         return tok.view(tok.shape[0], g, g, -1).permute(0, 3, 1, 2)
 
     @torch.no_grad()
@@ -206,7 +249,7 @@ class LISAForCausalLM:
     def _make_plan(self, key) -> dict:
         B, N, Tt, Ks, off, n_clip, no_mask = key
         dev, cfg = self.device, self.cfg
-        S, Sc = cfg.sam.img_size, cfg.clip.image_size
+        S, Sc = self.image_size, cfg.clip.image_size
         static = {
             "images": torch.empty((B, 3, S, S), dtype=BF16, device=dev),
             "images_clip": torch.empty((n_clip, 3, Sc, Sc), dtype=BF16, device=dev),
@@ -230,8 +273,8 @@ class LISAForCausalLM:
         no host->device copies; every index tensor comes from the plan)."""
         st = plan["static"]
         B, N, Tt = plan["key"][0], plan["key"][1], plan["key"][2]
-        # 1. SAM image encoder -> token-major embeddings [B,4096,256]
-        emb_tokens = self.sam.forward(st["images"])
+        # 1. image encoder (SAM ViT-H, or DINOv2 + lisa_dino_conv) -> token-major embeddings [B,4096,256]
+        emb_tokens = self.image_encoder.forward(st["images"])
         # 2. CLIP tower + projector (once per distinct image; the reference recomputes per conversation)
         feats = self.clip.forward(st["images_clip"])
         if plan["conv_index"] is not None:

@@ -11,7 +11,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .lisa import IMAGE_TOKEN_INDEX, ClipCfg, LisaCfg, LlamaCfg, SamCfg
+from .lisa import IMAGE_TOKEN_INDEX, ClipCfg, DinoCfg, LisaCfg, LlamaCfg, SamCfg
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
@@ -52,6 +52,33 @@ def sam_state_dict(cfg: SamCfg, seed: int, device, prefix: str = "model.visual_m
             b + "attn.rel_pos_h": G.rn(2 * S - 1, hd, std=0.1), b + "attn.rel_pos_w": G.rn(2 * S - 1, hd, std=0.1),
             b + "mlp.lin1.weight": G.rn(mlp, D, std=D ** -0.5), b + "mlp.lin1.bias": G.rn(mlp),
             b + "mlp.lin2.weight": G.rn(D, mlp, std=0.5 * mlp ** -0.5), b + "mlp.lin2.bias": G.rn(D),
+        })
+    return sd
+
+
+def dinov2_state_dict(cfg: DinoCfg, seed: int, device, prefix: str = "model.visual_model_dinov2.") -> Dict[str, Tensor]:
+    """hub `dinov2_vitl14` parameter names; LayerScale gammas O(1) (trained checkpoints are far from the 1e-5 init)."""
+    G = _Gen(seed, device)
+    D, p = cfg.embed_dim, cfg.patch_size
+    mlp = int(D * cfg.mlp_ratio)
+    sd = {
+        prefix + "cls_token": G.rn(1, 1, D, std=0.5),
+        prefix + "pos_embed": G.rn(1, 1 + cfg.train_grid ** 2, D, std=0.3),
+        prefix + "mask_token": G.rn(1, D),
+        prefix + "patch_embed.proj.weight": G.rn(D, 3, p, p, std=(3 * p * p) ** -0.5),
+        prefix + "patch_embed.proj.bias": G.rn(D, std=0.1),
+        prefix + "norm.weight": G.rn(D, std=0.1, mean=1.0), prefix + "norm.bias": G.rn(D, std=0.1),
+    }
+    for i in range(cfg.depth):
+        b = f"{prefix}blocks.{i}."
+        sd.update({
+            b + "norm1.weight": G.rn(D, std=0.1, mean=1.0), b + "norm1.bias": G.rn(D, std=0.1),
+            b + "norm2.weight": G.rn(D, std=0.1, mean=1.0), b + "norm2.bias": G.rn(D, std=0.1),
+            b + "attn.qkv.weight": G.rn(3 * D, D, std=D ** -0.5), b + "attn.qkv.bias": G.rn(3 * D, std=0.1),
+            b + "attn.proj.weight": G.rn(D, D, std=D ** -0.5), b + "attn.proj.bias": G.rn(D),
+            b + "ls1.gamma": G.rn(D, std=0.1, mean=0.5), b + "ls2.gamma": G.rn(D, std=0.1, mean=0.5),
+            b + "mlp.fc1.weight": G.rn(mlp, D, std=D ** -0.5), b + "mlp.fc1.bias": G.rn(mlp),
+            b + "mlp.fc2.weight": G.rn(D, mlp, std=mlp ** -0.5), b + "mlp.fc2.bias": G.rn(D),
         })
     return sd
 
@@ -134,7 +161,13 @@ def selector_state_dict(hidden: int, seed: int, device, prefix: str = "model.") 
 def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda") -> Dict[str, Tensor]:
     """Full random-init state dict with the reference's key names, bf16 on `device`."""
     sd: Dict[str, Tensor] = {}
-    sd.update(sam_state_dict(cfg.sam, seed + 1, device))
+    if cfg.image_encoder == "dinov2":
+        sd.update(dinov2_state_dict(cfg.dino, seed + 1, device))
+        G = _Gen(seed + 6, device)
+        sd["model.lisa_dino_conv.weight"] = G.rn(cfg.dino.out_chans, cfg.dino.embed_dim, 1, 1, std=cfg.dino.embed_dim ** -0.5)
+        sd["model.lisa_dino_conv.bias"] = G.rn(cfg.dino.out_chans, std=0.1)
+    else:
+        sd.update(sam_state_dict(cfg.sam, seed + 1, device))
     sd.update(clip_state_dict(cfg.clip, seed + 2, device))
     sd.update(llama_state_dict(cfg.llama, seed + 3, device))
     sd.update(selector_state_dict(cfg.llama.hidden, seed + 4, device))
@@ -166,7 +199,8 @@ def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int =
     assert t_text >= 8
     dev = torch.device(device)
     g = torch.Generator(device=dev).manual_seed(seed)
-    S, Sc = cfg.sam.img_size, cfg.clip.image_size
+    S = cfg.dino.img_size if cfg.image_encoder == "dinov2" else cfg.sam.img_size
+    Sc = cfg.clip.image_size
     images = torch.randn(batch, 3, S, S, generator=g, device=dev).to(BF16)
     images_clip = torch.randn(batch, 3, Sc, Sc, generator=g, device=dev).to(BF16)
     ids = torch.randint(3, 31999, (batch, t_text), generator=g, device=dev, dtype=torch.int64)

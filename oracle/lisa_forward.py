@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn.functional as F
 
-from . import clip_llama, sam_encoder, selector
+from . import clip_llama, dinov2, sam_encoder, selector
 
 Tensor = torch.Tensor
 
@@ -38,6 +38,8 @@ class LisaConfig:
     sam: sam_encoder.SamConfig = field(default_factory=sam_encoder.SamConfig)
     clip: clip_llama.ClipConfig = field(default_factory=clip_llama.ClipConfig)
     llama: clip_llama.LlamaConfig = field(default_factory=clip_llama.LlamaConfig)
+    dino: dinov2.Dinov2Config = field(default_factory=dinov2.Dinov2Config)
+    image_encoder: str = "sam"   # "sam" = variant A (LISA.py:173-184); "dinov2" = variant B (LISA.py:186-199,244-245)
     seg_token_idx: int = SEG_TOKEN_IDX
     out_dim: int = 256
 
@@ -83,12 +85,21 @@ def seg_token_mask(input_ids: Tensor, cfg: LisaConfig) -> Tensor:
     return torch.cat([torch.zeros((m.shape[0], cfg.n_image_tokens - 1), dtype=torch.bool, device=m.device), m], dim=1)
 
 
+def image_features(sd: Dict[str, Tensor], cfg: LisaConfig, images: Tensor) -> Tensor:
+    """[B,3,S,S] -> [B,256,64,64]: variant A `get_visual_embs` (LISA.py:173-184, commented out at :242) or
+    variant B `lisa_dino_conv(get_dinov2_visual_embs(images))` (LISA.py:244-245, the checked-in branch)."""
+    if cfg.image_encoder == "dinov2":
+        return dinov2.image_embeddings(images, sub_dict(sd, "model.visual_model_dinov2."),
+                                       sd["model.lisa_dino_conv.weight"], sd["model.lisa_dino_conv.bias"], cfg.dino)
+    return sam_encoder.image_encoder(images, sub_dict(sd, "model.visual_model.image_encoder."), cfg.sam)
+
+
 def model_forward_inference(sd: Dict[str, Tensor], cfg: LisaConfig, *, images: Tensor, images_clip: Tensor,
                             input_ids: Tensor, attention_masks: Tensor, offset: Tensor,
                             sam_segs_list: List[Tensor], masks_list: Optional[list] = None) -> dict:
     """One reference inference call (batch of ONE image, LISA.py:271).  Returns the reference's dict."""
     assert images_clip.shape[0] == 1, "reference inference is one image per forward (LISA.py:271)"
-    image_embeddings = sam_encoder.image_encoder(images, sub_dict(sd, "model.visual_model.image_encoder."), cfg.sam)
+    image_embeddings = image_features(sd, cfg, images)
     assert image_embeddings.shape[0] == len(offset) - 1
     seg_mask = seg_token_mask(input_ids, cfg)
 

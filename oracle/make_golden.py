@@ -20,7 +20,7 @@ REF = Path("/root/reference")
 GOLD = ROOT / "tests" / "golden"
 
 sys.path.insert(0, str(ROOT))
-from oracle import clip_llama, lisa_forward, sam_encoder, selector  # noqa: E402
+from oracle import clip_llama, dinov2, lisa_forward, sam_encoder, selector  # noqa: E402
 
 
 def checksum(sd) -> float:
@@ -210,6 +210,39 @@ def gold_llama():
     torch.save({"cfg": cfg.__dict__, "sd": sd, "embeds": emb, "mask": mask, "out": ref}, GOLD / "llama_tiny.pt")
 
 
+def gold_dinov2():
+    """Variant-B image encoder (hub DINOv2, absent offline) pinned against transformers' Dinov2Model."""
+    from transformers import Dinov2Config as HFConfig, Dinov2Model
+    # stored table 5x5 (image 70), evaluated on a 9x9 grid (image 126): the position table IS resampled
+    cfg = dinov2.Dinov2Config(img_size=126, patch_size=14, embed_dim=64, depth=3, num_heads=4, train_grid=5,
+                              out_chans=16, interpolate_offset=0.0)
+    hf = Dinov2Model(HFConfig(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, mlp_ratio=4,
+                              image_size=70, patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu",
+                              layerscale_value=1.0, attn_implementation="eager")).eval()
+    sd = dinov2.random_state_dict(cfg, seed=51)
+    full = dinov2.to_hf_names(sd, cfg)
+    hf_sd = hf.state_dict()
+    missing = [k for k in hf_sd if k not in full]
+    assert not missing, missing
+    hf.load_state_dict(full, strict=True)
+    g = torch.Generator().manual_seed(52)
+    x = torch.randn(2, 3, 126, 126, generator=g)
+    conv_w, conv_b = torch.randn(16, 64, 1, 1, generator=g) * 0.125, torch.randn(16, generator=g) * 0.1
+    with torch.no_grad():
+        ref = hf(x).last_hidden_state[:, 1:]                  # == x_norm_patchtokens
+        mine = dinov2.forward_features(x, sd, cfg)
+        emb = dinov2.image_embeddings(x, sd, conv_w, conv_b, cfg)
+    err = (ref - mine).abs().max().item()
+    print(f"[dinov2 tiny] oracle vs transformers eager x_norm_patchtokens max|d| = {err:.3e}")
+    assert err < 1e-4
+    # the hub default (offset 0.1) gives a slightly different table: record both so the test pins the switch
+    pos01 = dinov2.interpolate_pos_embed(sd["pos_embed"], cfg.grid, 0.1)
+    pos00 = dinov2.interpolate_pos_embed(sd["pos_embed"], cfg.grid, 0.0)
+    assert pos01.shape == pos00.shape and (pos01 - pos00).abs().max() > 0
+    torch.save({"cfg": cfg.__dict__, "sd": sd, "x": x, "tokens": ref, "conv_w": conv_w, "conv_b": conv_b,
+                "embeddings": emb, "pos_offset01": pos01}, GOLD / "dinov2_tiny.pt")
+
+
 def gold_splice():
     """Index arithmetic of SURVEY §A.6 on a worked example (no reference module is importable for it)."""
     cfg = lisa_forward.LisaConfig()
@@ -239,6 +272,7 @@ def main():
     gold_losses(ref_loss)
     gold_clip()
     gold_llama()
+    gold_dinov2()
     gold_splice()
     print("golden fixtures written to", GOLD)
 

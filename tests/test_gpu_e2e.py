@@ -14,20 +14,28 @@ DEV = "cuda"
 SIM_TOL = 4e-3
 
 
-def _setup(depths, B, K, T_text, seed=0):
+def _setup(depths, B, K, T_text, seed=0, image_encoder="sam"):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     from llmseg_b200 import lisa, synthetic
     from oracle import clip_llama as o_cl, lisa_forward as o_lf, sam_encoder as o_sam
     cfg = lisa.LisaCfg()
     sam_d, sam_g, clip_l, llama_l = depths
-    cfg.sam.depth, cfg.sam.global_attn_indexes = sam_d, sam_g
+    cfg.image_encoder = image_encoder
+    if image_encoder == "dinov2":
+        cfg.dino.depth = sam_d
+    else:
+        cfg.sam.depth, cfg.sam.global_attn_indexes = sam_d, sam_g
     cfg.clip.layers, cfg.llama.layers = clip_l, llama_l
     sd = synthetic.lisa_state_dict(cfg, seed=seed, device=DEV)
     model = lisa.LISAForCausalLM(sd, cfg, device=DEV)
     inp = synthetic.make_inputs(cfg, B, K, T_text, device=DEV)
-    ocfg = o_lf.LisaConfig(sam=o_sam.SamConfig(depth=sam_d, global_attn_indexes=sam_g),
-                           clip=o_cl.ClipConfig(layers=clip_l), llama=o_cl.LlamaConfig(layers=llama_l))
+    ocfg = o_lf.LisaConfig(clip=o_cl.ClipConfig(layers=clip_l), llama=o_cl.LlamaConfig(layers=llama_l),
+                           image_encoder=image_encoder)
+    if image_encoder == "dinov2":
+        ocfg.dino.depth = sam_d
+    else:
+        ocfg.sam = o_sam.SamConfig(depth=sam_d, global_attn_indexes=sam_g)
     return model, sd, inp, ocfg
 
 
@@ -64,6 +72,37 @@ def test_sam_encoder_vs_oracle(cuda_lib):
     assert nchw.shape == ref.shape == (1, 256, 64, 64)
     d = tok.float().reshape(1, 64, 64, 256).permute(0, 3, 1, 2) - ref
     assert d.abs().max().item() < 0.15 and d.abs().mean().item() < 1.5e-2   # LayerNorm2d output, rms ~1
+
+
+def test_dinov2_encoder_vs_oracle(cuda_lib):
+    """Variant B image features (reference LISA.py:186-199,244-245): DINOv2 ViT-L/14 @896 (4097 tokens,
+    head_dim 64, LayerScale, resampled position table) + lisa_dino_conv, full width, 3 blocks."""
+    from oracle import dinov2 as o_dino, lisa_forward as o_lf
+    model, sd, inp, ocfg = _setup((3, None, 2, 1), 2, 8, 16, image_encoder="dinov2")
+    assert inp["images"].shape[-1] == 896
+    with torch.no_grad():
+        tok = model.dino.forward(inp["images"])
+        pre = model.get_dinov2_visual_embs(inp["images"])
+        fsd = {k: v.float() for k, v in sd.items()}
+        ref = o_lf.image_features(fsd, ocfg, inp["images"].float())
+        ref_pre = o_dino.forward_features(inp["images"].float(), o_lf.sub_dict(fsd, "model.visual_model_dinov2."), ocfg.dino)
+    assert ref.shape == (2, 256, 64, 64) and pre.shape == (2, 1024, 64, 64)
+    d = tok.float().reshape(2, 64, 64, 256).permute(0, 3, 1, 2) - ref
+    dp = pre.float() - ref_pre.permute(0, 2, 1).reshape(2, 1024, 64, 64)
+    print(f"dinov2+conv max|d|={d.abs().max().item():.4f} mean|d|={d.abs().mean().item():.5f} ref_rms={ref.pow(2).mean().sqrt().item():.3f}; "
+          f"patch tokens max|d|={dp.abs().max().item():.4f} mean|d|={dp.abs().mean().item():.5f}")
+    assert d.abs().max().item() < 0.15 and d.abs().mean().item() < 1.5e-2
+    assert dp.abs().max().item() < 0.2 and dp.abs().mean().item() < 1.5e-2
+
+
+def test_forward_dinov2_variant(cuda_lib):
+    """The checked-in reference branch end to end: DINOv2 features -> selector, batch 2, K=48."""
+    model, sd, inp, ocfg = _setup((2, None, 2, 2), 2, 48, 32, image_encoder="dinov2")
+    with torch.no_grad():
+        out = model.forward(**inp)
+    _check(out, _oracle(sd, ocfg, inp), 2)
+    with pytest.raises(RuntimeError):
+        model.get_visual_embs(inp["images"])
 
 
 def test_forward_reduced_depth_batched(cuda_lib):

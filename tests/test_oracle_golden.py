@@ -2,7 +2,7 @@
 modules (oracle/make_golden.py).  This is what pins the oracle (the reference has no tests)."""
 import torch
 
-from oracle import clip_llama, lisa_forward, sam_encoder, selector
+from oracle import clip_llama, dinov2, lisa_forward, sam_encoder, selector
 
 
 def _load(golden_dir, name):
@@ -127,3 +127,32 @@ def test_end_to_end_tiny_oracle_runs():
     out2 = lisa_forward.forward_batched(sd, cfg, images=inp["images"], images_clip=inp["images_clip"], input_ids=ids,
                                         attention_masks=inp["attention_masks"], sam_segs_list=inp["sam_segs_list"])
     assert torch.equal(out2["pred_similarity"][0], out["pred_similarity"][0])
+
+
+def test_dinov2_tiny(golden_dir):
+    """Variant-B image encoder: hub-named weights, position table resampled 5x5 -> 9x9; golden tokens come from
+    transformers' Dinov2Model, golden embeddings add the reference's reshape + 1x1 lisa_dino_conv."""
+    fx = _load(golden_dir, "dinov2_tiny.pt")
+    cfg = dinov2.Dinov2Config(**fx["cfg"])
+    tok = dinov2.forward_features(fx["x"], fx["sd"], cfg)
+    assert tok.shape == (2, 81, 64) and torch.allclose(tok, fx["tokens"], atol=1e-5)
+    emb = dinov2.image_embeddings(fx["x"], fx["sd"], fx["conv_w"], fx["conv_b"], cfg)
+    assert emb.shape == (2, 16, 9, 9) and torch.allclose(emb, fx["embeddings"], atol=1e-5)
+    # hub default resampling (interpolate_offset=0.1) is a different table from the size= one
+    pos = dinov2.interpolate_pos_embed(fx["sd"]["pos_embed"], cfg.grid, 0.1)
+    assert torch.allclose(pos, fx["pos_offset01"], atol=1e-6)
+    assert (pos - dinov2.interpolate_pos_embed(fx["sd"]["pos_embed"], cfg.grid, 0.0)).abs().max() > 1e-4
+    # a table already stored at the evaluation grid is used as is
+    same = dinov2.interpolate_pos_embed(fx["sd"]["pos_embed"], cfg.train_grid, 0.1)
+    assert same is fx["sd"]["pos_embed"]
+
+
+def test_host_pos_embed_resampling_matches_oracle(golden_dir):
+    """The product's load-time resampling (llmseg_b200.encoders) against the oracle's, both offsets."""
+    from llmseg_b200.encoders import _resample_pos_embed
+    fx = _load(golden_dir, "dinov2_tiny.pt")
+    pe = fx["sd"]["pos_embed"]
+    for off in (0.1, 0.0):
+        mine = _resample_pos_embed(pe, 9, off)
+        assert torch.allclose(mine, dinov2.interpolate_pos_embed(pe, 9, off)[0], atol=1e-6)
+    assert torch.equal(_resample_pos_embed(pe, 5, 0.1), pe[0])
