@@ -256,6 +256,22 @@ int llmseg_select(const void* feat, const void* text, const void* h_iou, const v
                   float* iou_out, int32_t* best, void* stream);
 int llmseg_align_iou_loss(const float* sim, const float* pred_iou, const float* gt_iou, int K,
                           float temperature, float* out2, void* stream);
+ /* Training forward (LISA.py:416-474): per (image, round) group g, proposals k_off[g]..k_off[g+1] of rows with
+ * stride k_stride: align_g = softmax_align_loss(sim_g, gt_iou_g), regression_g = iou_regression_loss(pred_iou_g,
+ * gt_iop_g) (loss.py:50-94) -> per_group fp32 [n_groups,2]; then out4 = {loss, ce, align, regression} =
+ * {sum, w_ce*ce2[0], w_align*Σ_g weight_g*align_g, w_reg*Σ_g weight_g*regression_g} (ce2 may be NULL). */
+int llmseg_selector_losses(const float* sim, const float* pred_iou, const float* gt_iou,
+                           const float* gt_iop, const int32_t* k_off, int n_groups, int k_stride,
+                           float temperature, const float* group_weight, const float* ce2, float w_ce,
+                           float w_align, float w_reg, float* per_group, float* out4, void* stream);
+/* LM cross entropy of the training forward (llava_llama.py:107-118): logits bf16 [n_seq*T, ld] (T = t_text +
+ * n_img_tokens - 1, first `vocab` columns valid), row (n,t) scored against the label of spliced position t+1,
+ * where the spliced labels are labels[n] with the IMAGE token replaced by n_img_tokens IGNORE entries
+ * (llava_arch.py:185-245) — computed by index arithmetic from input_ids/labels int64 [n_seq,t_text].
+ * row_loss fp32 [n_seq*T] (scratch: CE, -1 = no target); out2 = {mean over targets, number of targets}. */
+int llmseg_lm_cross_entropy(const void* logits, int ld, const int64_t* input_ids, const int64_t* labels,
+                            int n_seq, int t_text, int n_img_tokens, int vocab, int64_t image_token_id,
+                            int64_t ignore_index, float* row_loss, float* out2, void* stream);
 int llmseg_dice_bce_loss(const float* logits, const float* targets, int n_masks, int hw,
                          float num_masks, float* workspace, float* out2, void* stream);
 

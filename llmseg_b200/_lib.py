@@ -86,6 +86,10 @@ def _declare(lib):
                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.llmseg_align_iou_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                           c_void_p]
+    lib.llmseg_selector_losses.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                           c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]
+    lib.llmseg_lm_cross_entropy.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                            C.c_int64, C.c_int64, c_void_p, c_void_p, c_void_p]
     lib.llmseg_dice_bce_loss.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
                                          c_void_p, c_void_p]
 
@@ -96,7 +100,7 @@ SYMBOLS = [
     "llmseg_gemm", "llmseg_gemm_workspace_bytes", "llmseg_gemm_stats_parts", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm", "llmseg_norm_stats",
     "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
-    "llmseg_align_iou_loss", "llmseg_dice_bce_loss",
+    "llmseg_align_iou_loss", "llmseg_dice_bce_loss", "llmseg_selector_losses", "llmseg_lm_cross_entropy",
 ]
 
 

@@ -292,12 +292,12 @@ __device__ float block_max(float v, float* sh) {
   return t;
 }
 
-// out[0] = KL(softmax(gt/τ) ‖ softmax(sim/τ)) (sum), out[1] = mean((p-g)²·e^{g-1})·50   (loss.py:50-94)
-__global__ void __launch_bounds__(256)
-align_iou_loss_kernel(const float* __restrict__ sim, const float* __restrict__ pred_iou,
-                      const float* __restrict__ gt_iou, int K, float temperature, float* __restrict__ out) {
-  __shared__ float sh[8];
-  const float it = 1.f / temperature;
+// kl = KL(softmax(gt_iou/τ) ‖ softmax(sim/τ)) (sum over the K proposals), mse = mean((p-g)²·e^{g-1})·50 with
+// g = gt_iop   (loss.py:50-94; the training forward feeds IoU to the first and IoP to the second,
+// LISA.py:452-453).  Whole block cooperates; results valid in every thread.
+__device__ void align_iou_pair(const float* __restrict__ sim, const float* __restrict__ pred_iou,
+                               const float* __restrict__ gt_iou, const float* __restrict__ gt_iop, int K,
+                               float it, float* sh, float& kl_out, float& mse_out) {
   float ms = -INFINITY, mg = -INFINITY;
   for (int i = threadIdx.x; i < K; i += blockDim.x) {
     ms = fmaxf(ms, sim[i] * it);
@@ -318,14 +318,153 @@ align_iou_loss_kernel(const float* __restrict__ sim, const float* __restrict__ p
     const float lp_s = sim[i] * it - ls, lp_g = gt_iou[i] * it - lg;
     const float pg = __expf(lp_g);
     kl += pg > 0.f ? pg * (lp_g - lp_s) : 0.f;
-    const float d = pred_iou[i] - gt_iou[i];
-    mse += d * d * __expf(gt_iou[i] - 1.f);
+    const float d = pred_iou[i] - gt_iop[i];
+    mse += d * d * __expf(gt_iop[i] - 1.f);
   }
-  kl = block_sum(kl, sh);
-  mse = block_sum(mse, sh);
+  kl_out = block_sum(kl, sh);
+  mse_out = block_sum(mse, sh) / (float)K * 50.f;
+}
+
+__global__ void __launch_bounds__(256)
+align_iou_loss_kernel(const float* __restrict__ sim, const float* __restrict__ pred_iou,
+                      const float* __restrict__ gt_iou, int K, float temperature, float* __restrict__ out) {
+  __shared__ float sh[8];
+  float kl, mse;
+  align_iou_pair(sim, pred_iou, gt_iou, gt_iou, K, 1.f / temperature, sh, kl, mse);
   if (threadIdx.x == 0) {
     out[0] = kl;
-    out[1] = mse / (float)K * 50.f;
+    out[1] = mse;
+  }
+}
+
+// Training forward, LISA.py:416-474: one block per (image, round) group g; rows of stride k_stride, K_g =
+// k_off[g+1]-k_off[g] valid proposals.  per_group[g] = {align_g, regression_g}.
+__global__ void __launch_bounds__(256)
+selector_losses_kernel(const float* __restrict__ sim, const float* __restrict__ pred_iou,
+                       const float* __restrict__ gt_iou, const float* __restrict__ gt_iop,
+                       const int32_t* __restrict__ k_off, int k_stride, float temperature,
+                       float* __restrict__ per_group) {
+  __shared__ float sh[8];
+  const int g = blockIdx.x;
+  const int K = k_off[g + 1] - k_off[g];
+  const size_t o = (size_t)g * k_stride;
+  float kl = 0.f, mse = 0.f;
+  if (K > 0) align_iou_pair(sim + o, pred_iou + o, gt_iou + o, gt_iop + o, K, 1.f / temperature, sh, kl, mse);
+  if (threadIdx.x == 0) {
+    per_group[2 * g + 0] = kl;
+    per_group[2 * g + 1] = mse;
+  }
+}
+// out4 = {loss, ce_loss, align_loss, regression_loss}: group_weight[g] = 1 / ((rounds of g's image + 1e-8) *
+// images with >= 1 round) reproduces the per-image mean over rounds and the mean over images (LISA.py:455-462);
+// fixed summation order.
+__global__ void selector_losses_final_kernel(const float* __restrict__ per_group, const float* __restrict__ group_weight,
+                                             int n_groups, const float* __restrict__ ce2, float w_ce, float w_align,
+                                             float w_reg, float* __restrict__ out4) {
+  float a = 0.f, r = 0.f;
+  for (int g = 0; g < n_groups; ++g) {
+    a += per_group[2 * g + 0] * group_weight[g];
+    r += per_group[2 * g + 1] * group_weight[g];
+  }
+  const float ce = (ce2 ? ce2[0] : 0.f) * w_ce;
+  a *= w_align;
+  r *= w_reg;
+  out4[0] = ce + a + r;
+  out4[1] = ce;
+  out4[2] = a;
+  out4[3] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Language-model cross entropy of the training forward: llava_llama.py:107-118 (shift by one, mean over the
+// targets != ignore_index) on the labels of prepare_inputs_labels_for_multimodal (llava_arch.py:185-245:
+// IGNORE over the image rows), with the label splice done by index arithmetic instead of a copy.
+// grid (T, n_seq): block (t, n) scores logits row n*T+t against the label of spliced position t+1.
+// row_loss: CE >= 0, -1 = no target at this row, NaN = target outside [0, vocab).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lm_ce_rows_kernel(const bf16* __restrict__ logits, int ld, const long long* __restrict__ input_ids,
+                  const long long* __restrict__ labels, int t_text, int n_img, int vocab, long long image_token,
+                  long long ignore_index, float* __restrict__ row_loss) {
+  __shared__ int s_img;
+  __shared__ float sh[8];
+  const int T = t_text + n_img - 1;
+  const int t = blockIdx.x, n = blockIdx.y;
+  const int pos = t + 1;
+  const long long* ids = input_ids + (size_t)n * t_text;
+  if (threadIdx.x == 0) s_img = t_text;
+  __syncthreads();
+  for (int j = threadIdx.x; j < t_text; j += blockDim.x)
+    if (ids[j] == image_token) atomicMin(&s_img, j);
+  __syncthreads();
+  const int i_img = s_img;
+  long long lab = ignore_index;
+  if (pos < T && i_img < t_text) {
+    if (pos < i_img) lab = labels[(size_t)n * t_text + pos];
+    else if (pos >= i_img + n_img) lab = labels[(size_t)n * t_text + pos - n_img + 1];
+  }
+  const size_t row = (size_t)n * T + t;
+  if (lab == ignore_index) {
+    if (threadIdx.x == 0) row_loss[row] = -1.f;
+    return;
+  }
+  if (lab < 0 || lab >= vocab) {
+    if (threadIdx.x == 0) row_loss[row] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const bf16* x = logits + row * (size_t)ld;
+  // online (max, sum exp) per thread over 16-byte vectors; ld % 8 == 0 keeps every row 16-byte aligned
+  float m = -INFINITY, z = 0.f;
+  const int nvec = vocab >> 3;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + v);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = __bfloat1622float2(h[j]);
+      f[2 * j] = p.x;
+      f[2 * j + 1] = p.y;
+    }
+    float vm = f[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) vm = fmaxf(vm, f[j]);
+    if (vm > m) {
+      z *= __expf(m - vm);
+      m = vm;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z += __expf(f[j] - m);
+  }
+  for (int c = (nvec << 3) + threadIdx.x; c < vocab; c += blockDim.x) {
+    const float f = __bfloat162float(x[c]);
+    if (f > m) {
+      z *= __expf(m - f);
+      m = f;
+    }
+    z += __expf(f - m);
+  }
+  const float bm = block_max(m, sh);
+  z = block_sum(z * __expf(m - bm), sh);
+  if (threadIdx.x == 0) row_loss[row] = bm + __logf(z) - __bfloat162float(x[lab]);
+}
+// out2 = {mean CE over the rows that have a target, number of such rows}; fixed summation order.
+__global__ void __launch_bounds__(256) lm_ce_final_kernel(const float* __restrict__ row_loss, int rows,
+                                                          float* __restrict__ out2) {
+  __shared__ float sh[8];
+  float s = 0.f, c = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float v = row_loss[r];
+    if (!(v < 0.f)) {  // NaN (bad target) propagates on purpose
+      s += v;
+      c += 1.f;
+    }
+  }
+  s = block_sum(s, sh);
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0) {
+    out2[0] = s / c;
+    out2[1] = c;
   }
 }
 
@@ -435,6 +574,48 @@ extern "C" int llmseg_align_iou_loss(const float* sim, const float* pred_iou, co
                                                                           temperature, out2);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int llmseg_selector_losses(const float* sim, const float* pred_iou, const float* gt_iou,
+                                      const float* gt_iop, const int32_t* k_off, int n_groups, int k_stride,
+                                      float temperature, const float* group_weight, const float* ce2, float w_ce,
+                                      float w_align, float w_reg, float* per_group, float* out4, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(sim && pred_iou && gt_iou && gt_iop && k_off && group_weight && per_group && out4, LLMSEG_EARG,
+                 "llmseg_selector_losses: null pointer");
+  LLMSEG_REQUIRE(n_groups > 0 && k_stride > 0 && temperature > 0.f, LLMSEG_ESHAPE,
+                 "llmseg_selector_losses: groups=%d k_stride=%d temperature=%f", n_groups, k_stride, temperature);
+  selector_losses_kernel<<<n_groups, 256, 0, stream>>>(sim, pred_iou, gt_iou, gt_iop, k_off, k_stride, temperature,
+                                                       per_group);
+  LLMSEG_CUDA(cudaGetLastError());
+  selector_losses_final_kernel<<<1, 1, 0, stream>>>(per_group, group_weight, n_groups, ce2, w_ce, w_align, w_reg,
+                                                    out4);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return 0;
+}
+
+extern "C" int llmseg_lm_cross_entropy(const void* logits, int ld, const int64_t* input_ids, const int64_t* labels,
+                                       int n_seq, int t_text, int n_img_tokens, int vocab, int64_t image_token_id,
+                                       int64_t ignore_index, float* row_loss, float* out2, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(logits && input_ids && labels && row_loss && out2, LLMSEG_EARG, "llmseg_lm_cross_entropy: null pointer");
+  LLMSEG_REQUIRE(n_seq > 0 && n_seq <= 65535 && t_text > 0 && n_img_tokens > 0 && vocab > 0 && ld >= vocab,
+                 LLMSEG_ESHAPE, "llmseg_lm_cross_entropy: n=%d t=%d F=%d vocab=%d ld=%d", n_seq, t_text, n_img_tokens,
+                 vocab, ld);
+  LLMSEG_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, LLMSEG_EALIGN,
+                 "llmseg_lm_cross_entropy: logits / ld not 16-byte aligned");
+  const int T = t_text + n_img_tokens - 1;
+  lm_ce_rows_kernel<<<dim3(T, n_seq), 256, 0, stream>>>(
+      static_cast<const bf16*>(logits), ld, reinterpret_cast<const long long*>(input_ids),
+      reinterpret_cast<const long long*>(labels), t_text, n_img_tokens, vocab, image_token_id, ignore_index, row_loss);
+  LLMSEG_CUDA(cudaGetLastError());
+  lm_ce_final_kernel<<<1, 256, 0, stream>>>(row_loss, n_seq * T, out2);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
   return 0;
 }
 

@@ -457,7 +457,8 @@ class ClipTower:
 # LLaMA decoder stack
 # ==============================================================================================
 class LlamaDecoder:
-    def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = "", max_seq: int = 1024):
+    def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = "", max_seq: int = 1024,
+                 lm_head: Optional[Tensor] = None):
         self.cfg, self.device = cfg, device
         if cfg.head_dim != 128:
             raise ValueError(f"LLaMA attention kernel is instantiated for head_dim 128, got {cfg.head_dim}")
@@ -481,6 +482,14 @@ class LlamaDecoder:
                 L["w_qkv"] = ops.fold_norm(L["w_qkv"], L["rms1"], rms=True)[0]
                 L["w_gu"] = ops.fold_norm(L["w_gu"], L["rms2"], rms=True)[0]
             self.layers.append(L)
+        # lm_head is dead work at inference (LISA.py:283,318); the training forward needs it.  Rows padded to a
+        # multiple of 8 (vocab 32003 -> 32008, zero rows; the CE kernel reads the first `vocab` columns only).
+        self.w_lm = None
+        if lm_head is not None:
+            v_pad = (lm_head.shape[0] + 7) // 8 * 8
+            w = torch.zeros(v_pad, cfg.hidden, dtype=BF16, device=device)
+            w[:lm_head.shape[0]] = _dev(lm_head, device)
+            self.w_lm = ops.fold_norm(w, self.norm, rms=True)[0] if FOLD_NORM else w
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.float32) / cfg.head_dim))
         fr = torch.outer(torch.arange(max_seq, dtype=torch.float32), inv)
         self.rope_cos = fr.cos().to(BF16).to(device).contiguous()
@@ -489,10 +498,14 @@ class LlamaDecoder:
         self.scratch = _Scratch(device)
 
     def forward(self, embeds: Tensor, n_seq: int, T: int, kv_len: Optional[Tensor],
-                out_rows: Optional[Tensor] = None) -> Tensor:
+                out_rows: Optional[Tensor] = None, with_logits: bool = False):
         """embeds [n_seq*T, hidden] bf16 -> final-norm hidden states; with `out_rows` (int32 flat row
-        indices) only those rows are normalised and returned (the row-wise norm commutes with the gather)."""
+        indices) only those rows are normalised and returned (the row-wise norm commutes with the gather).
+        with_logits (training forward, llava_llama.py:104-105): also returns lm_head(norm(x)) for every row,
+        bf16 [n_seq*T, vocab padded to 8] — the final norm folded into the lm_head GEMM."""
         cfg = self.cfg
+        if with_logits and self.w_lm is None:
+            raise RuntimeError("the training forward needs `lm_head.weight` in the state dict")
         if T > self.max_seq:
             raise ValueError(f"sequence length {T} exceeds the RoPE table ({self.max_seq})")
         H, hd = cfg.heads, cfg.head_dim
@@ -526,5 +539,13 @@ class LlamaDecoder:
                 m = ops.gemm(h, L["w_gu"], None, swiglu=True)
             ops.gemm(m, L["w_down"], None, residual=x, out=x, stats_out=st)
         if out_rows is not None:
-            return ops.rmsnorm(x, self.norm, cfg.eps, src_row_map=out_rows, rows_out=out_rows.numel())
-        return ops.rmsnorm(x, self.norm, cfg.eps)
+            hidden = ops.rmsnorm(x, self.norm, cfg.eps, src_row_map=out_rows, rows_out=out_rows.numel())
+        else:
+            hidden = ops.rmsnorm(x, self.norm, cfg.eps)
+        if not with_logits:
+            return hidden
+        if FOLD_NORM and st is not None:
+            logits = ops.gemm(x, self.w_lm, None, row_stats=st)
+        else:
+            logits = ops.gemm(hidden if out_rows is None else ops.rmsnorm(x, self.norm, cfg.eps), self.w_lm, None)
+        return hidden, logits

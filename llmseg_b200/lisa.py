@@ -8,7 +8,8 @@ LISA.py:173-184) — the encoder `north_star` names and the one fully in-tree.
 Differences from the reference that a caller can observe:
   * batched inference is allowed (reference asserts one image per call, LISA.py:271); a batch of B
     images with one conversation each is defined as B independent reference calls
-  * `inference=False` (training losses through the LLM) is outside the hot path and raises
+  * `inference=False` returns the reference's loss dict as forward VALUES (fp32 0-d tensors): the kernels
+    build no autograd graph, so this is the evaluation of the training objective, not a trainable step
   * extra keys (`best_index`, padded logits) are added to the returned dict; the reference keys are unchanged
   * the launch sequence of each input shape is captured once into a CUDA graph and replayed
     (`use_cuda_graph=True`): ~2300 launches per forward would otherwise be CPU-bound at batch 1
@@ -140,7 +141,8 @@ class LISAForCausalLM:
 
     def __init__(self, state_dict: Dict[str, Tensor], cfg: Optional[LisaCfg] = None, *,
                  device: str = "cuda:0", seg_token_idx: Optional[int] = None, max_seq: int = 1024,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, ce_loss_weight: float = 1.0, align_loss_weight: float = 1.0,
+                 regression_loss_weight: float = 1.0):
         if not torch.cuda.is_available():
             raise RuntimeError("llmseg_b200 needs a CUDA (sm_100) device; there is no CPU fallback")
         from . import _lib
@@ -162,7 +164,11 @@ class LISAForCausalLM:
             raise ValueError(f"image_encoder must be 'sam' or 'dinov2', got {self.cfg.image_encoder!r}")
         self.clip = ClipTower(_sub(sd, "model.vision_tower.vision_tower."), self.cfg.clip, self.device,
                               sd["model.mm_projector.weight"], sd["model.mm_projector.bias"])
-        self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq)
+        # loss weights of the training forward (reference LISA.py:158-160, training.py defaults 1.0)
+        self.ce_loss_weight, self.align_loss_weight = ce_loss_weight, align_loss_weight
+        self.regression_loss_weight = regression_loss_weight
+        self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq,
+                                  lm_head=sd.get("lm_head.weight"))
         self.selector = Selector(_sub(sd, "model."), self.device)
         self.use_cuda_graph = use_cuda_graph
         self._plans: Dict[tuple, dict] = {}
@@ -201,8 +207,8 @@ class LISAForCausalLM:
                       sam_ious_list: Optional[list] = None, sam_iops_list: Optional[list] = None,
                       inference: bool = False, **kwargs) -> dict:
         if not inference:
-            raise NotImplementedError("llmseg_b200 implements the inference forward (inference=True); the training "
-                                      "losses are out of the hot path (SURVEY §8f)")
+            return self._train_forward(images, images_clip, input_ids, labels, attention_masks, offset,
+                                       sam_segs_list, sam_ious_list, sam_iops_list)
         dev = self.device
         B, N, Tt = images.shape[0], input_ids.shape[0], input_ids.shape[1]
         if offset is None:
@@ -244,6 +250,77 @@ class LISAForCausalLM:
         pred_iou = [iou[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
         return {"pred_similarity": pred_similarity, "gt_masks": masks_list, "pred_iou": pred_iou,
                 "best_index": best.clone(), "similarity_padded": sim.clone(), "iou_padded": iou.clone()}
+
+    # ---- training forward (loss values only; no autograd graph is built) ---------------------------
+    def _train_forward(self, images, images_clip, input_ids, labels, attention_masks, offset, sam_segs_list,
+                       sam_ious_list, sam_iops_list) -> dict:
+        """`model_forward(inference=False)` (reference LISA.py:243-266,292-392,416-474 and the LLaVA forward + CE of
+        llava_llama.py:83-118): {"loss","ce_loss","align_loss","regression_loss"} as 0-d fp32 tensors.  Eager
+        launches (shapes vary per step; the [SEG] positions are read on the host like the reference's boolean
+        indexing does).  Exact shortcuts: CLIP runs once per image instead of once per conversation, mask pooling
+        once per image instead of once per round, text_hidden_fcs on the [SEG] rows only, the final RMSNorm folded
+        into the lm_head GEMM, and the label splice done by index arithmetic inside the CE kernel."""
+        dev, cfg = self.device, self.cfg
+        if labels is None or sam_segs_list is None or sam_ious_list is None or sam_iops_list is None:
+            raise ValueError("the training forward needs labels, sam_segs_list, sam_ious_list and sam_iops_list")
+        B, N, Tt = images.shape[0], input_ids.shape[0], input_ids.shape[1]
+        if offset is None:
+            offset = torch.arange(B + 1)
+        assert B == len(offset) - 1, "batch_size == len(offset) - 1 (reference LISA.py:250)"
+        off = [int(v) for v in offset.tolist()]
+        assert off[-1] == N and len(sam_segs_list) == B and images_clip.shape[0] == B
+        # [SEG] rows in row-major (conversation, position) order; the hidden state that predicts [SEG] sits at
+        # spliced position j + 255 for text index j with ids[j+1] == [SEG] (LISA.py:254-266)
+        ids_host = input_ids.detach().cpu()
+        n_img = self.cfg.clip.tokens - 1
+        T = Tt + n_img - 1
+        hits = (ids_host[:, 1:] == self.seg_token_idx).nonzero()
+        seg_rows = (hits[:, 0] * T + hits[:, 1] + (n_img - 1)).to(torch.int32)
+        per_conv = torch.bincount(hits[:, 0], minlength=N).tolist()
+        rounds = [sum(per_conv[off[i]:off[i + 1]]) for i in range(B)]
+        for i, r in enumerate(rounds):
+            if r == 0:   # reference LISA.py:435-437
+                raise ValueError("number of rounds = 0; gt_iou.shape: {}".format(tuple(sam_ious_list[i].shape)))
+        Ks = [int(s.shape[0]) for s in sam_segs_list]
+        # ---- encoders
+        emb_tokens = self.image_encoder.forward(images.to(dev, BF16))
+        feats = self.clip.forward(images_clip.to(dev, BF16))
+        conv_image = torch.tensor([i for i in range(B) for _ in range(off[i + 1] - off[i])], device=dev)
+        feats = feats.index_select(0, conv_image).contiguous()
+        ids = input_ids.to(dev).contiguous()
+        mask = None if attention_masks is None else attention_masks.to(dev)
+        embeds, kv_len, _ = ops.embed_splice(ids, mask, self.llama.embed, feats, image_token=IMAGE_TOKEN_INDEX,
+                                             seg_token=self.seg_token_idx)
+        hidden, logits = self.llama.forward(embeds, N, T, kv_len, out_rows=seg_rows.to(dev), with_logits=True)
+        ce2, _ = ops.lm_cross_entropy(logits, ids, labels.to(dev), n_img_tokens=n_img, vocab=cfg.llama.vocab,
+                                      image_token=IMAGE_TOKEN_INDEX)
+        text_embed = self.selector.text_embed(hidden)                       # [G,256], G = total rounds
+        # ---- selector over (image, round) groups sharing their image's pooled proposal features
+        plan_img = self.selector.make_plan(Ks)
+        segs = torch.cat([s.to(dev, BF16) for s in sam_segs_list], dim=0)
+        pooled = ops.maskpool(segs.contiguous(), emb_tokens.contiguous(), plan_img["mask_image"])
+        group_image = [i for i in range(B) for _ in range(rounds[i])]
+        k0 = [0]
+        for kk in Ks:
+            k0.append(k0[-1] + kk)
+        rep = torch.cat([torch.arange(k0[i], k0[i + 1]) for i in group_image]).to(dev)
+        plan_g = self.selector.make_plan([Ks[i] for i in group_image])
+        sim, iou, _ = self.selector.forward_pooled(pooled.index_select(0, rep).contiguous(), text_embed, plan_g)
+        # ---- losses: ground-truth IoU / IoP rows per round, cast to the model dtype like LISA.py:442-444
+        G, kmax = len(group_image), plan_g["kmax"]
+        gt = torch.zeros((2, G, kmax), dtype=torch.float32)
+        g = 0
+        for i in range(B):
+            for r in range(rounds[i]):
+                gt[0, g, :Ks[i]] = sam_ious_list[i][r].detach().to("cpu", BF16).float()
+                gt[1, g, :Ks[i]] = sam_iops_list[i][r].detach().to("cpu", BF16).float()
+                g += 1
+        gt = gt.to(dev)
+        valid = sum(1 for r in rounds if r > 0)
+        gw = torch.tensor([1.0 / ((rounds[i] + 1e-8) * valid) for i in group_image], dtype=torch.float32, device=dev)
+        out4, _ = ops.selector_losses(sim, iou, gt[0], gt[1], plan_g["k_off"], gw, ce=ce2,
+                                      weights=(self.ce_loss_weight, self.align_loss_weight, self.regression_loss_weight))
+        return {"loss": out4[0], "ce_loss": out4[1], "align_loss": out4[2], "regression_loss": out4[3]}
 
     # ---- plan / graph machinery ------------------------------------------------------------------
     def _make_plan(self, key) -> dict:

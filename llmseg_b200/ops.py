@@ -405,6 +405,43 @@ def align_iou_loss(sim: torch.Tensor, pred_iou: torch.Tensor, gt_iou: torch.Tens
     return out
 
 
+def selector_losses(sim: torch.Tensor, pred_iou: torch.Tensor, gt_iou: torch.Tensor, gt_iop: torch.Tensor,
+                    k_off: torch.Tensor, group_weight: torch.Tensor, *, ce: Optional[torch.Tensor] = None,
+                    weights=(1.0, 1.0, 1.0), temperature: float = 0.05):
+    """Training-forward loss assembly (reference LISA.py:416-474, loss.py:50-94) over G (image, round) groups:
+    sim/pred_iou/gt_iou/gt_iop fp32 [G, k_stride], k_off int32 [G+1], group_weight fp32 [G], ce fp32 [>=1] or None,
+    weights = (ce, align, regression).  -> (out4 = {loss, ce, align, regression}, per_group fp32 [G,2])."""
+    G, ks = sim.shape
+    for t in (sim, pred_iou, gt_iou, gt_iop):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == (G, ks)
+    assert k_off.dtype == torch.int32 and k_off.numel() == G + 1 and group_weight.dtype == torch.float32
+    per_group = torch.empty((G, 2), dtype=torch.float32, device=sim.device)
+    out = torch.empty(4, dtype=torch.float32, device=sim.device)
+    check(_lib.lib().llmseg_selector_losses(sim.data_ptr(), pred_iou.data_ptr(), gt_iou.data_ptr(), gt_iop.data_ptr(),
+                                            k_off.data_ptr(), G, ks, float(temperature), group_weight.data_ptr(),
+                                            _ptr(ce), float(weights[0]), float(weights[1]), float(weights[2]),
+                                            per_group.data_ptr(), out.data_ptr(), _stream()), "selector_losses")
+    return out, per_group
+
+
+def lm_cross_entropy(logits: torch.Tensor, input_ids: torch.Tensor, labels: torch.Tensor, *, n_img_tokens: int,
+                     vocab: int, image_token: int, ignore_index: int = -100):
+    """Shifted LM cross entropy on spliced labels (reference llava_llama.py:107-118, llava_arch.py:185-245).
+    logits bf16 [N*T, >=vocab] with T = T_text + n_img_tokens - 1.  -> (out2 = {mean CE, #targets}, row_loss [N*T])."""
+    _req_bf16(logits)
+    N, Tt = input_ids.shape
+    T = Tt + n_img_tokens - 1
+    assert logits.shape[0] == N * T and labels.shape == input_ids.shape
+    assert input_ids.dtype == torch.int64 and labels.dtype == torch.int64 and input_ids.is_cuda and labels.is_cuda
+    input_ids, labels = input_ids.contiguous(), labels.contiguous()
+    row_loss = torch.empty(N * T, dtype=torch.float32, device=logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    check(_lib.lib().llmseg_lm_cross_entropy(logits.data_ptr(), logits.stride(0), input_ids.data_ptr(), labels.data_ptr(),
+                                             N, Tt, n_img_tokens, vocab, image_token, ignore_index, row_loss.data_ptr(),
+                                             out.data_ptr(), _stream()), "lm_cross_entropy")
+    return out, row_loss
+
+
 def dice_bce_loss(logits: torch.Tensor, targets: torch.Tensor, num_masks: float) -> torch.Tensor:
     """logits/targets fp32 [n,H,W] -> fp32 [2] = {dice_loss, sigmoid_ce_loss} (reference model/loss.py:4-47)."""
     assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()

@@ -84,9 +84,16 @@ class Selector:
         """emb_tokens [B,4096,256]; seg_cat [ΣK_i,256,256] bf16 (proposals of all images, concatenated);
         text_embed [B,256] (conversation 0 of each image); plan from make_plan.
         -> (sim fp32 [B,Kmax], iou fp32 [B,Kmax], best int32 [B])."""
+        feat = ops.maskpool(seg_cat.contiguous(), emb_tokens.contiguous(), plan["mask_image"])
+        return self.forward_pooled(feat, text_embed, plan)
+
+    def forward_pooled(self, feat: Tensor, text_embed: Tensor, plan: dict):
+        """The selector after mask pooling, over G groups of mask tokens (plan = make_plan(K per group)):
+        feat [ΣK_g,256] pooled proposal features, text_embed [G,256].  At inference a group is an image; in the
+        training forward it is an (image, round) pair sharing its image's pooled features (the reference expands
+        them per conversation, LISA.py:372-375)."""
         B, kmax = plan["B"], plan["kmax"]
         k_off, b_off, mask_image = plan["k_off"], plan["b_off"], plan["mask_image"]
-        feat = ops.maskpool(seg_cat.contiguous(), emb_tokens.contiguous(), mask_image)
         text = text_embed
         ln = lambda x, n: ops.layernorm(x, n[0], n[1], 1e-5)
         for blk in self.blocks:

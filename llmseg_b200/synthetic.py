@@ -158,9 +158,12 @@ def selector_state_dict(hidden: int, seed: int, device, prefix: str = "model.") 
     return sd
 
 
-def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda") -> Dict[str, Tensor]:
-    """Full random-init state dict with the reference's key names, bf16 on `device`."""
+def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda", with_lm_head: bool = False) -> Dict[str, Tensor]:
+    """Full random-init state dict with the reference's key names, bf16 on `device`.
+    with_lm_head adds `lm_head.weight` (only the training forward reads it)."""
     sd: Dict[str, Tensor] = {}
+    if with_lm_head:
+        sd["lm_head.weight"] = _Gen(seed + 7, device).rn(cfg.llama.vocab, cfg.llama.hidden, std=cfg.llama.hidden ** -0.5)
     if cfg.image_encoder == "dinov2":
         sd.update(dinov2_state_dict(cfg.dino, seed + 1, device))
         G = _Gen(seed + 6, device)
@@ -217,3 +220,38 @@ def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int =
         "sam_segs_list": [make_proposals(n_props, g, dev) for _ in range(batch)],
         "sam_ious_list": None, "sam_iops_list": None, "inference": True,
     }
+
+
+def make_train_inputs(cfg: LisaCfg, convs_per_image, n_props, t_text: int, seed: int = 4321, device="cuda") -> dict:
+    """Training-shaped `input_dict` (reference utils/dataset.py:150-170): image i carries convs_per_image[i]
+    conversations (rounds) of t_text tokens, each ending `.. [SEG] . </s>` (right-padded variants get shorter
+    answers), labels = IGNORE over the prompt and the ids over the answer, n_props[i] proposals with
+    ground-truth IoU / IoP rows per round (`sam_ious_list[i]`: [R_i, K_i], bf16-representable values)."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    B = len(convs_per_image)
+    N = sum(convs_per_image)
+    inp = make_inputs(cfg, B, 8, t_text, seed=seed, device=device)
+    ids = torch.randint(3, 31999, (N, t_text), generator=g, device=dev, dtype=torch.int64)
+    ids[:, 0] = 1
+    ids[:, 1], ids[:, 2], ids[:, 3] = 32001, IMAGE_TOKEN_INDEX, 32002
+    labels = torch.full_like(ids, -100)
+    mask = torch.ones(N, t_text, dtype=torch.bool, device=dev)
+    for n in range(N):
+        end = t_text - (n % 3) * 2           # conversations of different lengths, right padded
+        ids[n, end - 3], ids[n, end - 2], ids[n, end - 1] = cfg.seg_token_idx, 29889, 2
+        ids[n, end:] = 0
+        mask[n, end:] = False
+        labels[n, end - 6:end] = ids[n, end - 6:end]      # the assistant's answer is the supervised span
+    off = [0]
+    for c in convs_per_image:
+        off.append(off[-1] + c)
+    q = lambda t: t.to(BF16).float()
+    inp.update({
+        "input_ids": ids, "labels": labels, "attention_masks": mask, "offset": torch.tensor(off),
+        "sam_segs_list": [make_proposals(k, g, dev) for k in n_props],
+        "sam_ious_list": [q(torch.rand(c, k, generator=g, device=dev)) for c, k in zip(convs_per_image, n_props)],
+        "sam_iops_list": [q(torch.rand(c, k, generator=g, device=dev)) for c, k in zip(convs_per_image, n_props)],
+        "inference": False,
+    })
+    return inp

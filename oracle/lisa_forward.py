@@ -138,6 +138,74 @@ def forward_batched(sd, cfg, *, images, images_clip, input_ids, attention_masks,
     return {"pred_similarity": sims, "gt_masks": None, "pred_iou": ious}
 
 
+IGNORE_INDEX = -100       # reference utils/utils.py:11
+
+
+def splice_labels(input_ids: Tensor, labels: Tensor, n_img: int) -> Tensor:
+    """Labels of `prepare_inputs_labels_for_multimodal` (llava_arch.py:185-208,230-245): the IMAGE position
+    is replaced by n_img IGNORE entries, everything else keeps its order."""
+    rows = []
+    for n in range(input_ids.shape[0]):
+        i = int((input_ids[n] == IMAGE_TOKEN_INDEX).nonzero().flatten()[0])
+        ign = torch.full((n_img,), IGNORE_INDEX, dtype=labels.dtype, device=labels.device)
+        rows.append(torch.cat([labels[n, :i], ign, labels[n, i + 1:i + 2], labels[n, i + 2:]], dim=0))
+    return torch.stack(rows, dim=0)
+
+
+def model_forward_training(sd: Dict[str, Tensor], cfg: LisaConfig, *, images: Tensor, images_clip: Tensor,
+                           input_ids: Tensor, labels: Tensor, attention_masks: Tensor, offset: Tensor,
+                           sam_segs_list: List[Tensor], sam_ious_list: List[Tensor], sam_iops_list: List[Tensor],
+                           ce_loss_weight: float = 1.0, align_loss_weight: float = 1.0,
+                           regression_loss_weight: float = 1.0) -> dict:
+    """`model_forward(inference=False)` (LISA.py:243-266,292-392,416-474) with the LLaVA forward + CE of
+    llava_llama.py:83-118: returns {"loss","ce_loss","align_loss","regression_loss"}."""
+    image_embeddings = image_features(sd, cfg, images)
+    assert image_embeddings.shape[0] == len(offset) - 1
+    seg_mask = seg_token_mask(input_ids, cfg)
+    # one CLIP image per conversation (LISA.py:293-303)
+    clip_in = torch.cat([images_clip[i:i + 1].expand(int(offset[i + 1] - offset[i]), -1, -1, -1)
+                         for i in range(len(offset) - 1)], dim=0).contiguous()
+    feats = encode_images(clip_in, sd, cfg)
+    embeds, mask = splice_inputs(input_ids, attention_masks, feats, sd["model.embed_tokens.weight"])
+    new_labels = splice_labels(input_ids, labels, feats.shape[1])
+    hidden = clip_llama.llama_last_hidden(embeds, mask, sub_dict(sd, "model."), cfg.llama)
+    logits = F.linear(hidden, sd["lm_head.weight"])
+    ce_loss = F.cross_entropy(logits[..., :-1, :].reshape(-1, logits.shape[-1]), new_labels[..., 1:].reshape(-1))
+
+    sel_sd = sub_dict(sd, "model.")
+    last = selector.text_hidden_fc(hidden, sel_sd)
+    pred = last[seg_mask]
+    counts = seg_mask.int().sum(-1)
+    seg_off = torch.cat([torch.zeros(1, dtype=torch.long, device=counts.device), counts.cumsum(-1)], dim=0)[offset]
+    pred_list = [pred[int(seg_off[i]):int(seg_off[i + 1])] for i in range(len(seg_off) - 1)]
+
+    emb_up = selector.upsample_embeddings(image_embeddings)
+    align_loss, regression_loss, valid_batch = 0.0, 0.0, 0
+    for b in range(len(sam_segs_list)):
+        gt_iou, gt_iop = sam_ious_list[b], sam_iops_list[b]
+        rounds = pred_list[b].shape[0]
+        if rounds == 0:   # LISA.py:435-437 (raised after the selector there; nothing observable happens in between)
+            raise ValueError("number of rounds = 0; gt_iou.shape: {}".format(gt_iou.shape))
+        segs_feature, pred_iou = selector.selector_features(emb_up[b], sam_segs_list[b], pred_list[b], sel_sd)
+        a_r, r_r = 0.0, 0.0
+        for r in range(rounds):
+            g_iou = gt_iou[r].unsqueeze(1).to(pred_iou.dtype)
+            g_iop = gt_iop[r].unsqueeze(1).to(pred_iou.dtype)
+            a_r = a_r + softmax_align_loss(segs_feature[r], pred_list[b][r].unsqueeze(0), g_iou)
+            r_r = r_r + iou_regression_loss(pred_iou[r], g_iop)
+        valid_batch += 1
+        align_loss = align_loss + a_r / (rounds + 1e-8)
+        regression_loss = regression_loss + r_r / (rounds + 1e-8)
+    if valid_batch > 0:
+        align_loss = align_loss / valid_batch
+        regression_loss = regression_loss / valid_batch
+    ce_loss = ce_loss * ce_loss_weight
+    align_loss = align_loss * align_loss_weight
+    regression_loss = regression_loss * regression_loss_weight
+    return {"loss": ce_loss + align_loss + regression_loss, "ce_loss": ce_loss, "align_loss": align_loss,
+            "regression_loss": regression_loss}
+
+
 # ---- losses (training only; reference model/loss.py) -------------------------------------------
 def dice_loss(inputs: Tensor, targets: Tensor, num_masks: float, scale: float = 1000, eps: float = 1e-6) -> Tensor:
     """loss.py:4-30."""

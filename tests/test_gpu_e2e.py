@@ -177,3 +177,42 @@ def test_eager_and_graph_paths_agree(cuda_lib):
     assert torch.equal(g["pred_similarity"][0], e["pred_similarity"][0])
     assert torch.equal(g["pred_iou"][0], e["pred_iou"][0])
     assert model.last_forward_launches > 50
+
+
+def test_training_forward_losses(cuda_lib):
+    """`model_forward(inference=False)`: CE through lm_head + align / regression losses over (image, round)
+    groups (reference LISA.py:292-313,416-474), 2 images with 2 and 1 conversations, ragged K, right padding.
+    Tolerance: bf16 kernels vs the fp32 oracle — 2 % relative on each loss term (values are O(0.1-10))."""
+    from llmseg_b200 import lisa, synthetic
+    from oracle import clip_llama as o_cl, lisa_forward as o_lf, sam_encoder as o_sam
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = lisa.LisaCfg()
+    cfg.sam.depth, cfg.sam.global_attn_indexes = 2, (1,)
+    cfg.clip.layers, cfg.llama.layers = 2, 2
+    sd = synthetic.lisa_state_dict(cfg, seed=3, device=DEV, with_lm_head=True)
+    model = lisa.LISAForCausalLM(sd, cfg, device=DEV, ce_loss_weight=1.0, align_loss_weight=2.0,
+                                 regression_loss_weight=0.5)
+    inp = synthetic.make_train_inputs(cfg, [2, 1], [24, 17], 32, device=DEV)
+    n0 = cuda_lib.llmseg_launch_count()
+    out = model.forward(**inp)
+    assert cuda_lib.llmseg_launch_count() - n0 > 50
+    ocfg = o_lf.LisaConfig(sam=o_sam.SamConfig(depth=2, global_attn_indexes=(1,)), clip=o_cl.ClipConfig(layers=2),
+                           llama=o_cl.LlamaConfig(layers=2))
+    with torch.no_grad():
+        ref = o_lf.model_forward_training(
+            {k: v.float() for k, v in sd.items()}, ocfg, images=inp["images"].float(),
+            images_clip=inp["images_clip"].float(), input_ids=inp["input_ids"], labels=inp["labels"],
+            attention_masks=inp["attention_masks"], offset=inp["offset"],
+            sam_segs_list=[s.float() for s in inp["sam_segs_list"]], sam_ious_list=inp["sam_ious_list"],
+            sam_iops_list=inp["sam_iops_list"], ce_loss_weight=1.0, align_loss_weight=2.0, regression_loss_weight=0.5)
+    for k in ("ce_loss", "align_loss", "regression_loss", "loss"):
+        mine, r = float(out[k]), float(ref[k])
+        print(f"{k}: ours {mine:.5f} oracle {r:.5f}")
+        assert out[k].dim() == 0 and abs(mine - r) <= 2e-2 * abs(r) + 1e-3, (k, mine, r)
+    # an image whose conversations hold no [SEG] is an error, as in the reference (LISA.py:435-437)
+    bad = dict(inp)
+    bad["input_ids"] = inp["input_ids"].clone()
+    bad["input_ids"][2][bad["input_ids"][2] == cfg.seg_token_idx] = 5
+    with pytest.raises(ValueError):
+        model.forward(**bad)

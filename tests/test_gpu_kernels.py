@@ -418,6 +418,53 @@ def test_losses_match_golden(cuda_lib, golden_dir):
     assert abs(out[1].item() - fx["expected"]["sigmoid_ce"]) < 1e-4
 
 
+def test_lm_cross_entropy_and_selector_losses(cuda_lib):
+    """CE kernel (label splice by index arithmetic, ignore_index, padded vocab stride) vs F.cross_entropy on the
+    oracle's spliced labels; batched align / regression losses vs the oracle's loss functions per group."""
+    import torch.nn.functional as F
+    from llmseg_b200 import ops
+    from oracle import lisa_forward as o_lf
+    g = torch.Generator(device=DEV).manual_seed(5)
+    N, Tt, F_, V = 3, 12, 7, 1003
+    T, ld = Tt + F_ - 1, 1008
+    ids = torch.randint(3, 900, (N, Tt), generator=g, device=DEV)
+    ids[:, 2] = -200
+    labels = ids.clone()
+    labels[:, :5] = -100
+    labels[1, 9:] = -100
+    logits = torch.zeros(N * T, ld, device=DEV, dtype=torch.bfloat16)
+    logits[:, :V] = (torch.randn(N * T, V, generator=g, device=DEV) * 3).to(torch.bfloat16)
+    logits[:, V:] = 50.0                                     # padding columns must never be read
+    out2, row_loss = ops.lm_cross_entropy(logits, ids, labels, n_img_tokens=F_, vocab=V, image_token=-200)
+    new_labels = o_lf.splice_labels(ids, labels, F_)
+    lg = logits[:, :V].float().view(N, T, V)
+    ref = F.cross_entropy(lg[:, :-1].reshape(-1, V), new_labels[:, 1:].reshape(-1))
+    n_tgt = int((new_labels[:, 1:] != -100).sum())
+    assert int(out2[1]) == n_tgt and n_tgt > 0
+    assert abs(float(out2[0]) - float(ref)) < 1e-4 * abs(float(ref))
+    assert int((row_loss >= 0).sum()) == n_tgt
+    # batched selector losses: 3 groups with ragged K
+    Ks, ks = [9, 64, 33], 64
+    k_off = torch.tensor([0, 9, 73, 106], dtype=torch.int32, device=DEV)
+    sim = torch.rand(3, ks, generator=g, device=DEV) * 2 - 1
+    piou, giou, giop = (torch.rand(3, ks, generator=g, device=DEV) for _ in range(3))
+    gw = torch.tensor([0.25, 0.25, 0.5], device=DEV)
+    ce = torch.tensor([1.25, 7.0], device=DEV)
+    out4, per = ops.selector_losses(sim, piou, giou, giop, k_off, gw, ce=ce, weights=(2.0, 0.5, 3.0))
+    a_ref = r_ref = 0.0
+    for i, K in enumerate(Ks):
+        s_, g_ = sim[i, :K, None] / 0.05, giou[i, :K, None] / 0.05
+        kl = F.kl_div(F.log_softmax(s_, 0), F.softmax(g_, 0), reduction="sum")
+        mse = o_lf.iou_regression_loss(piou[i, :K], giop[i, :K])
+        assert abs(float(per[i, 0]) - float(kl)) < 1e-4 * (1 + abs(float(kl)))
+        assert abs(float(per[i, 1]) - float(mse)) < 1e-4 * (1 + abs(float(mse)))
+        a_ref += float(gw[i]) * float(kl)
+        r_ref += float(gw[i]) * float(mse)
+    exp = [2.5 + 0.5 * a_ref + 3.0 * r_ref, 2.5, 0.5 * a_ref, 3.0 * r_ref]
+    for i in range(4):
+        assert abs(float(out4[i]) - exp[i]) < 1e-4 * (1 + abs(exp[i]))
+
+
 def test_ops_reject_bad_inputs(cuda_lib):
     from llmseg_b200 import ops
     a = torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV)      # K % 8 != 0
