@@ -219,6 +219,10 @@ int llmseg_embed_splice(const int64_t* input_ids, const uint8_t* attention_mask,
                         void* stream);
 int llmseg_add_rows_bcast(const void* x, const void* y, void* out, int rows, int dim, int group,
                           const int32_t* row_group, void* stream);
+/* out[r] = in[src_row_map[r]] (bf16 rows of `dim`, zero row for a negative index): gathers the [SEG] rows
+ * (LISA.py:322-337) so the tail of the last LLaMA layer runs on those rows only. */
+int llmseg_gather_rows(const void* in, int ld_in, void* out, int rows, int dim, const int32_t* src_row_map,
+                       void* stream);
 /* K and Vᵀ entries of window padding tokens: the reference pads with zeros AFTER LayerNorm, so their
  * k, v equal the projection bias (image_encoder.py:179-185,238-242).  pos_map: int32 [*, seq_in],
  * negative = padding position (the same map llmseg_attention takes as out_row_map); seq_ids: int32

@@ -73,6 +73,7 @@ def _declare(lib):
                                         c_int, c_void_p]
     lib.llmseg_add_rows_bcast.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_void_p, c_void_p]
+    lib.llmseg_gather_rows.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]
     lib.llmseg_fill_kv_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_int, c_void_p]
     lib.llmseg_im2col3x3.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
@@ -98,7 +99,7 @@ def _declare(lib):
 SYMBOLS = [
     "llmseg_last_error", "llmseg_version", "llmseg_launch_count",
     "llmseg_gemm", "llmseg_gemm_workspace_bytes", "llmseg_gemm_stats_parts", "llmseg_attention", "llmseg_relpos_prep", "llmseg_layernorm", "llmseg_rmsnorm", "llmseg_norm_stats",
-    "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
+    "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_gather_rows", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss", "llmseg_selector_losses", "llmseg_lm_cross_entropy",
 ]

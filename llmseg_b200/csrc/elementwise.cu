@@ -134,6 +134,22 @@ __global__ void add_rows_bcast_kernel(const bf16* __restrict__ x, const bf16* __
   }
 }
 
+// out[r] = in[map[r]] (zero row when map[r] < 0): the [SEG] rows of the residual stream / attention output feeding
+// the row-restricted tail of the last LLaMA layer (row-wise ops commute with the gather of LISA.py:322-337).
+__global__ void gather_rows_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int rows,
+                                   int dim, const int* __restrict__ map) {
+  const int nvec = dim >> 3;
+  const long long total = (long long)rows * nvec;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / nvec), v = (int)(idx % nvec);
+    const int src = map[r];
+    uint4 a = make_uint4(0, 0, 0, 0);
+    if (src >= 0) a = __ldg(reinterpret_cast<const uint4*>(in + (size_t)src * ld_in) + v);
+    reinterpret_cast<uint4*>(out + (size_t)r * dim)[v] = a;
+  }
+}
+
 // 3x3 / pad 1 im2col on token-major NHWC: out[(b,y,x), (ky,kx,c)] = in[(b,y+ky-1,x+kx-1), c] or 0.
 // One thread per 16-byte vector; feeds the SAM neck conv3x3 as a GEMM (image_encoder.py:100-106).
 __global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H,
@@ -295,6 +311,23 @@ extern "C" int llmseg_add_rows_bcast(const void* x, const void* y, void* out, in
   add_rows_bcast_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), static_cast<const bf16*>(y), static_cast<bf16*>(out), rows, dim,
       group, row_group);
+  LLMSEG_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+extern "C" int llmseg_gather_rows(const void* in, int ld_in, void* out, int rows, int dim, const int32_t* src_row_map,
+                                  void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(in && out && src_row_map, LLMSEG_EARG, "llmseg_gather_rows: null pointer");
+  LLMSEG_REQUIRE(rows > 0 && dim > 0 && dim % 8 == 0 && ld_in % 8 == 0, LLMSEG_ESHAPE,
+                 "llmseg_gather_rows: rows=%d dim=%d ld_in=%d", rows, dim, ld_in);
+  LLMSEG_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 LLMSEG_EALIGN, "llmseg_gather_rows: pointers must be 16-byte aligned");
+  const long long total = (long long)rows * (dim >> 3);
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  gather_rows_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), rows, dim, src_row_map);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

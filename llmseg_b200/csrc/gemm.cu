@@ -61,6 +61,8 @@ struct GemmDev {
   float norm_inv_dim, norm_eps;
   int norm_rms;
   int tma_store;         // PLAIN, no row map: C leaves through shared memory + TMA tile stores (pair kernel)
+  int tma_res;           // pair kernel, BN=256: the residual tile arrives through TMA into shared memory (the ring
+                         // gives up its last stage for the 8 x 4 KB landing buffers), see epilogue_tile
   float2* stats_out;     // PLAIN: per-row (sum, sum of squares) partials of this GEMM's output, or null
   int stats_parts_out;   // partials per row = num_n_tiles * 2 (one per epilogue warp sharing a row)
   float2* stats_final;   // (mean, rstd) per output row, finished in-kernel by the last tile of a row block
@@ -169,7 +171,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev& p, EpiPrefetch& pf, 
     pf.res[g] = make_uint4(0, 0, 0, 0);
     if (live && col < p.N) {
       if (p.bias) pf.bias[g] = ldg16(p.bias + col);
-      if (p.residual) {
+      if (p.residual && !p.tma_res) {
         const int rr = p.res_mod > 0 ? out_row % p.res_mod : out_row;
         pf.res[g] = ldg16(p.residual + (size_t)rr * p.ldr + col);
       }
@@ -178,9 +180,12 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev& p, EpiPrefetch& pf, 
 }
 // stage_row != nullptr: the packed bf16 groups go to this row of the warp's 128B-swizzled [32 x 64] staging
 // tile (16-byte chunk index chunk0 + j/8, XOR row&7) instead of global memory; a TMA store follows.
+// res_row != nullptr: the residual of this row's 32 columns sits in a 64B-swizzled [32 x 32] landing tile that a
+// TMA load filled (16-byte chunk index j/8 XOR res_swz) instead of in pf.res.
 __device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, int out_row, int n0,
                                           const EpiPrefetch& pf, float& st_s, float& st_ss,
-                                          uint8_t* stage_row = nullptr, int chunk0 = 0, int swz = 0) {
+                                          uint8_t* stage_row = nullptr, int chunk0 = 0, int swz = 0,
+                                          const uint8_t* res_row = nullptr, int res_swz = 0) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int col = n0 + j;
@@ -210,7 +215,8 @@ __device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, i
       for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e], p.act);
     }
     if (p.residual) {
-      const uint4 b = pf.res[j >> 3];
+      const uint4 b = res_row != nullptr ? *reinterpret_cast<const uint4*>(res_row + (((j >> 3) ^ res_swz) << 4))
+                                         : pf.res[j >> 3];
       const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -579,13 +585,34 @@ __device__ __forceinline__ void stats_finish(const GemmDev& p, int m_blk, int wa
   }
 }
 
+// tma_res: start the loads of a tile's first two residual blocks of this warp (called BEFORE the wait for the
+// tile's accumulators; the landing buffers are free since the previous tile's last reads).
+template <int BN, int NP>
+__device__ __forceinline__ void res_prefetch_first(const GemmDev& p, uint8_t* res_stage, uint64_t* res_bar,
+                                                   const CUtensorMap* tmR, int m_blk, int n_blk, int quarter,
+                                                   int chalf, int lane) {
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int n0b = n_blk * BN + (chalf * (BN / 32 / NP) + b) * 32;
+      if (n0b < p.N) {
+        mbar_expect_tx(&res_bar[b], 2048);
+        tma_load_2d(res_stage + b * 2048, tmR, &res_bar[b], n0b, m_blk * BM + quarter * 32);
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // One warp's share of a finished 128 x BN accumulator tile: quarter = TMEM lane quarter (32 rows),
 // chalf = which of the NP column parts of the tile (NP warps share a lane quarter).
 template <int BN, int MODE, bool ROPE, int NP = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage, uint32_t taddr, int m_blk,
                                               int n_blk, int quarter, int chalf, int lane, float rs,
                                               const SkOwner sk = SkOwner{0, 0, 0}, uint8_t* epi_stage = nullptr,
-                                              const CUtensorMap* tmC = nullptr) {
+                                              const CUtensorMap* tmC = nullptr, uint8_t* res_stage = nullptr,
+                                              uint64_t* res_bar = nullptr, const CUtensorMap* tmR = nullptr,
+                                              uint32_t* res_ph = nullptr) {
   const int row = m_blk * BM + quarter * 32 + lane;
   int out_row = row;
   if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
@@ -617,10 +644,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (live && col < p.N) epi_qkv_rope(p, lo, hi, out_row, col);
     }
   } else {
+    // Residual through TMA (pair kernel): the warp's 32-row x 32-column residual blocks land in two 2 KB
+    // 64B-swizzled buffers, two blocks ahead of their use; ncu had the epilogue warps parked ~30 % of their
+    // time on the first use of per-lane residual loads (32 rows per request), profiles/r02c.
+    constexpr int C_FIRST_STRIDE = BN / 32 / NP;
+    const bool tres = MODE == LLMSEG_GEMM_PLAIN && res_stage != nullptr && p.tma_res;
 #pragma unroll 1
     for (int c = chalf * (BN / 32 / NP); c < (chalf + 1) * (BN / 32 / NP); ++c) {
       uint32_t r[32];
       const int n0 = n_blk * BN + c * 32;
+      const int ci = c - chalf * C_FIRST_STRIDE;
       tmem_ld32(taddr + c * 32, r);
       EpiPrefetch pf;
       if (MODE != LLMSEG_GEMM_SWIGLU) epi_prefetch(p, pf, MODE == LLMSEG_GEMM_PLAIN ? out_row : 0, n0, live);
@@ -628,6 +661,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (sk.n_peers > 0) sk_accumulate(p, BN, r, c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
       if (fold) row_scale(r, rs);
       const bool staged = MODE == LLMSEG_GEMM_PLAIN && epi_stage != nullptr && p.tma_store;
+      if (tres && n0 < p.N) {
+        mbar_wait(&res_bar[ci & 1], (*res_ph >> (ci & 1)) & 1u);
+        *res_ph ^= 1u << (ci & 1);
+      }
       if (staged && (c & 1) == 0) {
         // the previous tile store of this warp must have drained the staging tile before it is rewritten
         if (lane == 0) bulk_wait_read0();
@@ -636,9 +673,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (live && n0 < p.N) {
         if (MODE == LLMSEG_GEMM_PLAIN)
           epi_plain(p, r, out_row, n0, pf, st_s, st_ss, staged ? epi_stage + lane * 128 : nullptr, (c & 1) * 4,
-                    lane & 7);
+                    lane & 7, tres ? res_stage + (ci & 1) * 2048 + lane * 64 : nullptr, (lane >> 1) & 3);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
         else epi_qkv(p, r, out_row, n0, pf);
+      }
+      if (tres) {
+        // every lane has consumed its row of this landing buffer: refill it with the block two steps ahead
+        __syncwarp();
+        const int n0n = n0 + 64;
+        if (lane == 0 && ci + 2 < C_FIRST_STRIDE && n0n < p.N) {
+          mbar_expect_tx(&res_bar[ci & 1], 2048);
+          tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, m_blk * BM + quarter * 32);
+        }
       }
       if (staged && (c & 1) == 1) {
         // 64 columns x 32 rows staged: hand them to the TMA (full 128-byte lines; rows >= M and
@@ -838,7 +884,10 @@ struct Cfg2 {
   static constexpr int EPI_TILE_BYTES = 32 * 128;
   static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + 8 * EPI_TILE_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 256;
+  static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 512;
+  // tma_res: the ring runs STAGES-1 deep and the last stage's 32 KB hold the residual landing buffers
+  // (two 2 KB [32 x 32] tiles per epilogue warp)
+  static constexpr int OFF_RES = (STAGES - 1) * STAGE_BYTES;
 };
 
 // Epilogue warps per CTA (G2_EPI_WARPS/4 per TMEM lane quarter, each BN*4/G2_EPI_WARPS columns).  16 warps
@@ -849,7 +898,7 @@ constexpr int G2_THREADS = 128 + G2_EPI_WARPS * 32;
 template <int BN, int MODE, bool ROPE>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmDev p) {
   using C = Cfg2<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -860,6 +909,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   uint64_t* stats_bar = tmem_empty + 3;  // [4]: epilogue warps -> statistics warp, one phase per tile
+  uint64_t* res_bar = stats_bar + 4;     // [2 per epilogue warp]: residual landing buffers (tma_res)
+  const int nst = p.tma_res ? C::STAGES - 1 : C::STAGES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -880,6 +931,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tmem_empty[i], 2 * G2_EPI_WARPS);  // leader's copy: epilogue warps x 2 CTAs
     }
     for (int i = 0; i < 4; ++i) mbar_init(&stats_bar[i], G2_EPI_WARPS);
+    for (int i = 0; i < 2 * G2_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_ptr, C::TMEM_COLS);
@@ -928,7 +980,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d_pair(sb, &tmB, lbar, kb * BK, n_blk * BN + cta_rank * (BN / 2));
           }
           __syncwarp();
-          if (++stage == C::STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -971,7 +1023,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (kb == k1 - 1) umma2_commit_mcast(&tmem_full[as], 3);
           }
           __syncwarp();
-          if (++stage == C::STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1;
           }
@@ -1050,6 +1102,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int as = 0;
     uint32_t aphase = 0;
     int st_it = 0;
+    uint32_t res_ph = 0;  // parity of this warp's two residual landing barriers
     SkWalk walk(p, num_groups, cluster_id, num_clusters);
     SkSeg sg;
     for (int grp = cluster_id;; grp += num_clusters) {
@@ -1064,6 +1117,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       const int m_blk = (n_fastest ? g / p.num_n_tiles : g % m_groups) * 2 + cta_rank;
       const int n_blk = n_fastest ? g % p.num_n_tiles : g / m_groups;
+      if (MODE == LLMSEG_GEMM_PLAIN && p.tma_res && !partial)
+        res_prefetch_first<BN, G2_EPI_WARPS / 4>(p, smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2, &tmR,
+                                                 m_blk, n_blk, quarter, chalf, lane);
       const float rs = partial ? 1.f : row_rstd(p, m_blk * BM + quarter * 32 + lane);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -1093,7 +1149,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");
         }
         epilogue_tile<BN, MODE, ROPE, G2_EPI_WARPS / 4>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
-                                                        smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC);
+                                                        smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC,
+                                                        smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2,
+                                                        &tmR, &res_ph);
         if (own.n_peers > 0) {
           asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");  // every reader of the partials is done
           if (warp == 4 && lane == 0)
@@ -1127,8 +1185,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 template <int BN, int MODE, bool ROPE>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmDev& d, int grid,
-            cudaStream_t stream) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+            const GemmDev& d, int grid, cudaStream_t stream) {
   auto kern = gemm2_kernel<BN, MODE, ROPE>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1147,7 +1205,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, d));
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, d));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -1226,6 +1284,11 @@ bool tma_store_enabled() {
     mode = e ? atoi(e) : 1;
   }
   return mode != 0;
+}
+// LLMSEG_GEMM_TMA_RES=0: residual tiles are read with per-lane global loads again (and the ring keeps all stages)
+bool tma_res_enabled() {
+  const char* e = getenv("LLMSEG_GEMM_TMA_RES");  // read per call: scripts/gpu_gemm_ab.py flips it between launches
+  return e == nullptr || atoi(e) != 0;
 }
 // LLMSEG_GEMM_STREAMK=0 disables the stream-K tail (A/B measurements)
 bool streamk_enabled() {
@@ -1409,13 +1472,23 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
       if (int e = make_tmap_bf16(&tmC, p->C, 2, cdims, cstr, cbox, 128)) return e;
       d.tma_store = 1;
     }
+    // residual through TMA landing buffers (LLMSEG_GEMM_TMA_RES=0: per-lane loads again): same tiling as C
+    CUtensorMap tmR = tmA;
+    d.tma_res = 0;
+    if (d.tma_store && bn == 256 && p->residual != nullptr && p->res_mod == 0 && tma_res_enabled()) {
+      uint64_t rdims[2] = {(uint64_t)p->N, (uint64_t)p->M};
+      uint64_t rstr[1] = {(uint64_t)p->ldr * 2};
+      uint32_t rbox[2] = {32, 32};
+      if (int e = make_tmap_bf16(&tmR, p->residual, 2, rdims, rstr, rbox, 64)) return e;
+      d.tma_res = 1;
+    }
 #define LLMSEG_GEMM2_DISPATCH(BN_)                                                              \
   switch (p->mode) {                                                                            \
-    case LLMSEG_GEMM_PLAIN: return launch2<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, tmC, d, pgrid, stream);   \
-    case LLMSEG_GEMM_SWIGLU: return launch2<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, tmC, d, pgrid, stream); \
+    case LLMSEG_GEMM_PLAIN: return launch2<BN_, LLMSEG_GEMM_PLAIN, false>(tmA, tmB, tmC, tmR, d, pgrid, stream);   \
+    case LLMSEG_GEMM_SWIGLU: return launch2<BN_, LLMSEG_GEMM_SWIGLU, false>(tmA, tmB, tmC, tmR, d, pgrid, stream); \
     default:                                                                                    \
-      return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, tmC, d, pgrid, stream)              \
-                  : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, tmC, d, pgrid, stream);            \
+      return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, tmC, tmR, d, pgrid, stream)              \
+                  : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, tmC, tmR, d, pgrid, stream);            \
   }
     if (bn == 256) {
       LLMSEG_GEMM2_DISPATCH(256)

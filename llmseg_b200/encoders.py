@@ -28,6 +28,10 @@ BF16 = torch.bfloat16
 # the norm pass over the residual stream becomes a statistics-only read.  LLMSEG_FOLD_NORM=0 keeps the
 # separate norm kernels (the reference's literal op order) for A/B runs.
 FOLD_NORM = os.environ.get("LLMSEG_FOLD_NORM", "1") != "0"
+# Row-restricted tail of the last LLaMA layer (exact: row-wise ops commute with the [SEG] gather).  Off by default:
+# measured no gain at batch 8 (80.30 vs 80.33 ms/step, profiles/r02b) — the M=8 GEMMs stream the same 300 MB of
+# weights — and it moves bf16 rounding points (the statistics come from the bf16 rows instead of the fp32 epilogue).
+LAST_LAYER_ROWS = os.environ.get("LLMSEG_LAST_LAYER_ROWS", "0") != "0"
 
 
 def _dev(t: Tensor, device) -> Tensor:
@@ -530,6 +534,18 @@ class LlamaDecoder:
                              rope_cos=self.rope_cos, rope_sin=self.rope_sin)
             ops.attention(q, k, vt, h, batch=n_seq, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=scale,
                           causal=True, kv_len=kv_len)
+            if L is self.layers[-1] and out_rows is not None and not with_logits and LAST_LAYER_ROWS:
+                # Only the hidden state that predicts [SEG] leaves the decoder (LISA.py:322-337), so everything
+                # after the last layer's attention — o_proj, both norms, the MLP — is row-wise and runs on the
+                # gathered rows alone.  Keys/values of the last layer still cover every position.
+                xr = ops.gather_rows(x, out_rows)
+                xr = ops.gemm(ops.gather_rows(h, out_rows), L["w_o"], None, residual=xr)
+                if FOLD_NORM:
+                    m = ops.gemm(xr, L["w_gu"], None, swiglu=True, row_stats=ops.norm_stats(xr, cfg.eps, rms=True))
+                else:
+                    m = ops.gemm(ops.rmsnorm(xr, L["rms2"], cfg.eps), L["w_gu"], None, swiglu=True)
+                xr = ops.gemm(m, L["w_down"], None, residual=xr)
+                return ops.rmsnorm(xr, self.norm, cfg.eps)
             ops.gemm(h, L["w_o"], None, residual=x, out=x, stats_out=stB)
             if FOLD_NORM:
                 m = ops.gemm(x, L["w_gu"], None, swiglu=True, row_stats=stB)

@@ -16,6 +16,7 @@ Differences from the reference that a caller can observe:
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -171,6 +172,8 @@ class LISAForCausalLM:
                                   lm_head=sd.get("lm_head.weight"))
         self.selector = Selector(_sub(sd, "model."), self.device)
         self.use_cuda_graph = use_cuda_graph
+        self.overlap_branches = os.environ.get("LLMSEG_OVERLAP", "1") != "0"
+        self._side_stream = torch.cuda.Stream(device=self.device)
         self._plans: Dict[tuple, dict] = {}
         self.last_forward_launches = 0
 
@@ -350,8 +353,27 @@ class LISAForCausalLM:
         no host->device copies; every index tensor comes from the plan)."""
         st = plan["static"]
         B, N, Tt = plan["key"][0], plan["key"][1], plan["key"][2]
-        # 1. image encoder (SAM ViT-H, or DINOv2 + lisa_dino_conv) -> token-major embeddings [B,4096,256]
-        emb_tokens = self.image_encoder.forward(st["images"])
+        # The image branch (1) and the text branch (2, 3) are independent until the selector; they run on two
+        # streams so that each one's launch gaps and partial last waves are filled by the other's CTAs (the fork /
+        # join is captured into the CUDA graph as two parallel chains).  LLMSEG_OVERLAP=0 serialises them.
+        cur = torch.cuda.current_stream()
+        if self.overlap_branches:
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                text_embed = self._text_branch(plan)
+            emb_tokens = self.image_encoder.forward(st["images"])
+            cur.wait_stream(side)
+        else:
+            emb_tokens = self.image_encoder.forward(st["images"])
+            text_embed = self._text_branch(plan)
+        # 4. selector
+        return self.selector.forward(emb_tokens, st["segs"], text_embed, plan["sel"])
+
+    def _text_branch(self, plan) -> Tensor:
+        """CLIP tower + projector -> splice -> LLaMA -> text_hidden_fcs on the [SEG] rows: [B,256]."""
+        st = plan["static"]
+        N, Tt = plan["key"][1], plan["key"][2]
         # 2. CLIP tower + projector (once per distinct image; the reference recomputes per conversation)
         feats = self.clip.forward(st["images_clip"])
         if plan["conv_index"] is not None:
@@ -362,9 +384,7 @@ class LISAForCausalLM:
         T = Tt + feats.shape[1] - 1
         rows = seg_row if plan["first_conv"] is None else seg_row.index_select(0, plan["first_conv"]).contiguous()
         hidden = self.llama.forward(embeds, N, T, kv_len, out_rows=rows)      # conversation 0 of each image (LISA.py:400)
-        text_embed = self.selector.text_embed(hidden)                         # [B,256]
-        # 4. selector
-        return self.selector.forward(emb_tokens, st["segs"], text_embed, plan["sel"])
+        return self.selector.text_embed(hidden)                               # [B,256]
 
     def _capture(self, plan) -> None:
         from . import _lib

@@ -346,6 +346,16 @@ def add_rows_bcast(x: torch.Tensor, y: torch.Tensor, *, group: int = 0,
     return out
 
 
+def gather_rows(x: torch.Tensor, src_row_map: torch.Tensor) -> torch.Tensor:
+    """out[r] = x[src_row_map[r]] (int32 map on the device; a negative index gives a zero row)."""
+    _req_bf16(x)
+    assert x.dim() == 2 and src_row_map.dtype == torch.int32 and src_row_map.is_cuda
+    out = torch.empty((src_row_map.numel(), x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().llmseg_gather_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.shape[0], x.shape[1],
+                                        src_row_map.data_ptr(), _stream()), "gather_rows")
+    return out
+
+
 def im2col3x3(x: torch.Tensor, batch: int, height: int, width: int) -> torch.Tensor:
     """token-major NHWC [B*H*W, C] -> [B*H*W, 9*C] (zero padded 3x3 neighbourhoods, (ky,kx,c) order)."""
     _req_bf16(x)

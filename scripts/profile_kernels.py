@@ -39,13 +39,18 @@ elif which == "attn_window":
         ops.attention(q, k, vt, out, batch=nb, heads=H, head_dim=hd, seq=S, seq_pad=S_pad, scale=scale, qext=qext, kext=kext, ext_cols=32)
 elif which.startswith("gemm"):
     shapes = {"gemm_qkv": (4096 * B, 3840, 1280), "gemm_mlp1": (4096 * B, 5120, 1280), "gemm_mlp2": (4096 * B, 1280, 5120),
-              "gemm_llama_gu": (319 * B, 22016, 4096), "gemm_llama_down": (319 * B, 4096, 11008)}
+              "gemm_llama_gu": (319 * B, 22016, 4096), "gemm_llama_down": (319 * B, 4096, 11008),
+              "gemm_proj": (4096 * B, 1280, 1280)}
     M, N, K = shapes[which]
     a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
     bias = torch.randn(N, device=dev).bfloat16()
     for _ in range(iters):
         if which == "gemm_mlp1": ops.gemm(a, w, bias, act="gelu")
         elif which == "gemm_llama_gu": ops.gemm(a, w, None, swiglu=True)
+        elif which == "gemm_proj":   # SAM attention out-projection as the encoder runs it: in-place residual + row statistics
+            if _ == 0:
+                x = torch.randn(M, N, device=dev).bfloat16(); st = ops.gemm_stats_buffer(M, N, M, 1e-6)
+            ops.gemm(a, w, bias, residual=x, out=x, stats_out=st)
         else: ops.gemm(a, w, bias)
 elif which == "maskpool":
     K = 64

@@ -137,6 +137,17 @@ def test_forward_right_padded_prompt_and_ragged_k(cuda_lib):
     _check(out, _oracle(sd, ocfg, inp), 2)
 
 
+def test_forward_long_prompt(cuda_lib):
+    """BASELINE configs[4] shape: 512-token reasoning prompt (T = 767 spliced positions, 6 causal key tiles),
+    batch 2, one row right-padded to 300 tokens."""
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 2), 2, 64, 512)
+    inp["attention_masks"][1, 300:] = False
+    inp["input_ids"][1, 297], inp["input_ids"][1, 509] = model.seg_token_idx, 17   # [SEG] inside the unpadded span
+    with torch.no_grad():
+        out = model.forward(**inp)
+    _check(out, _oracle(sd, ocfg, inp), 2)
+
+
 def test_forward_full_depth(cuda_lib):
     """BASELINE configs[1]: batch=1 full forward (SAM ViT-H 32 blocks + CLIP 23 layers + LLaMA-7B 32 layers).
 
@@ -216,3 +227,22 @@ def test_training_forward_losses(cuda_lib):
     bad["input_ids"][2][bad["input_ids"][2] == cfg.seg_token_idx] = 5
     with pytest.raises(ValueError):
         model.forward(**bad)
+
+
+def test_llama_last_layer_row_restriction(cuda_lib):
+    """LLMSEG_LAST_LAYER_ROWS: o_proj / MLP / norms of the last LLaMA layer on the gathered [SEG] rows only
+    (llmseg_gather_rows + M=B GEMMs) equals the all-rows path up to bf16 rounding of the [SEG] hidden state."""
+    from llmseg_b200 import encoders
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 2), 2, 16, 32)
+    model.use_cuda_graph = False
+    with torch.no_grad():
+        a = model.forward(**inp)
+        encoders.LAST_LAYER_ROWS = True
+        try:
+            b = model.forward(**inp)
+        finally:
+            encoders.LAST_LAYER_ROWS = False
+    for k in ("pred_similarity", "pred_iou"):
+        for i in range(2):
+            assert (a[k][i].float() - b[k][i].float()).abs().max().item() <= 8e-3     # 2 bf16 ulp at 0.5..1
+    assert torch.equal(a["best_index"], b["best_index"])
