@@ -187,12 +187,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
   const int bh = blockIdx.y;
   const int b = bh / p.heads;
 
-  int kv_limit = p.seq;
-  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
-  int kv_hi = kv_limit;
-  if (p.causal) kv_hi = min(kv_hi, q0 + BM);
-  const int n_tiles = (kv_hi + BN - 1) / BN;
-
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQa);
     tma_prefetch_desc(&tmKa);
@@ -206,6 +201,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
+
+  int kv_limit = p.seq;
+  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
+  int kv_hi = kv_limit;
+  if (p.causal) kv_hi = min(kv_hi, q0 + BM);
+  const int n_tiles = (kv_hi + BN - 1) / BN;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -520,6 +522,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -841,6 +844,7 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQa);
     tma_prefetch_desc(&tmKa);
@@ -857,6 +861,7 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -1174,8 +1179,15 @@ int launch_attn_win(const llmseg_attn_params* p, cudaStream_t stream) {
   }
   const int sms = num_sms_attn();
   const int grid = BH < sms ? BH : sms;
-  attn_win_kernel<<<grid, 320, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmQx, tmKa, tmKb, tmE, tmVa, tmVb, d, BH);
-  LLMSEG_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr, 0);
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, attn_win_kernel, tmQa, tmQb, tmQx, tmKa, tmKb, tmE, tmVa, tmVb, d, BH));
   g_launches.fetch_add(1);
   return 0;
 }
@@ -1269,8 +1281,15 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid((p->seq + BM - 1) / BM, BH);
-  kern<<<grid, 320, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
-  LLMSEG_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr, 0);
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d));
   g_launches.fetch_add(1);
   return 0;
 }

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/llmseg_b200.h"
 
@@ -37,11 +38,39 @@ int check_arch();  // 0 when the current device is sm_100, LLMSEG_EARCH otherwis
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
+// Programmatic dependent launch (opt-in, LLMSEG_PDL=1): the tcgen05 kernels are launched with the
+// programmatic-stream-serialization attribute, signal `launch_dependents` on entry and execute
+// `griddepcontrol.wait` after their prologue (barrier init, TMEM allocation, descriptor prefetch) and before
+// their first global-memory access — so the next kernel's CTAs are resident and set up when the previous
+// grid drains, instead of paying launch latency + prologue after it.  Captured into CUDA graphs as
+// programmatic dependency edges.  Measured on the batch-8 step under graph replay: 76.33 vs 76.37 ms — no gain
+// (a persistent GEMM CTA holds all of an SM's shared memory, so the next kernel's CTAs cannot become resident
+// early, and graph-internal launch latency is already ~1 us), hence off by default.
+inline bool pdl_enabled() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LLMSEG_PDL");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode != 0;
+}
+// appends the attribute when enabled; returns the new attribute count
+inline int pdl_attr(cudaLaunchAttribute* attrs, int n) {
+  if (!pdl_enabled()) return n;
+  attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[n].val.programmaticStreamSerializationAllowed = 1;
+  return n + 1;
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;
+
+// see pdl_enabled(): no-ops when the kernel was launched without the attribute
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -721,6 +721,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -749,6 +750,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (cl > 1) cluster_sync_all();  // peers' barriers must be initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
   // work items are groups of `cl` M-tiles x one N-tile, M-groups fastest; cluster c takes groups
   // c, c + num_clusters, ...  (all CTAs of a cluster iterate the same groups in lockstep)
@@ -914,6 +916,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int cta_rank = (int)cluster_ctarank();
   const bool leader = cta_rank == 0;
 
@@ -940,6 +943,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
   const int m_groups = (p.num_m_tiles + 1) / 2;
   const int num_groups = m_groups * p.num_n_tiles;
@@ -1198,13 +1202,13 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
   cfg.blockDim = dim3(G2_THREADS);
   cfg.dynamicSmemBytes = Cfg2<BN>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_attr(attr, 1);
   LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, d));
   g_launches.fetch_add(1);
   return 0;
@@ -1239,13 +1243,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, int
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = d.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_attr(attr, 1);
   LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, d));
   g_launches.fetch_add(1);
   return 0;

@@ -51,6 +51,7 @@ relpos_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQa);
     tma_prefetch_desc(&tmQb);
@@ -70,6 +71,7 @@ relpos_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
   // producer / MMA warps: warp-uniform loops, one elected lane issues (operands stay in uniform registers)
   if (warp == 0) {
@@ -230,8 +232,15 @@ int launch_relpos_win(const void* q, const void* rel_hw, int rows, int seq, int 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = d.n_tiles < sms ? d.n_tiles : sms;
-  relpos_win_kernel<<<grid, 320, C::SMEM_BYTES, stream>>>(tmQa, tmQb, tmRa, tmRb, d);
-  LLMSEG_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr, 0);
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, relpos_win_kernel, tmQa, tmQb, tmRa, tmRb, d));
   g_launches.fetch_add(1);
   return 0;
 }

@@ -32,6 +32,9 @@ FOLD_NORM = os.environ.get("LLMSEG_FOLD_NORM", "1") != "0"
 # measured no gain at batch 8 (80.30 vs 80.33 ms/step, profiles/r02b) — the M=8 GEMMs stream the same 300 MB of
 # weights — and it moves bf16 rounding points (the statistics come from the bf16 rows instead of the fp32 epilogue).
 LAST_LAYER_ROWS = os.environ.get("LLMSEG_LAST_LAYER_ROWS", "0") != "0"
+# SAM windowed layers: private k / vT buffers per layer with the constant padding rows written once (see SamEncoder).
+KV_PREFILL = os.environ.get("LLMSEG_KV_PREFILL", "1") != "0"
+KV_PREFILL_MAX_BYTES = 24 << 30
 
 
 def _dev(t: Tensor, device) -> Tensor:
@@ -116,6 +119,7 @@ class SamEncoder:
         self.kext_glb = ops.make_kext(64, device)
         self.scratch = _Scratch(device)
         self._maps: Dict[int, tuple] = {}
+        self._kv_filled = set()   # (layer, windows) whose private k / vT padding rows already hold the bias
 
     def _window_maps(self, B: int):
         """win_src[r]: image token feeding window row r (or -1 = zero padding token);
@@ -157,7 +161,7 @@ class SamEncoder:
         del a
         win_map, n_win, tok2win, pad_wins = self._window_maps(B)
         scale = hd ** -0.5
-        for blk in self.blocks:
+        for li, blk in enumerate(self.blocks):
             if blk["window"] > 0:
                 ws = blk["window"]
                 sw, sw_pad = ws * ws, (ws * ws + 7) // 8 * 8
@@ -168,8 +172,14 @@ class SamEncoder:
                 # values equal the projection bias exactly (zero input), their queries are cropped again
                 # (image_encoder.py:291-318), and attention writes straight back in token order.
                 q = self.scratch.zeros("q", nb * H, sw_pad, hd)
-                k = self.scratch.zeros("k", nb * H, sw_pad, hd)
-                vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
+                # The padding keys/values of a layer are constants of its weights (the projection bias).  With
+                # KV_PREFILL every windowed layer owns its k / vT buffers (2 x 102 MB per layer at batch 8, 5.7 GB
+                # for the 28 layers — HBM is not the scarce resource here), the padding rows are written once and
+                # the per-forward fill_kv_rows launch (35 us x 28) disappears from the step.
+                prefill = KV_PREFILL and 2 * nb * H * sw_pad * hd * 2 * len(self.blocks) <= KV_PREFILL_MAX_BYTES
+                tag = str(li) if prefill else ""
+                k = self.scratch.zeros("k" + tag, nb * H, sw_pad, hd)
+                vt = self.scratch.zeros("vt" + tag, nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
                 if FOLD_NORM:
                     wq, bq = blk["f_qkv"]
@@ -181,8 +191,11 @@ class SamEncoder:
                     ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
                                  seq_pad=sw_pad, row_map=tok2win)
                     o = h  # reuse the LN output buffer for the attention output (same shape)
-                ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
-                                 seq_ids=pad_wins)
+                if not (prefill and (tag, nb) in self._kv_filled):
+                    ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw,
+                                     seq_pad=sw_pad, seq_ids=pad_wins)
+                    if prefill and not torch.cuda.is_current_stream_capturing():
+                        self._kv_filled.add((tag, nb))
                 ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
                                 inv_scale=1.0 / scale, qext=qext)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
