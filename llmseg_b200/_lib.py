@@ -9,7 +9,10 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libllmseg_b200.so"
+import os as _os
+
+# LLMSEG_B200_LIB: load another build of the same library (A/B measurements of kernel changes on one box)
+LIB_PATH = Path(_os.environ["LLMSEG_B200_LIB"]) if _os.environ.get("LLMSEG_B200_LIB") else _PKG / "libllmseg_b200.so"
 
 c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
 

@@ -119,6 +119,15 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 // Exact-erf GELU (nn.GELU(), reference image_encoder.py:170 / common.py MLPBlock) on two values:
 // erf(z) = z * P(z^2) on |z| <= 3, clamped beyond (1 - erf(3) = 2.2e-5); P is the degree-8 least-squares
 // fit on Chebyshev nodes, |erf error| < 2.7e-5, |GELU error| < 5.6e-5 absolute — below the bf16 rounding
@@ -182,61 +191,53 @@ __device__ __forceinline__ void epi_prefetch(const GemmDev& p, EpiPrefetch& pf, 
 // tile (16-byte chunk index chunk0 + j/8, XOR row&7) instead of global memory; a TMA store follows.
 // res_row != nullptr: the residual of this row's 32 columns sits in a 64B-swizzled [32 x 32] landing tile that a
 // TMA load filled (16-byte chunk index j/8 XOR res_swz) instead of in pf.res.
-__device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, int out_row, int n0,
-                                          const EpiPrefetch& pf, float& st_s, float& st_ss,
+// All arithmetic runs on packed fp32 pairs (FFMA2 / FADD2): acc * rstd + bias is ONE instruction per pair
+// (rs = 1 without a folded norm, bias = 0 without a bias), residual one, the row statistics two — the epilogue
+// of the short-K GEMMs is what the MMA warp waits for (profiles/r02e), so instructions here are kernel time.
+__device__ __forceinline__ void epi_plain(const GemmDev& p, const uint32_t* r, float rs, int out_row, int n0,
+                                          const EpiPrefetch& pf, float2& st_s, float2& st_ss,
                                           uint8_t* stage_row = nullptr, int chunk0 = 0, int swz = 0,
                                           const uint8_t* res_row = nullptr, int res_swz = 0) {
+  const float2 rs2 = make_float2(rs, rs);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int col = n0 + j;
     if (col >= p.N) break;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
-    if (p.bias) {
-      const uint4 b = pf.bias[j >> 3];
+    float2 v[4];
+    {
+      const uint4 b = pf.bias[j >> 3];  // zeros when there is no bias
       const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = unpack_bf16(bw[e]);
-        v[2 * e] += f.x;
-        v[2 * e + 1] += f.y;
-      }
+      for (int e = 0; e < 4; ++e)
+        v[e] = ffma2(make_float2(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1])), rs2,
+                     unpack_bf16(bw[e]));
     }
     if (p.act == LLMSEG_ACT_GELU) {
 #pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        const float2 g = gelu2(make_float2(v[e], v[e + 1]));
-        v[e] = g.x;
-        v[e + 1] = g.y;
-      }
+      for (int e = 0; e < 4; ++e) v[e] = gelu2(v[e]);
     } else if (p.act != LLMSEG_ACT_NONE) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = apply_act(v[e], p.act);
+      for (int e = 0; e < 4; ++e) v[e] = make_float2(apply_act(v[e].x, p.act), apply_act(v[e].y, p.act));
     }
     if (p.residual) {
       const uint4 b = res_row != nullptr ? *reinterpret_cast<const uint4*>(res_row + (((j >> 3) ^ res_swz) << 4))
                                          : pf.res[j >> 3];
       const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = unpack_bf16(bw[e]);
-        v[2 * e] += f.x;
-        v[2 * e + 1] += f.y;
-      }
+      for (int e = 0; e < 4; ++e) v[e] = fadd2(v[e], unpack_bf16(bw[e]));
     }
     if (p.stats_out != nullptr) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        st_s += v[e];
-        st_ss = fmaf(v[e], v[e], st_ss);
+      for (int e = 0; e < 4; ++e) {
+        st_s = fadd2(st_s, v[e]);
+        st_ss = ffma2(v[e], v[e], st_ss);
       }
     }
     uint4 o;
-    o.x = pack_bf16(v[0], v[1]);
-    o.y = pack_bf16(v[2], v[3]);
-    o.z = pack_bf16(v[4], v[5]);
-    o.w = pack_bf16(v[6], v[7]);
+    o.x = pack_bf16(v[0].x, v[0].y);
+    o.y = pack_bf16(v[1].x, v[1].y);
+    o.z = pack_bf16(v[2].x, v[2].y);
+    o.w = pack_bf16(v[3].x, v[3].y);
     if (stage_row != nullptr)
       *reinterpret_cast<uint4*>(stage_row + (((chunk0 + (j >> 3)) ^ swz) << 4)) = o;
     else
@@ -619,7 +620,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
     out_row = p.out_row_map[row];  // QKV: position of this token in the (sequence, slot) index space
   const bool live = row < p.M && out_row >= 0;
   const bool fold = MODE != MODE_RELPOS && p.row_stats != nullptr;
-  float st_s = 0.f, st_ss = 0.f;
+  float2 st_s = make_float2(0.f, 0.f), st_ss = make_float2(0.f, 0.f);
   if (MODE == MODE_RELPOS) {
     relpos_tile(p, rp_stage + quarter * (128 * 32), taddr, row, n_blk, quarter, chalf, lane, row < p.M);
   } else if (MODE == LLMSEG_GEMM_QKV && ROPE) {
@@ -659,7 +660,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (MODE != LLMSEG_GEMM_SWIGLU) epi_prefetch(p, pf, MODE == LLMSEG_GEMM_PLAIN ? out_row : 0, n0, live);
       tmem_ld_wait();
       if (sk.n_peers > 0) sk_accumulate(p, BN, r, c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
-      if (fold) row_scale(r, rs);
+      if (fold && MODE != LLMSEG_GEMM_PLAIN) row_scale(r, rs);  // PLAIN folds the scale into its bias FFMA2
       const bool staged = MODE == LLMSEG_GEMM_PLAIN && epi_stage != nullptr && p.tma_store;
       if (tres && n0 < p.N) {
         mbar_wait(&res_bar[ci & 1], (*res_ph >> (ci & 1)) & 1u);
@@ -672,7 +673,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       }
       if (live && n0 < p.N) {
         if (MODE == LLMSEG_GEMM_PLAIN)
-          epi_plain(p, r, out_row, n0, pf, st_s, st_ss, staged ? epi_stage + lane * 128 : nullptr, (c & 1) * 4,
+          epi_plain(p, r, fold ? rs : 1.f, out_row, n0, pf, st_s, st_ss, staged ? epi_stage + lane * 128 : nullptr, (c & 1) * 4,
                     lane & 7, tres ? res_stage + (ci & 1) * 2048 + lane * 64 : nullptr, (lane >> 1) & 3);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
         else epi_qkv(p, r, out_row, n0, pf);
@@ -698,7 +699,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       }
     }
     if (MODE == LLMSEG_GEMM_PLAIN && p.stats_out != nullptr && live)
-      p.stats_out[(size_t)out_row * p.stats_parts_out + n_blk * NP + chalf] = make_float2(st_s, st_ss);
+      p.stats_out[(size_t)out_row * p.stats_parts_out + n_blk * NP + chalf] = make_float2(st_s.x + st_s.y, st_ss.x + st_ss.y);
   }
 }
 
