@@ -2,9 +2,13 @@
 oracle (oracle/lisa_forward.py) on identical bf16 weights and inputs.
 
 Tolerance: north_star asks 1e-3 abs on the bf16 outputs against the reference's bf16 PyTorch path.
-The oracle here is fp32 (the bf16 eager path itself is ~2e-3 away from fp32), so the
-bound on |ours - fp32 oracle| is 4e-3 for similarity / IoU; the selected index must equal the
-oracle's whenever the oracle's top-1/top-2 margin exceeds twice that bound (margin-qualified, T9).
+The oracle here is fp32 (the bf16 eager path itself is 2e-3 .. 4e-3 away from fp32: SURVEY §0/T9 and the
+three-way comparison in test_forward_full_depth), so the bound on |ours - fp32 oracle| is 4e-3 for the
+similarity (|values| < 0.5: bf16 ulp <= 2e-3).  pred_iou is a sigmoid around 0.5 .. 0.7, where the bf16 grid the
+reference (and the select kernel, which keeps the eager path's rounding points) rounds it to has a spacing of
+3.9e-3: its bound is the same 4e-3 plus half that spacing, IOU_TOL = 6e-3 (the bf16 reference path itself sits
+4.2e-3 from fp32 on this output, profiles/r02a_pytest_gpu.log).  The selected index must equal the oracle's whenever the
+oracle's top-1/top-2 margin exceeds twice the similarity bound (margin-qualified, T9).
 """
 import pytest
 import torch
@@ -12,6 +16,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 SIM_TOL = 4e-3
+IOU_TOL = 6e-3
 
 
 def _setup(depths, B, K, T_text, seed=0, image_encoder="sam"):
@@ -54,10 +59,12 @@ def _check(out, ref, B):
         i_, ri = out["pred_iou"][b].float(), ref["pred_iou"][b]
         assert s.shape == r.shape and out["pred_similarity"][b].dtype == torch.bfloat16
         assert (s - r).abs().max().item() <= SIM_TOL, f"similarity img{b}: {(s - r).abs().max().item()}"
-        assert (i_ - ri).abs().max().item() <= SIM_TOL, f"iou img{b}: {(i_ - ri).abs().max().item()}"
-        top2 = r[0].topk(2).values
-        if float(top2[0] - top2[1]) > 2 * SIM_TOL:
-            assert int(s.argmax()) == int(r.argmax())
+        assert (i_ - ri).abs().max().item() <= IOU_TOL, f"iou img{b}: {(i_ - ri).abs().max().item()}"
+        assert torch.equal(out["pred_iou"][b], out["iou_padded"][b:b + 1, :r.shape[-1]].to(torch.bfloat16))
+        if r.shape[-1] >= 2:
+            top2 = r[0].topk(2).values
+            if float(top2[0] - top2[1]) > 2 * SIM_TOL:
+                assert int(s.argmax()) == int(r.argmax())
         assert int(out["best_index"][b]) == int(s.argmax())      # fused argmax == torch.argmax of our logits
 
 
@@ -246,3 +253,63 @@ def test_llama_last_layer_row_restriction(cuda_lib):
         for i in range(2):
             assert (a[k][i].float() - b[k][i].float()).abs().max().item() <= 8e-3     # 2 bf16 ulp at 0.5..1
     assert torch.equal(a["best_index"], b["best_index"])
+
+
+def test_forward_multi_conversation(cuda_lib):
+    """The reference's own inference call shape (LISA.py:268-290): ONE image, N conversations about it
+    (`images_clip` [1,...] expanded per conversation, offset = [0, N]); the result is conversation 0's
+    (LISA.py:400,407).  Then two images with 2 + 1 conversations through `offset`."""
+    from llmseg_b200 import synthetic
+    from oracle import lisa_forward as o_lf
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 2), 2, 20, 24)
+    ids3 = synthetic.make_inputs(model.cfg, 3, 8, 24, seed=77, device=DEV)["input_ids"]
+    ids3[1, 10], ids3[1, 21] = model.seg_token_idx, 11      # conversation 1 asks about something else, earlier [SEG]
+    mask3 = torch.ones(3, 24, dtype=torch.bool, device=DEV)
+    fsd = {k: v.float() for k, v in sd.items()}
+    # (a) one image, three conversations
+    one = dict(inp, images=inp["images"][:1], images_clip=inp["images_clip"][:1], input_ids=ids3, labels=ids3,
+               attention_masks=mask3, offset=torch.tensor([0, 3]), sam_segs_list=inp["sam_segs_list"][:1])
+    with torch.no_grad():
+        out = model.forward(**one)
+        ref = o_lf.model_forward_inference(fsd, ocfg, images=one["images"].float(), images_clip=one["images_clip"].float(),
+                                           input_ids=ids3, attention_masks=mask3, offset=one["offset"],
+                                           sam_segs_list=[one["sam_segs_list"][0].float()])
+    assert len(out["pred_similarity"]) == 1 and out["pred_similarity"][0].shape == (1, 20)
+    _check(out, ref, 1)
+    # (b) two images, conversations [0,2) and [2,3)
+    two = dict(inp, input_ids=ids3, labels=ids3, attention_masks=mask3, offset=torch.tensor([0, 2, 3]))
+    with torch.no_grad():
+        out2 = model.forward(**two)
+        refs = [o_lf.model_forward_inference(fsd, ocfg, images=inp["images"][b:b + 1].float(),
+                                             images_clip=inp["images_clip"][b:b + 1].float(), input_ids=ids3[lo:hi],
+                                             attention_masks=mask3[lo:hi], offset=torch.tensor([0, hi - lo]),
+                                             sam_segs_list=[inp["sam_segs_list"][b].float()])
+                for b, (lo, hi) in enumerate(((0, 2), (2, 3)))]
+    ref2 = {k: refs[0][k] + refs[1][k] for k in ("pred_similarity", "pred_iou")}
+    _check(out2, ref2, 2)
+    # image 0 / conversation 0 is the same work item in (a) and (b)
+    assert (out2["pred_similarity"][0].float() - out["pred_similarity"][0].float()).abs().max().item() <= SIM_TOL
+
+
+def test_proposal_count_limits(cuda_lib):
+    """K = 1 and K = 128 (the selector kernels' maximum) run; K = 129 and an over-long prompt are rejected
+    with a ValueError before anything is launched; a broken offset contract asserts like LISA.py:250."""
+    from llmseg_b200 import synthetic
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 1), 2, 128, 16)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    inp["sam_segs_list"][1] = synthetic.make_proposals(1, g, DEV)
+    with torch.no_grad():
+        out = model.forward(**inp)
+    assert out["pred_similarity"][0].shape == (1, 128) and out["pred_similarity"][1].shape == (1, 1)
+    assert int(out["best_index"][1]) == 0
+    _check(out, _oracle(sd, ocfg, inp), 2)
+    inp["sam_segs_list"][0] = synthetic.make_proposals(129, g, DEV)
+    with pytest.raises(ValueError):
+        model.forward(**inp)
+    long_inp = synthetic.make_inputs(model.cfg, 1, 8, 800, device=DEV)      # T = 1055 > the RoPE table (max_seq 1024)
+    with pytest.raises(ValueError):
+        model.forward(**long_inp)
+    bad = synthetic.make_inputs(model.cfg, 2, 8, 16, device=DEV)
+    bad["offset"] = torch.tensor([0, 2])
+    with pytest.raises(AssertionError):
+        model.forward(**bad)
