@@ -213,7 +213,7 @@ def main():
     # CUDA events, on the launching stream, around every GEMM launch (the tcgen05 GEMM kernel is ~75 % of
     # the step) and every SAM global-attention launch.
     probes = []   # (group key, algorithmic flops, start event, end event)
-    orig = {n: getattr(ops, n) for n in ("attention", "gemm", "gemm_qkv")}
+    orig = {n: getattr(ops, n) for n in ("attention", "gemm", "gemm_qkv", "relpos_prep", "fill_kv_rows")}
 
     def probed(name, key_fn):
         fn = orig[name]
@@ -245,13 +245,19 @@ def main():
         return (f"gemm_qkv {M}x{N}x{K}" + (" rope" if kw.get("rope_cos") is not None else ""), 2.0 * M * N * K)
 
     def attn_key(a, kw):
-        return ("attn_global", GF_SAM_GLOBAL_ATTN * B * 1e9) if kw.get("ext_cols", 0) == 64 else None
+        if kw.get("ext_cols", 0) == 64:
+            return ("attn_global", GF_SAM_GLOBAL_ATTN * B * 1e9)
+        return (f"attn_other hd={kw.get('head_dim')} seq={kw.get('seq')}", 0.0)
+
+    def aux_key(a, kw):
+        return ("attn_aux (rel-pos prep / padding keys)", 0.0)
 
     model.use_cuda_graph = False
     overlap, model.overlap_branches = model.overlap_branches, False   # per-kernel times: one kernel at a time
     model.model_forward(**inp)      # un-probed eager pass: the first eager launches allocate (cudaMalloc syncs)
     torch.cuda.synchronize()
     ops.attention, ops.gemm, ops.gemm_qkv = probed("attention", attn_key), probed("gemm", gemm_key), probed("gemm_qkv", qkv_key)
+    ops.relpos_prep, ops.fill_kv_rows = probed("relpos_prep", aux_key), probed("fill_kv_rows", aux_key)
     try:
         for _ in range(min(args.steps, 3)):
             model.model_forward(**inp)
@@ -304,6 +310,26 @@ def main():
         steps_probed = max(1, min(args.steps, 3))
         gemm_all = {"achieved": round(fl / ms / 1e9, 1), "unit": "TFLOP/s", "frac": round(fl / ms / 1e9 / peak, 4),
                     "ms_per_step": round(ms / steps_probed, 2), "launches_per_step": sum(v[0] for v in gemm_groups.values()) // steps_probed}
+    # "Achieved fraction of the attention roofline" (BASELINE north_star): every kernel of the fused attention
+    # paths — Q/K/V projection GEMMs, rel-pos prep, padding keys, the attention kernels — against the algorithmic
+    # FLOPs of those paths (QKV GEMMs + QK^T + PV + rel-pos, causal pairs counted once).
+    fused_attn = None
+    fa_keys = [k for k in groups if k.startswith("gemm_qkv") or k.startswith("attn")]
+    if fa_keys:
+        T = T_TEXT + 255
+        if args.encoder == "sam":
+            gf_img = 28 * (48.17 + GF_SAM_WINDOW_ATTN) + 4 * (40.27 + GF_SAM_GLOBAL_ATTN)
+        else:   # DINOv2 ViT-L/14 @896: 24 x (QKV 2*4097*1024*3072 + core 4*4097^2*1024)
+            gf_img = 24 * (2 * 4097 * 1024 * 3072 + 4 * 4097 ** 2 * 1024) / 1e9
+        gf_img += 6.2 + 37.2                                                        # CLIP, 23 layers
+        gf_img += 32 * (2 * T * 4096 * 12288 + 4 * (T * (T + 1) // 2) * 128 * 32) / 1e9   # LLaMA-7B
+        steps_probed = max(1, min(args.steps, 3))
+        ms = sum(groups[k][2] for k in fa_keys) / steps_probed
+        ach = gf_img * B / ms                                                       # GFLOP / ms == TFLOP/s
+        fused_attn = {"what": "Q/K/V GEMMs + rel-pos prep + attention kernels of SAM/DINOv2, CLIP and LLaMA",
+                      "algorithmic_gflop_per_image": round(gf_img, 1), "ms_per_step": round(ms, 3),
+                      "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                      "share_of_step": round(ms / (total_ms / args.steps), 3)}
     if "attn_global" in groups:
         roof_attn = roof_of("attn_global", "attn_kernel<80,2> (SAM global attention, 64x64 tokens, rel-pos)", "attn_global_b8")
     line = {
@@ -323,6 +349,7 @@ def main():
         "roofline": roof,
         "roofline_all_gemms": gemm_all,
         "roofline_attn": roof_attn,
+        "attention_roofline": fused_attn,
     }
     if not args.no_cpu_baseline:
         from oracle.cpu_baseline import cpu_forward_sample

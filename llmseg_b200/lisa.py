@@ -173,7 +173,9 @@ class LISAForCausalLM:
         self.selector = Selector(_sub(sd, "model."), self.device)
         self.use_cuda_graph = use_cuda_graph
         self.overlap_branches = os.environ.get("LLMSEG_OVERLAP", "1") != "0"
-        self._side_stream = torch.cuda.Stream(device=self.device)
+        self._side_stream = torch.cuda.Stream(device=self.device)    # text branch
+        self._copy_stream = torch.cuda.Stream(device=self.device)    # image / proposal staging copies
+        self._cap_stream = torch.cuda.Stream(device=self.device)     # capture stream of the image / selector graphs
         self._plans: Dict[tuple, dict] = {}
         self.last_forward_launches = 0
 
@@ -226,27 +228,37 @@ class LISAForCausalLM:
         if plan is None:
             plan = self._make_plan(key)
             self._plans[key] = plan
-        # ---- stage the inputs into the plan's static device buffers (H2D or D2D copies)
+        # ---- stage the inputs into the plan's static device buffers (H2D or D2D copies) and run.  The small
+        # inputs (CLIP image, ids, mask: all the text branch needs) go first on the current stream; the 1024 px
+        # images and the proposals follow on a copy stream in the order they are needed, so the text branch starts
+        # under the image copy and the proposals (67 MB at batch 8, read only by the selector) arrive under the
+        # encoders instead of in front of them.
         st = plan["static"]
-        st["images"].copy_(images, non_blocking=True)
+        cur = torch.cuda.current_stream()
         st["images_clip"].copy_(images_clip, non_blocking=True)
         st["input_ids"].copy_(input_ids, non_blocking=True)
         if attention_masks is not None:
             st["mask"].copy_(attention_masks, non_blocking=True)
-        r0 = 0
-        for sgs, kk in zip(sam_segs_list, Ks):
-            st["segs"][r0:r0 + kk].copy_(sgs, non_blocking=True)
-            r0 += kk
-        # ---- run: CUDA-graph replay (captured on first use of this shape) or eager launches
+        cp = self._copy_stream if self.overlap_branches else cur
+        if cp is not cur:
+            cp.wait_stream(cur)      # the previous forward (enqueued on cur) has finished reading the static buffers
+        with torch.cuda.stream(cp):
+            st["images"].copy_(images, non_blocking=True)
+            ev_img = cp.record_event() if cp is not cur else None
+            r0 = 0
+            for sgs, kk in zip(sam_segs_list, Ks):
+                st["segs"][r0:r0 + kk].copy_(sgs, non_blocking=True)
+                r0 += kk
+            ev_segs = cp.record_event() if cp is not cur else None
+        # ---- CUDA-graph replay (three graphs captured on first use of this shape) or eager launches
         if self.use_cuda_graph:
-            if plan["graph"] is None:
+            if plan["graphs"] is None:
                 self._capture(plan)
-            plan["graph"].replay()
-            sim, iou, best = plan["outputs"]
+            sim, iou, best = self._pipeline(plan, ev_img, ev_segs, plan["graphs"])
         else:
             from . import _lib
             n0 = _lib.launch_count()
-            sim, iou, best = self._run(plan)
+            sim, iou, best = self._pipeline(plan, ev_img, ev_segs, None)
             plan["launches"] = _lib.launch_count() - n0
         self.last_forward_launches = plan["launches"]
         pred_similarity = [sim[i:i + 1, :Ks[i]].to(BF16) for i in range(B)]
@@ -346,29 +358,49 @@ class LISAForCausalLM:
         conv_index = None if conv_image == list(range(N)) and n_clip == N else torch.tensor(conv_image, device=dev)
         first_conv = None if N == B else torch.tensor(off[:-1], device=dev, dtype=torch.long)
         return {"key": key, "static": static, "conv_index": conv_index, "first_conv": first_conv,
-                "sel": self.selector.make_plan(Ks), "graph": None, "outputs": None, "launches": 0}
+                "sel": self.selector.make_plan(Ks), "graphs": None, "outputs": None, "launches": 0}
 
-    def _run(self, plan):
-        """The whole forward as kernel launches on the current stream (graph-capturable: no host syncs,
-        no host->device copies; every index tensor comes from the plan)."""
+    def _pipeline(self, plan, ev_img, ev_segs, graphs):
+        """The forward as three stages — text branch, image branch, selector — each either a captured CUDA graph
+        (`graphs`) or eager launches (graph-capturable: no host syncs, every index tensor comes from the plan).
+        The image branch (1) and the text branch (2, 3) are independent until the selector; they run on two
+        streams so that each one's launch gaps and partial last waves are filled by the other's CTAs.
+        ev_img / ev_segs: events after the image / proposal copies on the copy stream (None: copies were issued on
+        the current stream).  LLMSEG_OVERLAP=0 serialises everything on the current stream."""
         st = plan["static"]
-        B, N, Tt = plan["key"][0], plan["key"][1], plan["key"][2]
-        # The image branch (1) and the text branch (2, 3) are independent until the selector; they run on two
-        # streams so that each one's launch gaps and partial last waves are filled by the other's CTAs (the fork /
-        # join is captured into the CUDA graph as two parallel chains).  LLMSEG_OVERLAP=0 serialises them.
         cur = torch.cuda.current_stream()
+
+        def text():
+            if graphs is None:
+                return self._text_branch(plan)
+            graphs["text"].replay()
+            return plan["text_embed"]
+
+        def image():
+            if graphs is None:
+                return self.image_encoder.forward(st["images"])
+            graphs["image"].replay()
+            return plan["emb_tokens"]
+
         if self.overlap_branches:
             side = self._side_stream
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                text_embed = self._text_branch(plan)
-            emb_tokens = self.image_encoder.forward(st["images"])
+                text_embed = text()
+            if ev_img is not None:
+                cur.wait_event(ev_img)
+            emb_tokens = image()
             cur.wait_stream(side)
         else:
-            emb_tokens = self.image_encoder.forward(st["images"])
-            text_embed = self._text_branch(plan)
+            emb_tokens = image()
+            text_embed = text()
+        if ev_segs is not None:
+            cur.wait_event(ev_segs)
         # 4. selector
-        return self.selector.forward(emb_tokens, st["segs"], text_embed, plan["sel"])
+        if graphs is None:
+            return self.selector.forward(emb_tokens, st["segs"], text_embed, plan["sel"])
+        graphs["sel"].replay()
+        return plan["outputs"]
 
     def _text_branch(self, plan) -> Tensor:
         """CLIP tower + projector -> splice -> LLaMA -> text_hidden_fcs on the [SEG] rows: [B,256]."""
@@ -387,17 +419,27 @@ class LISAForCausalLM:
         return self.selector.text_embed(hidden)                               # [B,256]
 
     def _capture(self, plan) -> None:
+        """Warm-up (populates scratch buffers, per-stream GEMM workspaces, index maps, function attributes), then
+        capture the three stages.  The text graph is captured on the stream it will share SMs from (its GEMM
+        workspace is keyed by stream, and it replays concurrently with the image graph: separate capture streams,
+        separate memory pools)."""
         from . import _lib
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):       # warm-up: populates scratch buffers / index maps / func attributes
-            self._run(plan)
-        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)          # the staged inputs have landed
+        self._pipeline(plan, None, None, None)
         torch.cuda.synchronize(self.device)
-        graph = torch.cuda.CUDAGraph()
+        st = plan["static"]
+        for stream in (self._side_stream, self._cap_stream):
+            with torch.cuda.stream(stream):
+                ops.ensure_workspace(self.device)
+        torch.cuda.synchronize(self.device)
+        graphs = {n: torch.cuda.CUDAGraph() for n in ("text", "image", "sel")}
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
-            outs = self._run(plan)
+        with torch.cuda.graph(graphs["text"], stream=self._side_stream):
+            plan["text_embed"] = self._text_branch(plan)
+        with torch.cuda.graph(graphs["image"], stream=self._cap_stream):
+            plan["emb_tokens"] = self.image_encoder.forward(st["images"])
+        with torch.cuda.graph(graphs["sel"], stream=self._cap_stream):
+            plan["outputs"] = self.selector.forward(plan["emb_tokens"], st["segs"], plan["text_embed"], plan["sel"])
         plan["launches"] = _lib.launch_count() - n0
-        plan["graph"], plan["outputs"] = graph, outs
+        torch.cuda.synchronize(self.device)
+        plan["graphs"] = graphs

@@ -53,6 +53,11 @@ def _workspace(p: GemmParams, device) -> None:
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
 
 
+def ensure_workspace(device) -> None:
+    """Allocate (outside any graph capture) the GEMM workspace of the current stream on `device`."""
+    _workspace(GemmParams(), device)
+
+
 class RowStats:
     """Per-row normalisation statistics for gemm(row_stats=...): either (mean, rstd) pairs from norm_stats
     (parts == 0, t = fp32 [rows, 2]) or the (sum, sum of squares) partials a previous gemm(stats_out=...)
