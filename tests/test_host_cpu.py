@@ -1,0 +1,86 @@
+"""CPU: host-side logic of the product that needs no GPU — checkpoint key handling, the weight-side half of
+the folded norms, the bench.py contract of the CPU reference arm."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_strip_peft_prefix_and_lora_merge():
+    """Checkpoints saved through PEFT (reference training.py:194-237): `base_model.model.` prefix and unmerged
+    LoRA q/v deltas W + (alpha / r) * B @ A with r = 8, alpha = 16."""
+    from llmseg_b200.lisa import strip_peft_prefix
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(16, 16, generator=g)
+    a, b = torch.randn(8, 16, generator=g), torch.randn(16, 8, generator=g)
+    sd = {
+        "base_model.model.model.layers.0.self_attn.q_proj.weight": w,
+        "base_model.model.model.layers.0.self_attn.q_proj.lora_A.default.weight": a,
+        "base_model.model.model.layers.0.self_attn.q_proj.lora_B.default.weight": b,
+        "base_model.model.model.norm.weight": torch.ones(16),
+        "model.embed_tokens.weight": torch.zeros(4, 16),
+    }
+    out = strip_peft_prefix(sd)
+    assert set(out) == {"model.layers.0.self_attn.q_proj.weight", "model.norm.weight", "model.embed_tokens.weight"}
+    assert torch.allclose(out["model.layers.0.self_attn.q_proj.weight"], w + 2.0 * (b @ a), atol=1e-6)
+    # a plain state dict passes through untouched
+    plain = {"model.norm.weight": torch.ones(3)}
+    assert strip_peft_prefix(plain)["model.norm.weight"] is plain["model.norm.weight"]
+
+
+@pytest.mark.parametrize("rms", [False, True])
+def test_fold_norm_identity(rms):
+    """ops.fold_norm: Norm(x) @ W.T + b == rstd * (x @ W''.T) + b' with the row statistics applied in the GEMM
+    epilogue — the algebra behind every folded LayerNorm / RMSNorm of the encoders (fp32 check of the identity;
+    the bf16 rounding of W'' is the only approximation and is covered by the GPU tests)."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 64, generator=g) * 2 + 0.5
+    w, bias = torch.randn(24, 64, generator=g) / 8, torch.randn(24, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    eps = 1e-6
+    if rms:
+        rstd = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+        ref = (x * rstd * gamma) @ w.T + bias
+        w2, b2 = ops.fold_norm(w.double(), gamma.double(), None, bias.double(), rms=True)
+    else:
+        ref = torch.nn.functional.layer_norm(x, (64,), gamma, beta, eps) @ w.T + bias
+        rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + eps)
+        w2, b2 = ops.fold_norm(w.double(), gamma.double(), beta.double(), bias.double(), rms=False)
+    got = rstd * (x @ w2.float().T) + b2.float()
+    # w2 / b2 come back in bf16: compare against the same identity evaluated with the rounded operands' error bound
+    assert (got - ref).abs().max().item() < 0.08 and (got - ref).abs().mean().item() < 0.02
+    # exact identity in fp64 without the bf16 rounding (mirrors fold_norm's arithmetic)
+    wf = w.double() * gamma.double()[None, :]
+    if not rms:
+        wf = wf - wf.mean(1, keepdim=True)
+    bf = bias.double() + (0 if rms else w.double() @ beta.double())
+    exact = rstd.double() * (x.double() @ wf.T) + bf
+    assert (exact - ref.double()).abs().max().item() < 1e-5
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver launches next to ours): one JSON line with the same
+    metric / unit as the GPU arm, `impl`, a `cpu_baseline` describing the run and an `e2e` repeating the value."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "images/sec fwd 1024px+64tok" and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without output."""
+    import os
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, timeout=300, cwd=str(ROOT), env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
