@@ -209,6 +209,22 @@ def main():
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
+    # BASELINE configs[1] (batch = 1, the latency configuration) next to the throughput configuration: same
+    # forward, one image per step, host inputs (reported as a secondary object; `value` / `e2e` stay configs[2]).
+    b1 = None
+    if B != 1 and rank == 0 and world == 1:
+        inp1 = synthetic.make_inputs(cfg, 1, K_PROPS, T_TEXT, seed=99, device=dev)
+        host1 = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in inp1.items()}
+        host1["sam_segs_list"] = [s.cpu().pin_memory() for s in inp1["sam_segs_list"]]
+
+        def step_b1():
+            return model.forward(**host1)["best_index"].cpu()
+        for _ in range(3):
+            step_b1()
+        b1_ms = timed(step_b1, args.steps) / args.steps
+        b1 = {"workload": "configs[1]: batch=1 full fwd, host inputs", "ms_per_image": round(b1_ms, 3),
+              "value": round(1e3 / b1_ms, 3), "unit": "images/s"}
+
     # dominant-kernel timing: the same steps launched eagerly (graph nodes cannot carry timing events) with
     # CUDA events, on the launching stream, around every GEMM launch (the tcgen05 GEMM kernel is ~75 % of
     # the step) and every SAM global-attention launch.
@@ -350,6 +366,7 @@ def main():
         "roofline_all_gemms": gemm_all,
         "roofline_attn": roof_attn,
         "attention_roofline": fused_attn,
+        "batch1": b1,
     }
     if not args.no_cpu_baseline:
         from oracle.cpu_baseline import cpu_forward_sample

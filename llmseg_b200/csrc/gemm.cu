@@ -1297,12 +1297,8 @@ bool tma_res_enabled() {
 }
 // LLMSEG_GEMM_STREAMK=0 disables the stream-K tail (A/B measurements)
 bool streamk_enabled() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("LLMSEG_GEMM_STREAMK");
-    mode = e ? atoi(e) : 1;
-  }
-  return mode != 0;
+  const char* e = getenv("LLMSEG_GEMM_STREAMK");  // read per call (scripts/gpu_gemm_ab.py flips it between launches)
+  return e == nullptr || atoi(e) != 0;
 }
 // LLMSEG_RELPOS_WIN=0 routes the 14x14-window rel-pos prep through the generic GEMM kernel again
 bool relpos_win_enabled() {

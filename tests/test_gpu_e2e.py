@@ -313,3 +313,52 @@ def test_proposal_count_limits(cuda_lib):
     bad["offset"] = torch.tensor([0, 2])
     with pytest.raises(AssertionError):
         model.forward(**bad)
+
+
+def test_forward_full_depth_dinov2(cuda_lib):
+    """Variant B at full depth (DINOv2 ViT-L/14: 24 blocks at 4097 tokens, CLIP 23 layers, LLaMA-7B 32 layers),
+    batch 1: same three-way bar as test_forward_full_depth — no further from the fp32 oracle than the oracle
+    executed in bf16 eager PyTorch (x1.5 + tolerance), index equal when margin-qualified."""
+    from oracle import lisa_forward as o_lf
+    model, sd, inp, ocfg = _setup((24, None, 24, 32), 1, 64, 64, image_encoder="dinov2")
+    with torch.no_grad():
+        out = model.forward(**inp)
+    ref = _oracle(sd, ocfg, inp)
+    with torch.no_grad():
+        ref16 = o_lf.forward_batched(sd, ocfg, images=inp["images"], images_clip=inp["images_clip"],
+                                     input_ids=inp["input_ids"], attention_masks=inp["attention_masks"],
+                                     sam_segs_list=inp["sam_segs_list"])
+    for key, tol in (("pred_similarity", SIM_TOL), ("pred_iou", IOU_TOL)):
+        s, r, r16 = out[key][0].float(), ref[key][0], ref16[key][0].float()
+        e_ours, e_ref16 = (s - r).abs().max().item(), (r16 - r).abs().max().item()
+        print(f"dinov2 {key} max|d|: ours-fp32 {e_ours:.4f}  bf16ref-fp32 {e_ref16:.4f}")
+        assert e_ours <= 1.5 * e_ref16 + tol, (key, e_ours, e_ref16)
+    s, r = out["pred_similarity"][0].float(), ref["pred_similarity"][0]
+    top2 = r[0].topk(2).values
+    if float(top2[0] - top2[1]) > 2 * (s - r).abs().max().item():
+        assert int(s.argmax()) == int(r.argmax())
+
+
+def test_training_forward_dinov2_variant(cuda_lib):
+    """The checked-in reference's training branch end to end (DINOv2 features + LLaVA CE + align / regression)."""
+    from llmseg_b200 import lisa, synthetic
+    from oracle import clip_llama as o_cl, lisa_forward as o_lf
+    cfg = lisa.LisaCfg()
+    cfg.image_encoder = "dinov2"
+    cfg.dino.depth, cfg.clip.layers, cfg.llama.layers = 2, 2, 1
+    sd = synthetic.lisa_state_dict(cfg, seed=5, device=DEV, with_lm_head=True)
+    model = lisa.LISAForCausalLM(sd, cfg, device=DEV)
+    inp = synthetic.make_train_inputs(cfg, [1, 2], [9, 30], 24, device=DEV)
+    out = model.forward(**inp)
+    ocfg = o_lf.LisaConfig(clip=o_cl.ClipConfig(layers=2), llama=o_cl.LlamaConfig(layers=1), image_encoder="dinov2")
+    ocfg.dino.depth = 2
+    with torch.no_grad():
+        ref = o_lf.model_forward_training(
+            {k: v.float() for k, v in sd.items()}, ocfg, images=inp["images"].float(),
+            images_clip=inp["images_clip"].float(), input_ids=inp["input_ids"], labels=inp["labels"],
+            attention_masks=inp["attention_masks"], offset=inp["offset"],
+            sam_segs_list=[s.float() for s in inp["sam_segs_list"]], sam_ious_list=inp["sam_ious_list"],
+            sam_iops_list=inp["sam_iops_list"])
+    for k in ("ce_loss", "align_loss", "regression_loss", "loss"):
+        mine, r = float(out[k]), float(ref[k])
+        assert abs(mine - r) <= 2e-2 * abs(r) + 1e-3, (k, mine, r)
