@@ -123,6 +123,171 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming variant for large problems (>= 1 MB of rows): persistent, one CTA per SM, every warp owns a ring of
+// row buffers in shared memory that `cp.async.bulk` (the TMA engine's 1-D copy) keeps full — up to 24 KB per warp,
+// 192 KB per SM in flight with no register cost, and loads stay in flight while the warp normalises and stores
+// the previous row.  The register-resident kernel above overlaps nothing inside a warp (load, then reduce, then
+// store) and measured 46-63 % of the copy bandwidth (profiles/r01i_hbm_after.md).
+// ---------------------------------------------------------------------------------------------
+// Rows of >= 2 KB only (narrower rows stay on the register kernel: per-row overhead dominates there).
+// Warps per CTA follow the row width (8 for >= 4 KB rows, 16 for >= 2 KB, 24 below): the 192 KB of ring space is
+// split evenly between them, and narrow rows need more warps to keep the per-row latency chain (barrier wait,
+// three shuffle reductions, refill) off the critical path.
+constexpr int NS_MAX_WARPS = 24;
+constexpr int NS_RING_TOTAL = 196608;
+constexpr int NS_MAX_STAGES = 8;
+constexpr int NS_SMEM_BYTES = NS_RING_TOTAL + NS_MAX_WARPS * NS_MAX_STAGES * (8 + 4) + 128;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool RMS>
+__global__ void __launch_bounds__(NS_MAX_WARPS * 32, 1)
+norm_stream_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
+                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int rows, int dim, float eps,
+                   const int* __restrict__ src_map, float2* __restrict__ stats, int stages) {
+  extern __shared__ uint8_t ns_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ns_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)dim * 2u;
+  const int stage_bytes = (int)((row_bytes + 127u) & ~127u);
+  const int n_warps = blockDim.x >> 5;
+  uint8_t* ring = smem + warp * ((NS_RING_TOTAL / n_warps) & ~127);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS_RING_TOTAL) + warp * NS_MAX_STAGES;
+  int* absent = reinterpret_cast<int*>(smem + NS_RING_TOTAL + NS_MAX_WARPS * NS_MAX_STAGES * 8) + warp * NS_MAX_STAGES;
+  const int total_warps = gridDim.x * n_warps;
+  const int w0 = blockIdx.x * n_warps + warp;
+  const int nvec = dim >> 3;
+  const float inv_n = 1.0f / (float)dim;
+
+  // lane 0: start the copy of output row `row` into stage st (src_map < 0: nothing to copy, a zero row)
+  auto issue = [&](int st, int row) {
+    const int src = src_map ? src_map[row] : row;
+    absent[st] = src < 0;
+    if (src >= 0) {
+      mbar_expect_tx(&bars[st], row_bytes);
+      bulk_g2s(ring + st * stage_bytes, in + (size_t)src * ld_in, row_bytes, &bars[st]);
+    }
+  };
+  if (lane == 0) {
+    for (int st = 0; st < stages; ++st) mbar_init(&bars[st], 1);
+    fence_barrier_init();
+    for (int st = 0; st < stages; ++st) {
+      const int row = w0 + st * total_warps;
+      if (row < rows) issue(st, row);
+    }
+  }
+  __syncwarp();
+  uint32_t phases = 0;
+  int st = 0;
+  const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+  const uint4* b4 = reinterpret_cast<const uint4*>(beta);
+  for (int row = w0; row < rows; row += total_warps) {
+    const bool none = absent[st] != 0;
+    uint4* orow = reinterpret_cast<uint4*>(out + (size_t)row * ld_out);
+    if (none) {
+      if (stats == nullptr)
+        for (int i = lane; i < nvec; i += 32) orow[i] = make_uint4(0, 0, 0, 0);
+      else if (lane == 0) stats[row] = make_float2(0.f, rsqrtf(eps));
+    } else {
+      mbar_wait(&bars[st], (phases >> st) & 1u);
+      phases ^= 1u << st;
+      const uint4* v4 = reinterpret_cast<const uint4*>(ring + st * stage_bytes);
+      // statistics on packed fp32 pairs (FADD2 / FFMA2): the kernel is close to issue-bound once the loads are
+      // hidden, so instructions per element decide the achieved bandwidth
+      float2 s2 = make_float2(0.f, 0.f), ss2 = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int i = lane; i < nvec; i += 32) {
+        const uint4 v = v4[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(w[e]);
+          s2 = fadd2(s2, f);
+          ss2 = ffma2(f, f, ss2);
+        }
+      }
+      const float s = warp_sum(s2.x + s2.y);
+      const float ss = warp_sum(ss2.x + ss2.y);
+      float mean = 0.f, rstd;
+      if (RMS) {
+        rstd = rsqrtf(ss * inv_n + eps);
+      } else {
+        mean = s * inv_n;
+        const float2 nm = make_float2(-mean, -mean);
+        float2 sq2 = make_float2(0.f, 0.f);  // two-pass variance (the row is resident in shared memory)
+#pragma unroll 4
+        for (int i = lane; i < nvec; i += 32) {
+          const uint4 v = v4[i];
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = fadd2(unpack_bf16(w[e]), nm);
+            sq2 = ffma2(a, a, sq2);
+          }
+        }
+        rstd = rsqrtf(warp_sum(sq2.x + sq2.y) * inv_n + eps);
+      }
+      if (stats != nullptr) {
+        if (lane == 0) stats[row] = make_float2(mean, rstd);
+      } else {
+        const float2 r2 = make_float2(rstd, rstd);
+        const float2 sh = make_float2(-mean * rstd, -mean * rstd);
+#pragma unroll 2
+        for (int i = lane; i < nvec; i += 32) {
+          const uint4 v = v4[i];
+          const uint4 g = __ldg(g4 + i);
+          uint4 b = make_uint4(0, 0, 0, 0);
+          if (!RMS && beta) b = __ldg(b4 + i);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+          const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16(w[e]);
+            const float2 gg = unpack_bf16(gw[e]);
+            if (RMS) {
+              // HF: (x32 * rsqrt(var+eps)).to(bf16) * weight
+              const float2 a = fmul2(f, r2);
+              const float2 ar = unpack_bf16(pack_bf16(a.x, a.y));
+              const float2 y = fmul2(ar, gg);
+              o[e] = pack_bf16(y.x, y.y);
+            } else {
+              // ((x - mean) * rstd) * gamma + beta, the first product as x * rstd + (-mean * rstd)
+              const float2 y = ffma2(ffma2(f, r2, sh), gg, unpack_bf16(bw[e]));
+              o[e] = pack_bf16(y.x, y.y);
+            }
+          }
+          orow[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    // every lane is done with this stage: refill it with the row `stages` steps ahead
+    __syncwarp();
+    if (lane == 0) {
+      const int next = row + stages * total_warps;
+      if (next < rows) {
+        fence_async_smem();
+        issue(st, next);
+      }
+    }
+    __syncwarp();
+    st = st + 1 == stages ? 0 : st + 1;
+  }
+}
+
+// LLMSEG_NORM_STREAM=0: always the register-resident kernel (A/B; read per call)
+bool stream_norm_enabled() {
+  const char* e = getenv("LLMSEG_NORM_STREAM");
+  return e == nullptr || atoi(e) != 0;
+}
+
 template <bool RMS>
 int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* gamma, const void* beta,
                 int rows, int dim, float eps, const int32_t* src_map, cudaStream_t stream,
@@ -136,6 +301,30 @@ int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* ga
                      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) |
                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
                  LLMSEG_EALIGN, "norm: pointers / leading dims must be 16-byte aligned");
+  if ((size_t)rows * dim * 2 >= (1u << 20) && dim >= 1024 && stream_norm_enabled()) {
+    // large problem: persistent bulk-copy-staged kernel (see norm_stream_kernel)
+    auto kern = norm_stream_kernel<RMS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS_SMEM_BYTES));
+      attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int stage_bytes = (dim * 2 + 127) & ~127;
+    const int n_warps = stage_bytes >= 4096 ? 8 : (stage_bytes >= 2048 ? 16 : NS_MAX_WARPS);
+    int stages = ((NS_RING_TOTAL / n_warps) & ~127) / stage_bytes;
+    if (stages > NS_MAX_STAGES) stages = NS_MAX_STAGES;
+    const int need = (rows + n_warps - 1) / n_warps;
+    const int grid = need < sms ? need : sms;
+    kern<<<grid, n_warps * 32, NS_SMEM_BYTES, stream>>>(
+        static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out, static_cast<const bf16*>(gamma),
+        static_cast<const bf16*>(beta), rows, dim, eps, src_map, stats, stages);
+    LLMSEG_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
   const int per_lane = (dim / 8 + 31) / 32;

@@ -184,6 +184,26 @@ def test_forward_full_depth(cuda_lib):
     if float(top2[0] - top2[1]) > 2 * (s - r).abs().max().item():
         assert int(s.argmax()) == int(r.argmax())
     assert int(out["best_index"][0]) == int(s.argmax())
+    # Informational (printed with -s, recorded in profiles/): the reference's algorithm as eager bf16 PyTorch ops
+    # on this same GPU — cuBLAS GEMMs, materialised attention scores, one image per call like LISA.py:271 — next
+    # to the kernels of this repo on the same input.  Not a pass/fail criterion.
+    def _ms(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    with torch.no_grad():
+        t_ref = _ms(lambda: o_lf.forward_batched(sd, ocfg, images=inp["images"], images_clip=inp["images_clip"],
+                                                 input_ids=inp["input_ids"], attention_masks=inp["attention_masks"],
+                                                 sam_segs_list=inp["sam_segs_list"]))
+        t_ours = _ms(lambda: model.forward(**inp), n=10)
+    print(f"batch 1, full depth: eager bf16 PyTorch restatement {t_ref:.1f} ms/image, llmseg_b200 {t_ours:.1f} ms/image "
+          f"(x{t_ref / t_ours:.1f})")
 
 
 def test_eager_and_graph_paths_agree(cuda_lib):
