@@ -245,6 +245,12 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
   const int s = row - b * p.seq_in;
   const int hd = p.head_dim;
   const int hw = p.heads * hd;
+  // (q|k|v, head, offset in head) of the chunk's first column by division, then advanced by 8 per group: the
+  // runtime divisions (head_dim 80 is no power of two) were more instructions than the stores they steer
+  int which = n0 / hw;
+  const int rem0 = n0 - which * hw;
+  int h = rem0 / hd;
+  int d = rem0 - h * hd;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int col = n0 + j;
@@ -262,10 +268,6 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
         v[2 * e + 1] += f.y;
       }
     }
-    const int which = col / hw;
-    const int rem = col - which * hw;
-    const int h = rem / hd;
-    const int d = rem - h * hd;
     const size_t bh = (size_t)b * p.heads + h;
     if (which < 2) {
       bf16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq_pad + s) * hd + d;
@@ -279,6 +281,14 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
       bf16* dst = p.vt + (bh * hd + d) * p.seq_pad + s;
 #pragma unroll
       for (int e = 0; e < 8; ++e) dst[(size_t)e * p.seq_pad] = __float2bfloat16_rn(v[e]);
+    }
+    d += 8;   // 8-column groups never straddle a head (head_dim % 8 == 0)
+    if (d >= hd) {
+      d = 0;
+      if (++h == p.heads) {
+        h = 0;
+        ++which;
+      }
     }
   }
 }
