@@ -829,17 +829,17 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* bar_e = bars + 0;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;
-  uint64_t* k_full = bars + 3;    // [2]
-  uint64_t* k_empty = bars + 5;   // [2]
-  uint64_t* v_full = bars + 7;    // [2]
-  uint64_t* v_empty = bars + 9;   // [2]
-  uint64_t* bar_s = bars + 11;    // [2] score tile t ready
-  uint64_t* bar_p = bars + 13;    // [2] P_t written          (4 elected arrivals)
-  uint64_t* bar_o = bars + 15;    // [2] O_t complete
-  uint64_t* o_free = bars + 17;   // [2] O_t/S_t columns released by the epilogue (4 elected arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* q_full = bars + 1;    // [2] Q tile t of the current item landed
+  uint64_t* q_empty = bars + 3;   // [2] score MMA of tile t done with its Q tile
+  uint64_t* k_full = bars + 5;    // [2]
+  uint64_t* k_empty = bars + 7;   // [2]
+  uint64_t* v_full = bars + 9;    // [2]
+  uint64_t* v_empty = bars + 11;  // [2]
+  uint64_t* bar_s = bars + 13;    // [2] score tile t ready
+  uint64_t* bar_p = bars + 15;    // [2] P_t written          (4 elected arrivals)
+  uint64_t* bar_o = bars + 17;    // [2] O_t complete
+  uint64_t* o_free = bars + 19;   // [2] O_t/S_t columns released by the epilogue (4 elected arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -849,7 +849,7 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
     tma_prefetch_desc(&tmQa);
     tma_prefetch_desc(&tmKa);
     tma_prefetch_desc(&tmVa);
-    for (int i = 0; i < 19; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 21; ++i) mbar_init(&bars[i], 1);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bar_p[t], 4);
       mbar_init(&o_free[t], 4);
@@ -893,18 +893,18 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
         tma_load_3d(sv + 3 * C::V_CHUNK, &tmVb, &v_full[st], 192, 0, item);
       }
       __syncwarp();
-      mbar_wait(q_empty, (it & 1) ^ 1);
-      if (issuer) {
-        mbar_expect_tx(q_full, C::Q_TX);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&q_empty[t], (it & 1) ^ 1);
+        if (issuer) {
           uint8_t* sq = smem + C::OFF_Q + t * C::QT_BYTES;
-          tma_load_3d(sq, &tmQa, q_full, 0, t * 128, item);
-          tma_load_3d(sq + 16384, &tmQb, q_full, 64, t * 128, item);
-          tma_load_3d(sq + 20480, &tmQx, q_full, 0, t * 128, item);
+          mbar_expect_tx(&q_full[t], C::QT_BYTES);
+          tma_load_3d(sq, &tmQa, &q_full[t], 0, t * 128, item);
+          tma_load_3d(sq + 16384, &tmQb, &q_full[t], 64, t * 128, item);
+          tma_load_3d(sq + 20480, &tmQx, &q_full[t], 0, t * 128, item);
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -915,58 +915,82 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
       const uint32_t sE = smem_u32(smem + C::OFF_E);
       const uint64_t dE = umma_smem_desc(sE, 512, UMMA_SW64);
       mbar_wait(bar_e, 0);
+      // The two query tiles of an item run half a period apart:  S0(i)  PV1(i-1)  S1(i)  PV0(i)  S0(i+1) ...
+      // Tile 0's warps are in their softmax (MUFU-bound) while tile 1's read O and store, and vice versa, so each
+      // softmax has the MUFU pipe to itself and the tensor pipe works for one tile while the other one's threads
+      // are busy.  Issued back to back (S0 S1 ... PV0 PV1, both softmaxes at once) an item was one serial chain:
+      // 10.7k clk against a 3.3k clk MUFU floor (profiles/r01k).
+      auto issue_s = [&](int t, uint32_t sk) {
+        const uint32_t sq = smem_u32(smem + C::OFF_Q + t * C::QT_BYTES);
+        const uint32_t tS = tmem_base + t * 256;
+        const uint64_t dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
+        const uint64_t dK1 = umma_smem_desc(sk + 26624, 256, UMMA_SW32);
+        const uint64_t dQ0 = umma_smem_desc(sq, 1024, UMMA_SW128);
+        const uint64_t dQ1 = umma_smem_desc(sq + 16384, 256, UMMA_SW32);
+        const uint64_t dQX = umma_smem_desc(sq + 20480, 512, UMMA_SW64);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
+          umma_ss(tS, dQ1, dK1, idesc_s, 1);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_ss(tS, dQX + 2 * k, dE + 2 * k, idesc_s, 1);
+          umma_commit(&bar_s[t]);
+          umma_commit(&q_empty[t]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int t, uint32_t sv) {
+        const uint32_t tS = tmem_base + t * 256;
+        const uint64_t dV = umma_smem_desc(sv, 1024, UMMA_SW128);
+        const uint64_t dVt = umma_smem_desc(sv + 3 * C::V_CHUNK, 256, UMMA_SW32);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k)
+            umma_ts(tS + C::O_COL, tS + k * 8, dV + (uint64_t)((k >> 2) * (C::V_CHUNK >> 4) + (k & 3) * 2), idesc_o,
+                    k != 0);
+          umma_ts(tS + C::O_COL, tS + 96, dVt, idesc_o, 1);
+          umma_commit(&bar_o[t]);
+        }
+        __syncwarp();
+      };
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int st = it & 1;
         const uint32_t ph = it & 1, kvph = (it >> 1) & 1;
         const uint32_t sk = smem_u32(smem + C::OFF_K + st * C::K_ALLOC);
         const uint32_t sv = smem_u32(smem + C::OFF_V + st * C::V_ALLOC);
-        const uint64_t dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
-        const uint64_t dK1 = umma_smem_desc(sk + 26624, 256, UMMA_SW32);
-        mbar_wait(q_full, ph);
+        // ---- S0(i)
+        mbar_wait(&q_full[0], ph);
         mbar_wait(&k_full[st], kvph);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (it > 0) mbar_wait(&o_free[t], ph ^ 1);  // previous item's O_t / S_t columns drained
+        if (it > 0) mbar_wait(&o_free[0], ph ^ 1);  // previous item's O_0 / S_0 columns drained
+        tc_fence_after();
+        issue_s(0, sk);
+        // ---- PV1(i-1): the other V buffer (its v_full was waited for by PV0(i-1))
+        if (it > 0) {
+          mbar_wait(&bar_p[1], ph ^ 1);
           tc_fence_after();
-          const uint32_t sq = smem_u32(smem + C::OFF_Q + t * C::QT_BYTES);
-          const uint32_t tS = tmem_base + t * 256;
-          const uint64_t dQ0 = umma_smem_desc(sq, 1024, UMMA_SW128);
-          const uint64_t dQ1 = umma_smem_desc(sq + 16384, 256, UMMA_SW32);
-          const uint64_t dQX = umma_smem_desc(sq + 20480, 512, UMMA_SW64);
-          if (issuer) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
-            umma_ss(tS, dQ1, dK1, idesc_s, 1);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) umma_ss(tS, dQX + 2 * k, dE + 2 * k, idesc_s, 1);
-            umma_commit(&bar_s[t]);
-          }
+          issue_pv(1, smem_u32(smem + C::OFF_V + (st ^ 1) * C::V_ALLOC));
+          if (issuer) umma_commit(&v_empty[st ^ 1]);
           __syncwarp();
         }
-        if (issuer) {
-          umma_commit(&k_empty[st]);
-          umma_commit(q_empty);
-        }
+        // ---- S1(i)
+        mbar_wait(&q_full[1], ph);
+        if (it > 0) mbar_wait(&o_free[1], ph ^ 1);
+        tc_fence_after();
+        issue_s(1, sk);
+        if (issuer) umma_commit(&k_empty[st]);
         __syncwarp();
+        // ---- PV0(i)
         mbar_wait(&v_full[st], kvph);
-        const uint64_t dV = umma_smem_desc(sv, 1024, UMMA_SW128);
-        const uint64_t dVt = umma_smem_desc(sv + 3 * C::V_CHUNK, 256, UMMA_SW32);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&bar_p[t], ph);
-          tc_fence_after();
-          const uint32_t tS = tmem_base + t * 256;
-          if (issuer) {
-#pragma unroll
-            for (int k = 0; k < 12; ++k)
-              umma_ts(tS + C::O_COL, tS + k * 8, dV + (uint64_t)((k >> 2) * (C::V_CHUNK >> 4) + (k & 3) * 2), idesc_o,
-                      k != 0);
-            umma_ts(tS + C::O_COL, tS + 96, dVt, idesc_o, 1);
-            umma_commit(&bar_o[t]);
-          }
-          __syncwarp();
-        }
+        mbar_wait(&bar_p[0], ph);
+        tc_fence_after();
+        issue_pv(0, sv);
+      }
+      if (it > 0) {  // PV1 of the last item
+        const int st = (it - 1) & 1;
+        mbar_wait(&bar_p[1], (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+        issue_pv(1, smem_u32(smem + C::OFF_V + st * C::V_ALLOC));
         if (issuer) umma_commit(&v_empty[st]);
         __syncwarp();
       }
@@ -1027,6 +1051,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
         mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
       }
       const float moff = -mx * c1;  // c1 > 0
+      // (tried: gating the two tiles' exp passes so that they strictly take turns on the MUFU pipe — 132 us
+      //  against 125 ungated on the same box; the pass is bound by its own TMEM-load / ex2 / pack chain, and the
+      //  gate only adds waiting)
       // ---- pass 2: P = exp2((s - max) * c1) -> packed bf16 over S columns [0,104) ----
       float l0 = 0.f, l1 = 0.f;
       auto exp_chunk = [&](const uint32_t* r, int c) {
@@ -1099,6 +1126,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           }
         }
       }
+      // (releasing the columns right after the TMEM read, before the row stores, measured SLOWER — 134-141 us
+      //  against 118: the next score MMA then starts early enough for both tiles' softmaxes to overlap again and
+      //  share the MUFU pipe; the stores are what keeps the two tiles half a period apart)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
