@@ -137,6 +137,21 @@ def strip_peft_prefix(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
     return {k: v for k, v in out.items() if ".lora_" not in k}
 
 
+def select_proposals(output_dict: dict, threshold: Optional[float] = None):
+    """The two selection rules the reference's validation loops apply to a forward's outputs:
+    `validate` keeps the proposal with the highest similarity (training.py:627-629) — here the argmax fused into
+    the select kernel (`best_index`, falling back to argmax of `pred_similarity` for a plain reference dict) — and
+    `validate_threshold` keeps every proposal whose predicted IoU exceeds `threshold` (training.py:712-718).
+    Returns one `(best, kept)` pair per image; `kept` is None without a threshold."""
+    sims, ious = output_dict["pred_similarity"], output_dict["pred_iou"]
+    best = output_dict.get("best_index")
+    best = [int(v) for v in best.tolist()] if best is not None else [int(torch.argmax(s_)) for s_ in sims]
+    kept = None
+    if threshold is not None:
+        kept = [[i for i, v in enumerate(u[0].float().tolist()) if v > threshold] for u in ious]
+    return [(best[i], None if kept is None else kept[i]) for i in range(len(sims))]
+
+
 class LISAForCausalLM:
     """B200 implementation of the reference class of the same name (inference forward only)."""
 

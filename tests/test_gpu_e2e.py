@@ -382,3 +382,24 @@ def test_training_forward_dinov2_variant(cuda_lib):
     for k in ("ce_loss", "align_loss", "regression_loss", "loss"):
         mine, r = float(out[k]), float(ref[k])
         assert abs(mine - r) <= 2e-2 * abs(r) + 1e-3, (k, mine, r)
+
+
+def test_proposal_permutation_equivariance(cuda_lib):
+    """The selector has no positional encoding over the K proposals: permuting them permutes similarity / IoU (up to
+    the summation order inside the K x K self-attention) and moves the selected index with them."""
+    from llmseg_b200.lisa import select_proposals
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 1), 1, 40, 16)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    perm = torch.randperm(40, generator=g).to(DEV)
+    with torch.no_grad():
+        a = model.forward(**inp)
+        inp2 = dict(inp, sam_segs_list=[inp["sam_segs_list"][0][perm].contiguous()])
+        b = model.forward(**inp2)
+    for k in ("pred_similarity", "pred_iou"):
+        assert (a[k][0][:, perm].float() - b[k][0].float()).abs().max().item() <= SIM_TOL
+    sa, sb = a["pred_similarity"][0].float()[0], b["pred_similarity"][0].float()[0]
+    top2 = sa.topk(2).values
+    if float(top2[0] - top2[1]) > 2 * SIM_TOL:
+        assert int(perm[int(sb.argmax())]) == int(sa.argmax())
+    (best, kept), = select_proposals(b, threshold=0.5)
+    assert best == int(b["best_index"][0]) and all(float(b["pred_iou"][0][0, i]) > 0.5 for i in kept)

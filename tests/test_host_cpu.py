@@ -84,3 +84,15 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                        text=True, timeout=300, cwd=str(ROOT), env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_select_proposals_rules():
+    """training.py:627-629 (argmax of the similarity) and :712-718 (predicted IoU above a threshold), on a dict
+    shaped like the forward's output, with and without the fused `best_index`."""
+    from llmseg_b200.lisa import select_proposals
+    out = {"pred_similarity": [torch.tensor([[0.1, 0.7, 0.3]]), torch.tensor([[0.9, -0.2]])],
+           "pred_iou": [torch.tensor([[0.6, 0.4, 0.51]], dtype=torch.bfloat16), torch.tensor([[0.2, 0.1]], dtype=torch.bfloat16)]}
+    assert select_proposals(out) == [(1, None), (0, None)]
+    assert select_proposals(out, threshold=0.5) == [(1, [0, 2]), (0, [])]
+    out["best_index"] = torch.tensor([1, 0], dtype=torch.int32)
+    assert select_proposals(out, threshold=0.5) == [(1, [0, 2]), (0, [])]
