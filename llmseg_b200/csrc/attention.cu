@@ -1009,54 +1009,55 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
       const uint32_t ph = it & 1;
       mbar_wait(&bar_s[t], ph);
       tc_fence_after();
-      // TMEM loads cost a ~300-clk round trip each; issued one per wait they were 19 serial round trips per
-      // item and dominated the tile time.  Now: pass 1 in two bulk loads, pass 2 double-buffered (the next
-      // chunk is in flight while the current one goes through the MUFU), the O read in one batch.
-      // ---- pass 1: row max over the 196 valid keys ----
-      float mx = -INFINITY;
-      {
-        uint32_t r[96];
-        tmem_ld32(tS, r);
-        tmem_ld32(tS + 32, r + 32);
-        tmem_ld32(tS + 64, r + 64);
-        tmem_ld_wait();
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 96; e += 4) {
-          m0 = fmaxf(m0, __uint_as_float(r[e]));
-          m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
-          m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
-          m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      {
-        uint32_t r[112];
-        tmem_ld32(tS + 96, r);
-        tmem_ld32(tS + 128, r + 32);
-        tmem_ld32(tS + 160, r + 64);
-        tmem_ld16(tS + 192, r + 96);
-        tmem_ld_wait();
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 96; e += 4) {
-          m0 = fmaxf(m0, __uint_as_float(r[e]));
-          m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
-          m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
-          m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (192 + e < seq) m0 = fmaxf(m0, __uint_as_float(r[96 + e]));
-        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-      }
-      const float moff = -mx * c1;  // c1 > 0
-      // (tried: gating the two tiles' exp passes so that they strictly take turns on the MUFU pipe — 132 us
-      //  against 125 ungated on the same box; the pass is bound by its own TMEM-load / ex2 / pack chain, and the
-      //  gate only adds waiting)
-      // ---- pass 2: P = exp2((s - max) * c1) -> packed bf16 over S columns [0,104) ----
+      // ONE pass over the score tile.  TMEM reads run at 64 B/clk per SM: a [256 x 208] fp32 item is 3.3k clk per
+      // read, and the separate row-max pass this replaces made the kernel TMEM-read-bound (2 reads + O = 8k of its
+      // 9.7k clk per item, profiles/r02m).  Now every 32-key chunk is read once: its maximum joins a RUNNING maximum
+      // m_run, P = exp2(s*c1 - m_run) goes back to TMEM as bf16, and only when some row's maximum grows by more than
+      // 2^8 over what its earlier chunks were scaled with (warp-uniform vote; rare after the first chunk) the
+      // chunks already written are rescaled in place — the same lazy rescale the multi-tile kernel applies to O.
       float l0 = 0.f, l1 = 0.f;
+      float m_run = -INFINITY;
+      auto chunk_max = [&](const uint32_t* r, int n) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          if (e + 0 < n) m0 = fmaxf(m0, __uint_as_float(r[e]));
+          if (e + 1 < n) m1 = fmaxf(m1, __uint_as_float(r[e + 1]));
+          if (e + 2 < n) m2 = fmaxf(m2, __uint_as_float(r[e + 2]));
+          if (e + 3 < n) m3 = fmaxf(m3, __uint_as_float(r[e + 3]));
+        }
+        return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c1;  // c1 > 0: max commutes with the scaling
+      };
+      // join chunk c's maximum (log2 units); on a large jump rescale P chunks [0, c) and the row sums
+      auto advance_max = [&](float cm, int c) {
+        if (c == 0) {
+          m_run = cm;
+          return;
+        }
+        const bool grow = cm > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float f = grow ? ex2(m_run - cm) : 1.0f;
+          if (grow) m_run = cm;
+          l0 *= f;
+          l1 *= f;
+          tmem_st_wait();
+#pragma unroll 1
+          for (int cc = 0; cc < c; ++cc) {
+            uint32_t pq[16];
+            tmem_ld16(tS + cc * 16, pq);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float2 v = unpack_bf16(pq[e]);
+              pq[e] = pack_bf16(v.x * f, v.y * f);
+            }
+            tmem_st16(tS + cc * 16, pq);
+          }
+        }
+      };
       auto exp_chunk = [&](const uint32_t* r, int c) {
+        advance_max(chunk_max(r, 32), c);
+        const float moff = -m_run;
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -1082,6 +1083,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           exp_chunk(rb, c + 1);
         }
         tmem_ld_wait();
+        // keys 192..207: valid below seq (196)
+        advance_max(chunk_max(ra, seq - 192 < 16 ? seq - 192 : 16), 6);
+        const float moff = -m_run;
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; e += 2) {

@@ -226,6 +226,40 @@ def test_sam_relpos_attention(cuda_lib, grid, nb):
     assert d.abs().mean().item() <= 4e-3
 
 
+def test_window_attention_running_max_rescale(cuda_lib):
+    """The window kernel reads every 32-key chunk of a score row once and scales it with a RUNNING row maximum;
+    when a later chunk's maximum exceeds it by more than 2^8 the chunks already written are rescaled in place.
+    Force that path: keys whose scores climb by ~20 (natural units) from one 32-key chunk to the next for half of
+    the rows, and fall for the other half (no rescale: both behaviours inside one warp)."""
+    from llmseg_b200 import ops
+    H, hd, S, Sp, nb = 2, 80, 196, 200, 3
+    g = torch.Generator().manual_seed(11)
+    scale = hd ** -0.5
+    d = torch.nn.functional.normalize(torch.randn(hd, generator=g), dim=0)
+    q = torch.randn(nb * H, S, hd, generator=g) * 0.3
+    sign = torch.where(torch.arange(S) % 2 == 0, 1.0, -1.0)                 # even rows climb, odd rows fall
+    q = q + sign[None, :, None] * 6.0 * d                                    # q.d = +-6
+    step = (torch.arange(S) // 32).float() * (20.0 / (6.0 * scale))          # k.d grows per chunk: score += 20 per chunk
+    k = torch.randn(nb * H, S, hd, generator=g) * 0.3 + step[None, :, None] * d
+    v = torch.randn(nb * H, S, hd, generator=g)
+    qp, kp = torch.zeros(nb * H, Sp, hd), torch.zeros(nb * H, Sp, hd)
+    qp[:, :S], kp[:, :S] = q, k
+    vt = torch.zeros(nb * H, hd, Sp)
+    vt[:, :, :S] = v.transpose(-1, -2)
+    qd, kd, vtd = _bf(qp), _bf(kp), _bf(vt)
+    qext = torch.zeros(nb * H, Sp, 32, device=DEV, dtype=torch.bfloat16)     # zero rel-pos tables: plain attention
+    out = torch.full((nb * S, H * hd), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention(qd, kd, vtd, out, batch=nb, heads=H, head_dim=hd, seq=S, seq_pad=Sp, scale=scale, qext=qext,
+                  kext=ops.make_kext(14, DEV), ext_cols=32)
+    qf, kf, vf = qd[:, :S].float(), kd[:, :S].float(), vtd[:, :, :S].float().transpose(-1, -2)
+    sc = (qf @ kf.transpose(-1, -2)) * scale
+    assert float((sc[:, 0::2, 160:].amax(-1) - sc[:, 0::2, :32].amax(-1)).min()) > 60      # the jump is really there
+    ref = (torch.softmax(sc, -1) @ vf).reshape(nb, H, S, hd).permute(0, 2, 1, 3).reshape(nb * S, H * hd)
+    dlt = out.float() - ref
+    assert not torch.isnan(dlt).any()
+    assert dlt.abs().max().item() <= 3e-2 * max(1.0, float(ref.abs().max())) and dlt.abs().mean().item() <= 3e-3
+
+
 @pytest.mark.parametrize("rows,dim,N,rms", [(1000, 1280, 1024, False), (319, 4096, 512, True), (257, 1024, 768, False)])
 def test_norm_folded_into_gemm(cuda_lib, rows, dim, N, rms):
     """y = act(Norm(x) @ W.T + b) with the norm folded into the GEMM (norm_stats + fold_norm + row_stats)
