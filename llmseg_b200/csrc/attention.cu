@@ -1130,9 +1130,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           }
         }
       }
-      // (releasing the columns right after the TMEM read, before the row stores, measured SLOWER — 134-141 us
-      //  against 118: the next score MMA then starts early enough for both tiles' softmaxes to overlap again and
-      //  share the MUFU pipe; the stores are what keeps the two tiles half a period apart)
+      // (releasing the columns right after the TMEM read, before the row stores, measured SLOWER twice — 134-141 us
+      //  against 118 with the two-pass softmax, 98 against 93.6 with the single pass: the stores are part of what
+      //  keeps the two tiles half a period apart)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
