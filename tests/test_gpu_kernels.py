@@ -126,6 +126,38 @@ def test_norms(cuda_lib, rows, dim, eps):
     assert (y.float() - ref4).abs().max().item() <= _ulp_tol(ref4)
 
 
+@pytest.mark.parametrize("rows,dim,rms", [(6000, 1280, False), (2100, 4096, True), (3000, 1024, False)])
+def test_streaming_norm_with_row_gather(cuda_lib, rows, dim, rms):
+    """The bulk-copy-staged kernel (>= 1 MB, rows >= 2 KB) with a gather map that repeats rows and contains
+    negative entries (zero rows), more rows than one pass of the persistent grid, and a strided input."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(rows + dim)
+    xs = _bf(torch.randn(rows // 2, dim + 64, generator=g) * 1.5 - 0.3)
+    x = xs[:, :dim]                                                    # row stride dim + 64
+    gm, bt = _bf(1 + 0.1 * torch.randn(dim, generator=g)), _bf(0.1 * torch.randn(dim, generator=g))
+    m = torch.randint(0, rows // 2, (rows,), generator=g)
+    m[::17] = -1
+    md = m.to(torch.int32).to(DEV)
+    eps = 1e-6
+    if rms:
+        y = ops.rmsnorm(x, gm, eps, src_row_map=md, rows_out=rows)
+        xf = x.float()
+        full = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).bfloat16().float() * gm.float()
+    else:
+        y = ops.layernorm(x, gm, bt, eps, src_row_map=md, rows_out=rows)
+        full = torch.nn.functional.layer_norm(x.float(), (dim,), gm.float(), bt.float(), eps)
+    ref = full[m.clamp_min(0).to(DEV)]
+    ref[(m < 0).to(DEV)] = 0
+    assert y.shape == (rows, dim)
+    assert (y.float() - ref).abs().max().item() <= _ulp_tol(ref)
+    st = ops.norm_stats(x.contiguous(), eps, rms=rms)                  # statistics-only mode on the same kernel
+    xf = x.float()
+    rstd = torch.rsqrt((xf.pow(2).mean(-1) if rms else xf.var(-1, unbiased=False)) + eps)
+    assert (st.t[:, 1] - rstd).abs().max().item() <= 1e-3 * float(rstd.max())
+    if not rms:
+        assert (st.t[:, 0] - xf.mean(-1)).abs().max().item() <= 1e-3
+
+
 def _qkv_setup(B, H, hd, S, g, rope=False):
     from llmseg_b200 import ops
     D = H * hd
