@@ -1,5 +1,6 @@
-"""Developer GPU check: stage-by-stage parity of the CUDA path against the fp32 oracle (same bf16
-weights), reduced depth by default; `full` runs the real depths and times the forward."""
+"""Developer GPU check (run by hand: `python tests/manual_e2e_check.py [full]`; lives under tests/ because it
+imports the oracle): stage-by-stage parity of the CUDA path against the fp32 oracle (same bf16 weights), reduced
+depth by default; `full` runs the real depths and times the forward."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
