@@ -87,28 +87,26 @@ class ClockSampler:
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle port: fp32 eager
-    PyTorch on all host threads), bounded sample per step (oracle/cpu_baseline.py)."""
+    """Reference arm: the reference's own CPU implementation of the path (oracle port: fp32 eager PyTorch on the
+    host threads), one REAL full-depth single-image forward per step (oracle/cpu_baseline.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.cpu_baseline import cpu_forward_sample
+    from oracle.cpu_baseline import cpu_forward_full
     steps = max(1, min(args.steps, 3))
-    vals = []
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_forward_sample(T_TEXT, K_PROPS)
+    warm = max(0, min(args.warmup, 1))
     t0 = time.perf_counter()
-    for _ in range(steps):
-        res = cpu_forward_sample(T_TEXT, K_PROPS)
-        vals.append(res["value"])
+    res = cpu_forward_full(args.t_text, K_PROPS, reps=steps, warmup=warm)
     wall = time.perf_counter() - t0
-    v = statistics.median(vals)
+    v = res["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"1 image, 1024px, {T_TEXT}-tok prompt, {K_PROPS} proposals (CPU, extrapolated from a bounded sample)"},
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "config": {"workload": f"1 image per step, 1024px, {args.t_text}-tok prompt, {K_PROPS} proposals: full-depth forward "
+                               f"(SAM ViT-H + CLIP ViT-L/14 + LLaMA-7B + selector) on the host CPU"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                         "seconds_per_image": res["seconds"], "spread": res["spread"]},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(wall, 1),
     }
@@ -123,7 +121,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step (weak scaling)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and eager-GPU baseline legs")
+    ap.add_argument("--sync-gather", action="store_true",
+                    help="blocking all-gather every step (default: issued async, consumed one step later)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the configs[3] / configs[4] secondary objects")
     # non-default workloads (the default is the BASELINE metric's configuration)
     ap.add_argument("--t-text", type=int, default=T_TEXT, help="prompt tokens (configs[4]: 512)")
     ap.add_argument("--encoder", default="sam", choices=["sam", "dinov2"],
@@ -154,44 +155,73 @@ def main():
     model = lisa.LISAForCausalLM(sd, cfg, device=str(dev))
     del sd
     torch.cuda.empty_cache()
-    dp = lsd.DataParallelLisa(model, k_max=K_PROPS)
     inp = synthetic.make_inputs(cfg, B, K_PROPS, T_TEXT, seed=1234 + 1000 * rank, device=dev)
     k_max, b_max = K_PROPS, B
+    pending = []          # the in-flight all-gather of the previous step: [(gathered tensor, work handle)]
+    last = {}
 
-    def step_resident():
-        out = model.model_forward(**inp)
-        ks = [K_PROPS] * B
-        packed = lsd.pack_logits(out["similarity_padded"], out["iou_padded"], out["best_index"], ks, k_max, b_max)
-        return lsd.all_gather_logits(packed)
+    def consume():
+        """Finish the previous step's all-gather (the logits of every rank's images become readable)."""
+        if pending:
+            out, work = pending.pop()
+            if work is not None:
+                work.wait()
+            last["gathered"] = out
 
-    # host-side (pinned) copies for the e2e arm
-    host = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
-    host["sam_segs_list"] = [s.cpu().pin_memory() for s in inp["sam_segs_list"]]
+    def make_steps(model_inputs, host_inputs, batch):
+        def pack(out):
+            return lsd.pack_logits(out["similarity_padded"], out["iou_padded"], out["best_index"], [K_PROPS] * batch,
+                                   k_max, batch)
+
+        def resident():
+            packed = pack(model.model_forward(**model_inputs))
+            if args.sync_gather:
+                last["gathered"] = lsd.all_gather_logits(packed)
+                return
+            # ONE collective per forward, off the critical path: this rank starts its next forward while slower ranks
+            # finish this one; the result is consumed one step later (and drained before the clock stops)
+            consume()
+            pending.append(lsd.all_gather_logits(packed, async_op=True))
+
+        def e2e():
+            packed = pack(model.forward(**host_inputs))   # pinned host tensors: forward() stages them with async H2D copies
+            res = lsd.all_gather_logits(packed)
+            return res.cpu()   # device -> host read of every image's logits + selected index
+        return resident, e2e
+
+    def to_host(x):
+        h = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in x.items()}
+        h["sam_segs_list"] = [t.cpu().pin_memory() for t in x["sam_segs_list"]]
+        return h
+
+    host = to_host(inp)
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("images", "images_clip", "input_ids", "attention_masks"))
-    h2d += sum(s.numel() * s.element_size() for s in host["sam_segs_list"])
-
-    def step_e2e():
-        out = model.forward(**host)   # pinned host tensors: forward() stages them with async H2D copies
-        packed = lsd.pack_logits(out["similarity_padded"], out["iou_padded"], out["best_index"], [K_PROPS] * B, k_max, b_max)
-        res = lsd.all_gather_logits(packed)
-        return res.cpu()   # device -> host read of every image's logits + selected index
+    h2d += sum(t.numel() * t.element_size() for t in host["sam_segs_list"])
+    step_resident, step_e2e = make_steps(inp, host, B)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, per_rank=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        consume()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            if per_rank is not None:
+                allms = torch.empty(world, device=dev)
+                dist.all_gather_into_tensor(allms, ms)
+                per_rank.extend(round(float(v) / steps, 3) for v in allms.tolist())
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        elif per_rank is not None:
+            per_rank.append(round(float(ms.item()) / steps, 3))
         return float(ms.item())
 
     sampler = ClockSampler(local)
@@ -201,7 +231,8 @@ def main():
         step_resident()
     torch.cuda.synchronize()
     sampler.mark()
-    total_ms = timed(step_resident, args.steps)          # CUDA-graph replay of the captured forward
+    rank_ms = []
+    total_ms = timed(step_resident, args.steps, rank_ms)  # CUDA-graph replay of the captured forward
     launches = model.last_forward_launches                # kernels captured in (= launched by) one forward
     clocks = sampler.stop() if rank == 0 else None
 
@@ -209,13 +240,76 @@ def main():
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
 
+    # ---- N > 1: is the all-gather the concatenation of single-GPU results?  Outside any timed region, rank 0
+    # rebuilds every other rank's seeded inputs, runs them itself and compares with the rows it gathered — bit-equal,
+    # since the replicas are independent and the kernels deterministic (SURVEY §4 tier 4).
+    gather_check = per_rank = None
+    if world > 1:
+        step_resident()
+        consume()
+        torch.cuda.synchronize()
+        gathered = last["gathered"].clone()
+        if rank == 0:
+            ok, worst = True, 0.0
+            for r in range(world):
+                inp_r = synthetic.make_inputs(cfg, B, K_PROPS, T_TEXT, seed=1234 + 1000 * r, device=dev)
+                out_r = model.model_forward(**inp_r)
+                exp = lsd.pack_logits(out_r["similarity_padded"], out_r["iou_padded"], out_r["best_index"],
+                                      [K_PROPS] * B, k_max, b_max)
+                got = gathered[r * b_max:(r + 1) * b_max]
+                ok &= bool(torch.equal(got, exp))
+                fin = torch.isfinite(exp)
+                worst = max(worst, float((got[fin] - exp[fin]).abs().max()))
+            gather_check = {"ranks_verified": world, "rows": int(gathered.shape[0]), "bit_equal": ok, "max_abs_diff": worst,
+                            "what": "rank 0 recomputed every rank's seeded inputs locally and compared with the rows it gathered"}
+        # per-rank pace: forward time and the time this rank then spends blocked in a SYNCHRONOUS all-gather
+        fwd, gat = [], []
+        for _ in range(min(args.steps, 5)):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            dist.barrier()
+            e[0].record()
+            out = model.model_forward(**inp)
+            e[1].record()
+            lsd.all_gather_logits(lsd.pack_logits(out["similarity_padded"], out["iou_padded"], out["best_index"],
+                                                  [K_PROPS] * B, k_max, b_max))
+            e[2].record()
+            torch.cuda.synchronize()
+            fwd.append(e[0].elapsed_time(e[1]))
+            gat.append(e[1].elapsed_time(e[2]))
+        mine = torch.tensor([statistics.median(fwd), statistics.median(gat)], device=dev)
+        allr = torch.empty(2 * world, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, 2).tolist()
+        per_rank = {"timed_region_ms_per_step": rank_ms, "forward_ms": [round(v[0], 3) for v in allr],
+                    "blocked_in_sync_all_gather_ms": [round(v[1], 3) for v in allr],
+                    "gather": "sync" if args.sync_gather else "async, consumed one step later"}
+
+    # ---- secondary workloads on the same replica set (reported like batch1; `value` / `e2e` stay configs[2]):
+    # BASELINE configs[3] = batch 32 over 8 GPUs = 4 images / GPU; configs[4] = 512-token prompts, batch 16 over
+    # 8 GPUs = 2 images / GPU.  At N < 8 the same per-GPU shapes are timed (weak scaling: global batch = N x per-GPU).
+    extra = {}
+    if not args.no_extra_configs and args.encoder == "sam" and T_TEXT == 64 and B == 8:
+        for name, bb, tt in (("configs3", 4, 64), ("configs4", 2, 512)):
+            x = synthetic.make_inputs(cfg, bb, K_PROPS, tt, seed=4321 + 1000 * rank, device=dev)
+            res_x, e2e_x = make_steps(x, to_host(x), bb)
+            for _ in range(3):
+                res_x()
+            ms = timed(res_x, args.steps)
+            for _ in range(2):
+                e2e_x()
+            ms2 = timed(e2e_x, args.steps)
+            extra[name] = {"workload": (f"configs[{name[-1]}]-shaped: batch={bb}/GPU x {world} GPU(s) = {bb * world}, "
+                                        f"{tt}-tok prompt, {K_PROPS} proposals, full fwd"),
+                           "value": round(bb * world * args.steps / (ms / 1e3), 3), "unit": "images/s",
+                           "ms_per_step": round(ms / args.steps, 3),
+                           "e2e": round(bb * world * args.steps / (ms2 / 1e3), 3)}
+
     # BASELINE configs[1] (batch = 1, the latency configuration) next to the throughput configuration: same
     # forward, one image per step, host inputs (reported as a secondary object; `value` / `e2e` stay configs[2]).
     b1 = None
     if B != 1 and rank == 0 and world == 1:
         inp1 = synthetic.make_inputs(cfg, 1, K_PROPS, T_TEXT, seed=99, device=dev)
-        host1 = {k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in inp1.items()}
-        host1["sam_segs_list"] = [s.cpu().pin_memory() for s in inp1["sam_segs_list"]]
+        host1 = to_host(inp1)
 
         def step_b1():
             return model.forward(**host1)["best_index"].cpu()
@@ -360,17 +454,66 @@ def main():
                    "l2": "15.4 GB of weights streamed per step (>> 126 MB L2); no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(world * b_max * (2 * k_max + 2) * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
+                "d2h_bytes_per_step": int(world * b_max * lsd.packed_width(k_max) * 4), "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
         "roofline": roof,
         "roofline_all_gemms": gemm_all,
         "roofline_attn": roof_attn,
         "attention_roofline": fused_attn,
         "batch1": b1,
+        "configs3": extra.get("configs3"), "configs4": extra.get("configs4"),
+        "gather_check": gather_check, "per_rank": per_rank,
     }
+    if roof_attn is not None:
+        # BASELINE.json's second metric: tensor-pipe utilisation of the fused attention kernels, from the committed
+        # `ncu --set full` captures (profiles/; a number taken under the profiler, so it is quoted, not re-measured)
+        for k_, name in (("attn_global_b8", "tensor_pipe_pct"), ("attn_win_b8", "tensor_pipe_pct_window_kernel")):
+            if traffic_db.get(k_, {}).get("tensor_pipe_pct") is not None:
+                roof_attn[name] = traffic_db[k_]["tensor_pipe_pct"]
+                roof_attn[name + "_source"] = traffic_db[k_].get("source")
     if not args.no_cpu_baseline:
-        from oracle.cpu_baseline import cpu_forward_sample
-        cb = cpu_forward_sample(T_TEXT, K_PROPS)
+        # ---- baselines (checker code timed as a baseline, never part of the product path; rank 0, N = 1 only)
+        # (1) the reference's algorithm as eager bf16 PyTorch on THIS GPU — cuBLAS GEMMs, materialised attention
+        #     scores, one image per call like reference model/LISA.py:271: the number a B200 user of the reference
+        #     would see, since no Blackwell kernel exists upstream
+        if world == 1 and args.encoder == "sam":
+            from oracle import lisa_forward as o_lf
+            del model
+            torch.cuda.empty_cache()
+            sd = synthetic.lisa_state_dict(cfg, seed=0, device=dev)
+            ocfg = o_lf.LisaConfig()
+            x8 = synthetic.make_inputs(cfg, B, K_PROPS, T_TEXT, seed=1234, device=dev)
+
+            def eager(n_img):
+                return o_lf.forward_batched(sd, ocfg, images=x8["images"][:n_img], images_clip=x8["images_clip"][:n_img],
+                                            input_ids=x8["input_ids"][:n_img], attention_masks=x8["attention_masks"][:n_img],
+                                            sam_segs_list=x8["sam_segs_list"][:n_img])
+
+            def ms_of(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+            with torch.no_grad():
+                t1 = ms_of(lambda: eager(1), 3)
+                tb = ms_of(lambda: eager(B), 2)
+            line["eager_gpu_baseline"] = {
+                "what": "oracle restatement of reference model/LISA.py:225-414 as eager bf16 PyTorch ops on the same B200 "
+                        "(cuBLAS, materialised attention, one image per call as LISA.py:271 asserts)",
+                "batch1_ms_per_image": round(t1, 2), "batch1_images_per_s": round(1e3 / t1, 2),
+                f"batch{B}_as_{B}_calls_ms": round(tb, 2), f"batch{B}_images_per_s": round(B * 1e3 / tb, 2),
+                "ours_over_eager_batch1": round(t1 / b1["ms_per_image"], 2) if b1 else None,
+                f"ours_over_eager_batch{B}": round(value / (B * 1e3 / tb), 2)}
+            del sd
+            torch.cuda.empty_cache()
+        # (2) the same algorithm on the host CPU: one REAL full-depth single-image forward
+        from oracle.cpu_baseline import cpu_forward_full
+        cb = cpu_forward_full(T_TEXT, K_PROPS, reps=1, warmup=0)
         line["cpu_baseline"] = {"value": round(cb["value"], 5), "unit": "images/s", "cores": cb["cores"],
                                 "kind": cb["kind"], "sample": cb["sample"]}
     print(json.dumps(line), flush=True)

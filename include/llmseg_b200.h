@@ -244,8 +244,13 @@ int llmseg_im2col3x3(const void* in, void* out, int batch, int height, int width
  *                   out bf16 [n_masks,256]; workspace = llmseg_maskpool_workspace(n_masks) bytes.
  *   small_attention 32-dim heads among <=128 mask tokens (self-attention) or from the single
  *                   text token to the masks; q rows q_off[b]..q_off[b+1], kv rows kv_off[b]..
- *   select          sim[b,k] = cos(text_b, feat_k), iou[b,k] = sigmoid(h_iou_k·w2+b2), first
- *                   argmax per image; outputs fp32 [batch,k_stride] (-inf / 0 padding), int32 [batch]
+ *   select          per conversation c of group g = conv_group[c] (NULL: identity, n_conv == n_groups; a
+ *                   group's conversations are contiguous): sim[c,k] = cos(text_c, feat_k) over the group's mask
+ *                   tokens (LISA.py:397-403, [C,K] per image); per group: iou[g,k] = sigmoid(h_iou_k·w2+b2),
+ *                   best[g] = first argmax_k of the group's FIRST conversation; conv_valid[c] < 0 (no [SEG] in
+ *                   that conversation; NULL: all valid) -> NaN row (and NaN iou / best -1 for a first
+ *                   conversation).  sim fp32 [n_conv,k_stride], iou fp32 [n_groups,k_stride] (-inf / 0
+ *                   padding), best int32 [n_groups]
  *   losses          align/IoU-regression (loss.py:50-94) → out2 = {kl, mse*50};
  *                   dice/BCE (loss.py:4-47) → out2 = {dice, bce}; workspace = 2*n_masks floats
  * ------------------------------------------------------------------------------------------ */
@@ -256,7 +261,8 @@ int llmseg_small_attention(const void* q, int ldq, const void* k, int ldk, const
                            void* out, int ldo, const int32_t* q_off, const int32_t* kv_off,
                            int batch, int heads, int head_dim, int max_kv, void* stream);
 int llmseg_select(const void* feat, const void* text, const void* h_iou, const void* w2,
-                  const void* b2, const int32_t* k_off, int batch, int k_stride, float* sim_out,
+                  const void* b2, const int32_t* k_off, int n_groups, int k_stride,
+                  const int32_t* conv_group, const int32_t* conv_valid, int n_conv, float* sim_out,
                   float* iou_out, int32_t* best, void* stream);
 int llmseg_align_iou_loss(const float* sim, const float* pred_iou, const float* gt_iou, int K,
                           float temperature, float* out2, void* stream);

@@ -87,7 +87,7 @@ def _declare(lib):
                                            c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                            c_int, c_void_p]
     lib.llmseg_select.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+                                  c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.llmseg_align_iou_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                           c_void_p]
     lib.llmseg_selector_losses.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,

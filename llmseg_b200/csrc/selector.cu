@@ -75,7 +75,7 @@ maskpool_adjoint_kernel(const bf16* __restrict__ segs, float* __restrict__ wt,
   }
 }
 
-// stage 2: out[k, c] = bf16( bf16(Σ_cell wt[k,cell]·E[img(k), cell, c]) / bf16(Σ_p w[k,p]) )
+// stage 2: out[k, c] = bf16( (Σ_cell wt[k,cell]·E[img(k), cell, c]) / (Σ_p w[k,p] + 1e-8) )
 // E is token-major [B, 4096, 256] bf16 (the SAM neck output in NHWC).  The 4096-cell contraction is
 // split 8 ways over blockIdx.y (512 cells each) into fp32 partials so 8x more blocks stream E;
 // stage 3 sums the partials in a fixed order (deterministic) and normalises.
@@ -120,7 +120,7 @@ maskpool_apply_kernel(const float* __restrict__ wt, const bf16* __restrict__ emb
     if (k0 + m < n_masks) partial[((size_t)blockIdx.y * n_masks + k0 + m) * 256 + c] = acc[m];
 }
 
-// stage 3: fixed-order sum of the 8 partials, bf16 rounding points of the reference, normalise
+// stage 3: fixed-order sum of the 8 partials, normalise (LISA.py:211-213), round once
 __global__ void __launch_bounds__(256)
 maskpool_final_kernel(const float* __restrict__ partial, const float* __restrict__ part_sum,
                       bf16* __restrict__ out, int n_masks) {
@@ -131,13 +131,12 @@ maskpool_final_kernel(const float* __restrict__ partial, const float* __restrict
     acc += partial[((size_t)i * n_masks + k) * 256 + c];
     s += part_sum[k * 8 + i];
   }
-  const float den = bf16_round(bf16_round(s) + 1e-8f);  // bf16 sum, +1e-8 vanishes in bf16
-  out[(size_t)k * 256 + c] = __float2bfloat16_rn(bf16_round(acc) / den);
+  out[(size_t)k * 256 + c] = __float2bfloat16_rn(acc / (s + 1e-8f));  // fp32 up to the one bf16 store
 }
 
 // ---------------------------------------------------------------------------------------------
 // small attention: per (image, head) block; queries q_off[b]..q_off[b+1], keys kv_off[b]..kv_off[b+1].
-// Rounding as the bf16 reference: attn=bf16(q·k) → bf16(attn/√d) → softmax→bf16 → bf16(attn·v).
+// fp32 arithmetic on the bf16 q/k/v (scores, softmax and P·V never round); one bf16 rounding at the store.
 // ---------------------------------------------------------------------------------------------
 constexpr int SA_MAX = 128;  // max keys per image
 constexpr int SA_HD = 32;
@@ -166,7 +165,7 @@ small_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ 
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
-      s = bf16_round(bf16_round(s) * inv_sqrt_d);
+      s *= inv_sqrt_d;
       mx = fmaxf(mx, s);
     }
     float den = 0.f;
@@ -174,7 +173,7 @@ small_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ 
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
-      s = bf16_round(bf16_round(s) * inv_sqrt_d);
+      s *= inv_sqrt_d;
       den += __expf(s - mx);
     }
     float o[SA_HD];
@@ -185,8 +184,8 @@ small_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ 
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < SA_HD; ++d) s = fmaf(qv[d], ks[j][d], s);
-      s = bf16_round(bf16_round(s) * inv_sqrt_d);
-      const float p = bf16_round(__expf(s - mx) * inv);
+      s *= inv_sqrt_d;
+      const float p = __expf(s - mx) * inv;
 #pragma unroll
       for (int d = 0; d < SA_HD; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
     }
@@ -198,19 +197,33 @@ small_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// select: one block per image, one warp per mask token (looping).
-//   iou[k]  = sigmoid(bf16(h_iou[k]·w2 + b2))                      h_iou = relu(W1·q+b1) [*,128]
-//   sim[k]  = bf16( (t/‖t‖) · (e_k/‖e_k‖) )  with bf16 norms / quotients like the reference
-//   best    = first argmax_k sim[k]  (torch.argmax tie-break)
-// outputs are fp32 copies of the bf16 values, padded to k_stride per image (-inf / 0 beyond K_b).
+// select: one block per CONVERSATION c of group g = conv_group[c] (identity when NULL), one warp per mask
+// token (looping).  The mask tokens of a group went through the selector blocks with the group's FIRST
+// conversation as their text key (reference LISA.py:359-391: `sam_segs_feature_list[b][0]`), and every
+// conversation of the group is scored against them (LISA.py:397-403: `pred_embeddings[b]` is [C,256]):
+//   sim[c,k] = (t_c/‖t_c‖) · (e_k/‖e_k‖)                         fp32 arithmetic on the bf16 inputs
+//   iou[g,k] = sigmoid(h_iou[k]·w2 + b2)                          h_iou = relu(W1·q+b1) [*,128]
+//   best[g]  = first argmax_k bf16(sim[c0(g),k])  (torch.argmax tie-break on the bf16 values the reference
+//              returns, training.py:627-629; c0 = first conversation of the group)
+// sim / iou leave in fp32, UNROUNDED: the bf16 `pred_similarity` / `pred_iou` the caller hands out are one
+// rounding of these.  (Round 1 mimicked the eager path's five bf16 rounding points here — norm, quotients,
+// dot, logit, sigmoid; tests/parity_bisect.py showed that chain alone cost up to 4e-3 on pred_iou against
+// the fp32 oracle with exact inputs, more than both encoders together.)
+// conv_valid[c] < 0 (the conversation holds no [SEG], its text row is meaningless): the row is NaN and, for a
+// first conversation, iou is NaN and best = -1 — a sentinel instead of plausible-looking numbers.
+// outputs are padded to k_stride (-inf / 0 beyond K_g).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 select_kernel(const bf16* __restrict__ feat, const bf16* __restrict__ text,
               const bf16* __restrict__ h_iou, const bf16* __restrict__ w2, const bf16* __restrict__ b2,
-              const int* __restrict__ k_off, float* __restrict__ sim_out, float* __restrict__ iou_out,
+              const int* __restrict__ k_off, const int* __restrict__ conv_group,
+              const int* __restrict__ conv_valid, float* __restrict__ sim_out, float* __restrict__ iou_out,
               int* __restrict__ best, int k_stride) {
-  const int b = blockIdx.x;
-  const int r0 = k_off[b], nk = k_off[b + 1] - r0;
+  const int c = blockIdx.x;
+  const int g = conv_group ? conv_group[c] : c;
+  const bool first = conv_group == nullptr || c == 0 || conv_group[c - 1] != g;
+  const bool valid = conv_valid == nullptr || conv_valid[c] >= 0;
+  const int r0 = k_off[g], nk = k_off[g + 1] - r0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float tn[256];
   __shared__ float sims[SA_MAX];
@@ -218,19 +231,20 @@ select_kernel(const bf16* __restrict__ feat, const bf16* __restrict__ text,
     float t[8], ss = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      t[i] = __bfloat162float(text[(size_t)b * 256 + lane * 8 + i]);
+      t[i] = __bfloat162float(text[(size_t)c * 256 + lane * 8 + i]);
       ss += t[i] * t[i];
     }
-    const float nrm = bf16_round(sqrtf(warp_sum(ss)));
+    const float inv = 1.f / sqrtf(warp_sum(ss));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tn[lane * 8 + i] = bf16_round(t[i] / nrm);
+    for (int i = 0; i < 8; ++i) tn[lane * 8 + i] = t[i] * inv;
   }
   __syncthreads();
+  const float qnan = __int_as_float(0x7fc00000);
   for (int kk = warp; kk < k_stride; kk += 8) {
     if (kk >= nk) {
       if (lane == 0) {
-        sim_out[(size_t)b * k_stride + kk] = -INFINITY;
-        iou_out[(size_t)b * k_stride + kk] = 0.f;
+        sim_out[(size_t)c * k_stride + kk] = -INFINITY;
+        if (first) iou_out[(size_t)g * k_stride + kk] = 0.f;
       }
       continue;
     }
@@ -241,30 +255,33 @@ select_kernel(const bf16* __restrict__ feat, const bf16* __restrict__ text,
       e[i] = __bfloat162float(feat[r * 256 + lane * 8 + i]);
       ss += e[i] * e[i];
     }
-    const float nrm = bf16_round(sqrtf(warp_sum(ss)));
+    const float inv = 1.f / sqrtf(warp_sum(ss));
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dot += tn[lane * 8 + i] * bf16_round(e[i] / nrm);
-    dot = bf16_round(warp_sum(dot));
-    float hi = 0.f;
+    for (int i = 0; i < 8; ++i) dot += tn[lane * 8 + i] * e[i];
+    dot = warp_sum(dot) * inv;
+    float io = 0.f;
+    if (first) {
+      float hi = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      hi += __bfloat162float(h_iou[r * 128 + lane * 4 + i]) * __bfloat162float(w2[lane * 4 + i]);
-    hi = bf16_round(warp_sum(hi) + __bfloat162float(b2[0]));
-    const float io = bf16_round(1.f / (1.f + __expf(-hi)));
+      for (int i = 0; i < 4; ++i)
+        hi += __bfloat162float(h_iou[r * 128 + lane * 4 + i]) * __bfloat162float(w2[lane * 4 + i]);
+      hi = warp_sum(hi) + __bfloat162float(b2[0]);
+      io = 1.f / (1.f + expf(-hi));
+    }
     if (lane == 0) {
-      sim_out[(size_t)b * k_stride + kk] = dot;
-      iou_out[(size_t)b * k_stride + kk] = io;
-      if (kk < SA_MAX) sims[kk] = dot;
+      sim_out[(size_t)c * k_stride + kk] = valid ? dot : qnan;
+      if (first) iou_out[(size_t)g * k_stride + kk] = valid ? io : qnan;
+      if (kk < SA_MAX) sims[kk] = bf16_round(dot);
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && first) {
     int bi = 0;
     float bv = -INFINITY;
     for (int i = 0; i < nk && i < SA_MAX; ++i)
       if (sims[i] > bv) { bv = sims[i]; bi = i; }
-    best[b] = nk > 0 ? bi : -1;
+    best[g] = (nk > 0 && valid) ? bi : -1;
   }
 }
 
@@ -550,16 +567,21 @@ extern "C" int llmseg_small_attention(const void* q, int ldq, const void* k, int
 }
 
 extern "C" int llmseg_select(const void* feat, const void* text, const void* h_iou, const void* w2,
-                             const void* b2, const int32_t* k_off, int batch, int k_stride,
+                             const void* b2, const int32_t* k_off, int n_groups, int k_stride,
+                             const int32_t* conv_group, const int32_t* conv_valid, int n_conv,
                              float* sim_out, float* iou_out, int32_t* best, void* stream) {
   if (int e = check_arch()) return e;
   LLMSEG_REQUIRE(feat && text && h_iou && w2 && b2 && k_off && sim_out && iou_out && best, LLMSEG_EARG,
                  "llmseg_select: null pointer");
-  LLMSEG_REQUIRE(batch > 0 && k_stride > 0 && k_stride <= SA_MAX, LLMSEG_ESHAPE,
-                 "llmseg_select: batch=%d k_stride=%d (<= %d)", batch, k_stride, SA_MAX);
-  select_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  LLMSEG_REQUIRE(n_groups > 0 && k_stride > 0 && k_stride <= SA_MAX, LLMSEG_ESHAPE,
+                 "llmseg_select: n_groups=%d k_stride=%d (<= %d)", n_groups, k_stride, SA_MAX);
+  LLMSEG_REQUIRE(conv_group ? n_conv >= n_groups : n_conv == n_groups, LLMSEG_ESHAPE,
+                 "llmseg_select: n_conv=%d for %d groups (%s conv_group)", n_conv, n_groups,
+                 conv_group ? "with" : "without");
+  select_kernel<<<n_conv, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(feat), static_cast<const bf16*>(text), static_cast<const bf16*>(h_iou),
-      static_cast<const bf16*>(w2), static_cast<const bf16*>(b2), k_off, sim_out, iou_out, best, k_stride);
+      static_cast<const bf16*>(w2), static_cast<const bf16*>(b2), k_off, conv_group, conv_valid, sim_out,
+      iou_out, best, k_stride);
   LLMSEG_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return 0;

@@ -24,10 +24,18 @@ import os
 
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
-# LayerNorm / RMSNorm in front of a projection is folded into that GEMM (ops.fold_norm + ops.norm_stats):
-# the norm pass over the residual stream becomes a statistics-only read.  LLMSEG_FOLD_NORM=0 keeps the
-# separate norm kernels (the reference's literal op order) for A/B runs.
-FOLD_NORM = os.environ.get("LLMSEG_FOLD_NORM", "1") != "0"
+# LayerNorm / RMSNorm in front of a projection can be folded into that GEMM (ops.fold_norm + ops.norm_stats):
+# the norm pass over the residual stream becomes a statistics-only read.  LLMSEG_FOLD_NORM selects where:
+#   "image" (default)  SAM / DINOv2 only      "all" / "1"  every encoder      "0"  nowhere (the reference's literal op order)
+# Why not everywhere: folding moves a bf16 rounding from the normalised ACTIVATIONS (independent per token, averaged
+# away by attention) to the gamma-scaled WEIGHTS (the same perturbation for every token, so it adds up coherently).
+# tests/parity_bisect.py (profiles/round2_parity_bisect.md): with the text branch folded, its contribution to the
+# |pred_similarity - fp32 oracle| error is 3x larger (1.2e-3 vs 0.4e-3 mean) — the level of the reference's own bf16
+# path — while the image branch's contribution is negligible either way (2e-4), and the image branch is where the
+# norm passes cost time (64 x [32768, 1280] at batch 8 vs 64 x [2552, 4096]).
+_FOLD = os.environ.get("LLMSEG_FOLD_NORM", "image").lower()
+FOLD_NORM_IMAGE = _FOLD in ("image", "all", "1")
+FOLD_NORM_TEXT = _FOLD in ("all", "1")
 # Row-restricted tail of the last LLaMA layer (exact: row-wise ops commute with the [SEG] gather).  Off by default:
 # measured no gain at batch 8 (80.30 vs 80.33 ms/step, profiles/r02b) — the M=8 GEMMs stream the same 300 MB of
 # weights — and it moves bf16 rounding points (the statistics come from the bf16 rows instead of the fp32 epilogue).
@@ -78,6 +86,7 @@ class _Scratch:
 class SamEncoder:
     def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = ""):
         self.cfg, self.device = cfg, device
+        self.fold = FOLD_NORM_IMAGE
         D = cfg.embed_dim
         self.heads, self.hd = cfg.num_heads, cfg.embed_dim // cfg.num_heads
         if self.hd != 80:
@@ -103,7 +112,7 @@ class SamEncoder:
                 w1=d(bp + "mlp.lin1.weight"), b1=d(bp + "mlp.lin1.bias"),
                 w2=d(bp + "mlp.lin2.weight"), b2=d(bp + "mlp.lin2.bias"),
             )
-            if FOLD_NORM:
+            if self.fold:
                 blk["f_qkv"] = ops.fold_norm(blk["w_qkv"], blk["ln1_w"], blk["ln1_b"], blk["b_qkv"])
                 blk["f_1"] = ops.fold_norm(blk["w1"], blk["ln2_w"], blk["ln2_b"], blk["b1"])
                 # the padding keys/values of a window are the projection of a zero token = the bias, in bf16
@@ -155,8 +164,8 @@ class SamEncoder:
         a = ops.patchify(images.contiguous(), cfg.patch_size, 3 * cfg.patch_size ** 2)
         # stA / stB: per-row (sum, sum of squares) partials of the residual stream, written by the epilogue of
         # whichever GEMM produced it (patch embed / lin2 -> stA for norm1, proj -> stB for norm2)
-        stA = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "a") if FOLD_NORM else None
-        stB = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "b") if FOLD_NORM else None
+        stA = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "a") if self.fold else None
+        stB = self.scratch.gemm_stats(B * S, D, cfg.ln_eps, "b") if self.fold else None
         x = ops.gemm(a, self.w_patch, self.b_patch, residual=self.pos, res_mod=S, stats_out=stA)
         del a
         win_map, n_win, tok2win, pad_wins = self._window_maps(B)
@@ -181,7 +190,7 @@ class SamEncoder:
                 k = self.scratch.zeros("k" + tag, nb * H, sw_pad, hd)
                 vt = self.scratch.zeros("vt" + tag, nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
-                if FOLD_NORM:
+                if self.fold:
                     wq, bq = blk["f_qkv"]
                     ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad,
                                  row_map=tok2win, row_stats=stA)
@@ -207,7 +216,7 @@ class SamEncoder:
                 vt = self.scratch.zeros("vtg", B * H, hd, S)
                 qext = self.scratch.zeros("qext_g", B * H, S, 64)
                 rb = self.scratch.zeros("rb_g", B * H, S, 64)
-                if FOLD_NORM:
+                if self.fold:
                     wq, bq = blk["f_qkv"]
                     ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S, row_stats=stA)
                     o = self.scratch.zeros("o", B * S, D)
@@ -220,7 +229,7 @@ class SamEncoder:
                 ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale,
                               qext=qext, kext=self.kext_glb, row_bias=rb, ext_cols=64)
                 ops.gemm(o, blk["w_proj"], blk["b_proj"], residual=x, out=x, stats_out=stB)
-            if FOLD_NORM:
+            if self.fold:
                 w1, b1 = blk["f_1"]
                 m = ops.gemm(x, w1, b1, act="gelu", row_stats=stB)
             else:
@@ -274,6 +283,7 @@ class Dinov2Encoder:
 
     def __init__(self, sd: Dict[str, Tensor], cfg, device, conv_w: Tensor, conv_b: Tensor, prefix: str = ""):
         self.cfg, self.device = cfg, device
+        self.fold = FOLD_NORM_IMAGE
         D, p = cfg.embed_dim, cfg.patch_size
         self.heads, self.hd = cfg.num_heads, cfg.embed_dim // cfg.num_heads
         if self.hd != 64:
@@ -300,7 +310,7 @@ class Dinov2Encoder:
                      w1=d(bp + "mlp.fc1.weight"), b1=d(bp + "mlp.fc1.bias"))
             L["w_o"], L["b_o"] = scaled(bp + "attn.proj", ls1)
             L["w2"], L["b2"] = scaled(bp + "mlp.fc2", ls2)
-            if FOLD_NORM:
+            if self.fold:
                 L["f_qkv"] = ops.fold_norm(L["w_qkv"], L["ln1"][0], L["ln1"][1], L["b_qkv"])
                 L["f_1"] = ops.fold_norm(L["w1"], L["ln2"][0], L["ln2"][1], L["b1"])
                 del L["w_qkv"], L["w1"]
@@ -308,7 +318,7 @@ class Dinov2Encoder:
         self.norm = (d("norm.weight"), d("norm.bias"))
         self.w_conv = _dev(conv_w, device).reshape(conv_w.shape[0], D).contiguous()
         self.b_conv = _dev(conv_b, device)
-        if FOLD_NORM:
+        if self.fold:
             self.f_conv = ops.fold_norm(self.w_conv, self.norm[0], self.norm[1], self.b_conv)
         self.scratch = _Scratch(device)
         self._drop_cls: Dict[int, Tensor] = {}
@@ -335,15 +345,15 @@ class Dinov2Encoder:
             raise ValueError(f"DINOv2 encoder is laid out for {cfg.img_size}x{cfg.img_size} images, got {tuple(images.shape)}")
         T_pad = (T + 7) // 8 * 8
         a = ops.patchify(images.contiguous(), cfg.patch_size, self.k_pad, cls_rows=1)
-        stA = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "a") if FOLD_NORM else None
-        stB = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "b") if FOLD_NORM else None
+        stA = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "a") if self.fold else None
+        stB = self.scratch.gemm_stats(B * T, D, cfg.ln_eps, "b") if self.fold else None
         x = ops.gemm(a, self.w_patch, None, residual=self.pos, res_mod=T, stats_out=stA)
         del a
         q = self.scratch.zeros("q", B * H, T_pad, hd)
         k = self.scratch.zeros("k", B * H, T_pad, hd)
         vt = self.scratch.zeros("vt", B * H, hd, T_pad)
         for L in self.layers:
-            if FOLD_NORM:
+            if self.fold:
                 wq, bq = L["f_qkv"]
                 ops.gemm_qkv(x, wq, bq, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad, row_stats=stA)
                 h = self.scratch.zeros("o", B * T, D)
@@ -352,7 +362,7 @@ class Dinov2Encoder:
                 ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
             ops.attention(q, k, vt, h, batch=B, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
             ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x, stats_out=stB)
-            if FOLD_NORM:
+            if self.fold:
                 w1, b1 = L["f_1"]
                 m = ops.gemm(x, w1, b1, act="gelu", row_stats=stB)
             else:
@@ -372,7 +382,7 @@ class Dinov2Encoder:
     def forward(self, images: Tensor) -> Tensor:
         """[B,3,S,S] bf16 -> token-major `lisa_dino_conv` output [B, g*g, out_chans] bf16 (NHWC)."""
         x, stA, B, T = self._blocks(images)
-        if FOLD_NORM:
+        if self.fold:
             w, b = self.f_conv
             y = ops.gemm(x, w, b, row_stats=stA, out_row_map=self._drop_cls_map(B), out_rows=B * (T - 1))
         else:
@@ -388,6 +398,7 @@ class ClipTower:
     def __init__(self, sd: Dict[str, Tensor], cfg, device, proj_w: Tensor, proj_b: Tensor,
                  prefix: str = "vision_model."):
         self.cfg, self.device = cfg, device
+        self.fold = FOLD_NORM_TEXT
         D, p = cfg.hidden, cfg.patch_size
         self.heads, self.hd = cfg.heads, cfg.hidden // cfg.heads
         if self.hd != 64:
@@ -414,7 +425,7 @@ class ClipTower:
                 w1=d(lp + "mlp.fc1.weight"), b1=d(lp + "mlp.fc1.bias"),
                 w2=d(lp + "mlp.fc2.weight"), b2=d(lp + "mlp.fc2.bias"),
             )
-            if FOLD_NORM:
+            if self.fold:
                 L["f_qkv"] = ops.fold_norm(L["w_qkv"], L["ln1"][0], L["ln1"][1], L["b_qkv"])
                 L["f_1"] = ops.fold_norm(L["w1"], L["ln2"][0], L["ln2"][1], L["b1"])
                 del L["w_qkv"], L["w1"]
@@ -444,10 +455,10 @@ class ClipTower:
         q = self.scratch.zeros("q", N * H, T_pad, hd)
         k = self.scratch.zeros("k", N * H, T_pad, hd)
         vt = self.scratch.zeros("vt", N * H, hd, T_pad)
-        stB = self.scratch.gemm_stats(N * T, D, cfg.eps, "b") if FOLD_NORM else None
+        stB = self.scratch.gemm_stats(N * T, D, cfg.eps, "b") if self.fold else None
         st = None
         for L in self.layers:
-            if FOLD_NORM:
+            if self.fold:
                 if st is None:  # first layer: x comes out of pre_layrnorm, not out of a GEMM
                     st = ops.norm_stats(x, cfg.eps, out=self.scratch.stats(N * T, 1, "n"))
                 wq, bq = L["f_qkv"]
@@ -458,7 +469,7 @@ class ClipTower:
                 ops.gemm_qkv(h, L["w_qkv"], L["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad)
             ops.attention(q, k, vt, h, batch=N, heads=H, head_dim=hd, seq=T, seq_pad=T_pad, scale=hd ** -0.5)
             ops.gemm(h, L["w_o"], L["b_o"], residual=x, out=x, stats_out=stB)
-            if FOLD_NORM:
+            if self.fold:
                 w1, b1 = L["f_1"]
                 m = ops.gemm(x, w1, b1, act="quick_gelu", row_stats=stB)
                 st = self.scratch.gemm_stats(N * T, D, cfg.eps, "a")
@@ -477,6 +488,7 @@ class LlamaDecoder:
     def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = "", max_seq: int = 1024,
                  lm_head: Optional[Tensor] = None):
         self.cfg, self.device = cfg, device
+        self.fold = FOLD_NORM_TEXT
         if cfg.head_dim != 128:
             raise ValueError(f"LLaMA attention kernel is instantiated for head_dim 128, got {cfg.head_dim}")
         d = lambda k: _dev(sd[prefix + k], device)
@@ -495,7 +507,7 @@ class LlamaDecoder:
                 w_down=d(lp + "mlp.down_proj.weight"),
             )
             del gate, up
-            if FOLD_NORM:  # RMSNorm: gamma folds into the weight, rstd is applied per row in the epilogue
+            if self.fold:  # RMSNorm: gamma folds into the weight, rstd is applied per row in the epilogue
                 L["w_qkv"] = ops.fold_norm(L["w_qkv"], L["rms1"], rms=True)[0]
                 L["w_gu"] = ops.fold_norm(L["w_gu"], L["rms2"], rms=True)[0]
             self.layers.append(L)
@@ -506,7 +518,7 @@ class LlamaDecoder:
             v_pad = (lm_head.shape[0] + 7) // 8 * 8
             w = torch.zeros(v_pad, cfg.hidden, dtype=BF16, device=device)
             w[:lm_head.shape[0]] = _dev(lm_head, device)
-            self.w_lm = ops.fold_norm(w, self.norm, rms=True)[0] if FOLD_NORM else w
+            self.w_lm = ops.fold_norm(w, self.norm, rms=True)[0] if self.fold else w
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.float32) / cfg.head_dim))
         fr = torch.outer(torch.arange(max_seq, dtype=torch.float32), inv)
         self.rope_cos = fr.cos().to(BF16).to(device).contiguous()
@@ -532,10 +544,10 @@ class LlamaDecoder:
         vt = self.scratch.zeros("vt", n_seq * H, hd, T_pad)
         x = embeds
         scale = 1.0 / math.sqrt(hd)
-        stB = self.scratch.gemm_stats(n_seq * T, cfg.hidden, cfg.eps, "b", rms=True) if FOLD_NORM else None
+        stB = self.scratch.gemm_stats(n_seq * T, cfg.hidden, cfg.eps, "b", rms=True) if self.fold else None
         st = None
         for L in self.layers:
-            if FOLD_NORM:
+            if self.fold:
                 if st is None:  # first layer: x is the spliced embedding sequence, not a GEMM output
                     st = ops.norm_stats(x, cfg.eps, rms=True, out=self.scratch.stats(n_seq * T, 1, "n"))
                 ops.gemm_qkv(x, L["w_qkv"], None, q, k, vt, heads=H, head_dim=hd, seq_in=T, seq_pad=T_pad,
@@ -553,14 +565,14 @@ class LlamaDecoder:
                 # gathered rows alone.  Keys/values of the last layer still cover every position.
                 xr = ops.gather_rows(x, out_rows)
                 xr = ops.gemm(ops.gather_rows(h, out_rows), L["w_o"], None, residual=xr)
-                if FOLD_NORM:
+                if self.fold:
                     m = ops.gemm(xr, L["w_gu"], None, swiglu=True, row_stats=ops.norm_stats(xr, cfg.eps, rms=True))
                 else:
                     m = ops.gemm(ops.rmsnorm(xr, L["rms2"], cfg.eps), L["w_gu"], None, swiglu=True)
                 xr = ops.gemm(m, L["w_down"], None, residual=xr)
                 return ops.rmsnorm(xr, self.norm, cfg.eps)
             ops.gemm(h, L["w_o"], None, residual=x, out=x, stats_out=stB)
-            if FOLD_NORM:
+            if self.fold:
                 m = ops.gemm(x, L["w_gu"], None, swiglu=True, row_stats=stB)
                 st = self.scratch.gemm_stats(n_seq * T, cfg.hidden, cfg.eps, "a", rms=True)
             else:
@@ -573,7 +585,7 @@ class LlamaDecoder:
             hidden = ops.rmsnorm(x, self.norm, cfg.eps)
         if not with_logits:
             return hidden
-        if FOLD_NORM and st is not None:
+        if self.fold and st is not None:
             logits = ops.gemm(x, self.w_lm, None, row_stats=st)
         else:
             logits = ops.gemm(hidden if out_rows is None else ops.rmsnorm(x, self.norm, cfg.eps), self.w_lm, None)

@@ -321,7 +321,8 @@ def patchify(images: torch.Tensor, patch: int, k_pad: int, cls_rows: int = 0) ->
 
 
 def embed_splice(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], embed: torch.Tensor,
-                 feats: torch.Tensor, *, image_token: int, seg_token: int):
+                 feats: torch.Tensor, *, image_token: int, seg_token: int,
+                 seg_row_out: Optional[torch.Tensor] = None):
     """-> (embeds [N*T, D] bf16, kv_len int32 [N], seg_row int32 [N]) with T = T_text + F - 1."""
     _req_bf16(embed, feats)
     assert input_ids.dtype == torch.int64 and input_ids.is_cuda and input_ids.is_contiguous()
@@ -333,7 +334,8 @@ def embed_splice(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor]
         m = attention_mask.to(torch.uint8).contiguous()
     out = torch.empty((N * T, D), dtype=torch.bfloat16, device=embed.device)
     kv_len = torch.empty(N, dtype=torch.int32, device=embed.device)
-    seg_row = torch.empty(N, dtype=torch.int32, device=embed.device)
+    seg_row = seg_row_out if seg_row_out is not None else torch.empty(N, dtype=torch.int32, device=embed.device)
+    assert seg_row.dtype == torch.int32 and seg_row.numel() == N and seg_row.is_cuda
     check(_lib.lib().llmseg_embed_splice(input_ids.data_ptr(), _ptr(m), embed.data_ptr(), feats.data_ptr(),
                                          out.data_ptr(), kv_len.data_ptr(), seg_row.data_ptr(), N, Tt, F_,
                                          D, image_token, seg_token, embed.shape[0], _stream()),
@@ -396,15 +398,24 @@ def small_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_off: to
 
 
 def select(feat: torch.Tensor, text: torch.Tensor, h_iou: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
-           k_off: torch.Tensor, *, batch: int, k_stride: int):
+           k_off: torch.Tensor, *, batch: int, k_stride: int, conv_group: Optional[torch.Tensor] = None,
+           conv_valid: Optional[torch.Tensor] = None):
+    """text [n_conv,256]: one row per conversation; conv_group int32 [n_conv] maps a conversation to its group
+    of mask tokens (None: n_conv == batch, identity); conv_valid int32 [n_conv] (< 0: no [SEG], NaN sentinel).
+    -> (sim fp32 [n_conv,k_stride], iou fp32 [batch,k_stride], best int32 [batch])."""
     _req_bf16(feat, text, h_iou, w2, b2)
     dev = feat.device
-    sim = torch.empty((batch, k_stride), dtype=torch.float32, device=dev)
+    n_conv = text.shape[0]
+    for t in (conv_group, conv_valid):
+        if t is not None and not (t.is_cuda and t.dtype == torch.int32 and t.numel() == n_conv):
+            raise ValueError("conv_group / conv_valid must be int32 [n_conv] on the GPU")
+    sim = torch.empty((n_conv, k_stride), dtype=torch.float32, device=dev)
     iou = torch.empty((batch, k_stride), dtype=torch.float32, device=dev)
     best = torch.empty(batch, dtype=torch.int32, device=dev)
     check(_lib.lib().llmseg_select(feat.data_ptr(), text.data_ptr(), h_iou.data_ptr(), w2.data_ptr(),
-                                   b2.data_ptr(), k_off.data_ptr(), batch, k_stride, sim.data_ptr(),
-                                   iou.data_ptr(), best.data_ptr(), _stream()), "select")
+                                   b2.data_ptr(), k_off.data_ptr(), batch, k_stride, _ptr(conv_group),
+                                   _ptr(conv_valid), n_conv, sim.data_ptr(), iou.data_ptr(), best.data_ptr(),
+                                   _stream()), "select")
     return sim, iou, best
 
 

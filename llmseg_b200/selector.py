@@ -56,42 +56,65 @@ class Selector:
         self.w_e1, self.b_e1 = d("lisa_embedding_head.0.weight"), d("lisa_embedding_head.0.bias")
         self.w_e2, self.b_e2 = d("lisa_embedding_head.2.weight"), d("lisa_embedding_head.2.bias")
 
-    def text_embed(self, hidden_rows: Tensor) -> Tensor:
+    def text_embed(self, hidden_rows: Tensor, out: Tensor = None) -> Tensor:
         """text_hidden_fcs on the gathered rows (reference LISA.py:56-65,317-337)."""
         t = ops.gemm(hidden_rows, self.fc0[0], self.fc0[1], act="relu")
-        return ops.gemm(t, self.fc2[0], self.fc2[1])
+        return ops.gemm(t, self.fc2[0], self.fc2[1], out=out)
 
-    def make_plan(self, Ks) -> dict:
-        """Device-side index tensors for a batch with Ks[i] proposals per image (built once per shape,
-        outside any CUDA-graph capture)."""
+    def make_plan(self, Ks, k_cap: int = 0) -> dict:
+        """Device-side index tensors for a batch with Ks[i] proposals per image (built outside any CUDA-graph
+        capture).  With k_cap > 0 the plan is sized for UP TO k_cap proposals per image (rows = B * k_cap, the
+        proposals stay concatenated at the front) and `update_plan` re-targets it to other counts in place, so a
+        captured graph serves every call of its (B, k_cap) bucket."""
         Ks = [int(k) for k in Ks]
-        kmax = max(Ks)
-        if kmax > 128:
-            raise ValueError(f"selector kernels support at most 128 proposals per image, got {kmax}")
         dev, B = self.device, len(Ks)
+        if B == 0:
+            raise ValueError("selector plan needs at least one image")
+        kmax = k_cap if k_cap > 0 else max(Ks)
+        if kmax > 128 or max(Ks) > kmax:
+            raise ValueError(f"selector kernels support at most 128 proposals per image, got {max(max(Ks), kmax)}")
+        rows = B * k_cap if k_cap > 0 else sum(Ks)
+        plan = {
+            "Ks": None, "kmax": kmax, "B": B, "rows": rows,
+            "k_off": torch.zeros(B + 1, dtype=torch.int32, device=dev),
+            "b_off": torch.arange(B + 1, dtype=torch.int32, device=dev),
+            "mask_image": torch.zeros(max(rows, 1), dtype=torch.int32, device=dev),
+        }
+        return self.update_plan(plan, Ks)
+
+    def update_plan(self, plan: dict, Ks) -> dict:
+        Ks = [int(k) for k in Ks]
+        if plan["Ks"] == Ks:
+            return plan
+        if len(Ks) != plan["B"] or min(Ks) < 1 or max(Ks) > plan["kmax"] or sum(Ks) > plan["rows"]:
+            raise ValueError(f"proposal counts {Ks} do not fit the selector plan (B={plan['B']}, K<={plan['kmax']})")
         offs = [0]
         for kk in Ks:
             offs.append(offs[-1] + kk)
-        return {
-            "Ks": Ks, "kmax": kmax, "B": B,
-            "k_off": torch.tensor(offs, dtype=torch.int32, device=dev),
-            "b_off": torch.arange(B + 1, dtype=torch.int32, device=dev),
-            "mask_image": torch.repeat_interleave(torch.arange(B, dtype=torch.int32, device=dev),
-                                                  torch.tensor(Ks, device=dev)).contiguous(),
-        }
+        img = torch.repeat_interleave(torch.arange(len(Ks), dtype=torch.int32), torch.tensor(Ks))
+        # rows beyond the last proposal (capacity padding) point at the last image: they are computed and ignored
+        pad = torch.full((plan["rows"] - offs[-1],), len(Ks) - 1, dtype=torch.int32)
+        plan["k_off"].copy_(torch.tensor(offs, dtype=torch.int32))
+        plan["mask_image"][:plan["rows"]].copy_(torch.cat([img, pad]))
+        plan["Ks"] = Ks
+        return plan
 
-    def forward(self, emb_tokens: Tensor, seg_cat: Tensor, text_embed: Tensor, plan: dict):
-        """emb_tokens [B,4096,256]; seg_cat [ΣK_i,256,256] bf16 (proposals of all images, concatenated);
+    def forward(self, emb_tokens: Tensor, seg_cat: Tensor, text_embed: Tensor, plan: dict, **conv):
+        """emb_tokens [B,4096,256]; seg_cat [rows,256,256] bf16 (proposals of all images, concatenated);
         text_embed [B,256] (conversation 0 of each image); plan from make_plan.
-        -> (sim fp32 [B,Kmax], iou fp32 [B,Kmax], best int32 [B])."""
+        -> (sim fp32 [n_conv,Kmax], iou fp32 [B,Kmax], best int32 [B])."""
         feat = ops.maskpool(seg_cat.contiguous(), emb_tokens.contiguous(), plan["mask_image"])
-        return self.forward_pooled(feat, text_embed, plan)
+        return self.forward_pooled(feat, text_embed, plan, **conv)
 
-    def forward_pooled(self, feat: Tensor, text_embed: Tensor, plan: dict):
+    def forward_pooled(self, feat: Tensor, text_embed: Tensor, plan: dict, *, text_all: Tensor = None,
+                       conv_group: Tensor = None, conv_valid: Tensor = None):
         """The selector after mask pooling, over G groups of mask tokens (plan = make_plan(K per group)):
-        feat [ΣK_g,256] pooled proposal features, text_embed [G,256].  At inference a group is an image; in the
+        feat [rows,256] pooled proposal features, text_embed [G,256].  At inference a group is an image; in the
         training forward it is an (image, round) pair sharing its image's pooled features (the reference expands
-        them per conversation, LISA.py:372-375)."""
+        them per conversation, LISA.py:372-375).
+        text_all [n_conv,256] + conv_group int32 [n_conv]: every conversation of a group is scored against the
+        group's mask embeddings (LISA.py:397-403 — they were updated with the group's first conversation,
+        `sam_segs_feature_list[b][0]`); default: one conversation per group."""
         B, kmax = plan["B"], plan["kmax"]
         k_off, b_off, mask_image = plan["k_off"], plan["b_off"], plan["mask_image"]
         text = text_embed
@@ -113,4 +136,5 @@ class Selector:
         feat = ln(ops.add_rows_bcast(feat, to, row_group=mask_image), self.n_fin)
         h_iou = ops.gemm(feat, self.w_i1, self.b_i1, act="relu")
         e = ops.gemm(ops.gemm(feat, self.w_e1, self.b_e1, act="relu"), self.w_e2, self.b_e2)
-        return ops.select(e, text_embed, h_iou, self.w_i2, self.b_i2, k_off, batch=B, k_stride=kmax)
+        return ops.select(e, text_embed if text_all is None else text_all, h_iou, self.w_i2, self.b_i2, k_off,
+                          batch=B, k_stride=kmax, conv_group=conv_group, conv_valid=conv_valid)

@@ -180,10 +180,14 @@ def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda", with_lm_head: bo
     return sd
 
 
-def make_proposals(K: int, gen: torch.Generator, device) -> Tensor:
+def make_proposals(K: int, gen: torch.Generator, device, area_range: Tuple[float, float] = (0.01, 0.4)) -> Tensor:
     """K structured soft masks [K,256,256] in [0,1]: axis-aligned rectangles with log-uniform area in
-    [1%, 40%], blurred by a 3x3 box (mimics the antialiased resize of reference utils/dataset.py:620-622)."""
-    area = torch.exp(torch.empty(K, device=device).uniform_(-4.605, -0.916, generator=gen))  # ln(0.01)..ln(0.4)
+    `area_range` (fraction of the image; default [1%, 40%]), blurred by a 3x3 box (mimics the antialiased resize of
+    reference utils/dataset.py:620-622).  Small proposals (a few cells of the 64x64 feature grid) pool very
+    different features each, which spreads the similarities: the margin-qualified index tests use them."""
+    import math
+    lo, hi = math.log(area_range[0]), math.log(area_range[1])
+    area = torch.exp(torch.empty(K, device=device).uniform_(lo, hi, generator=gen))
     aspect = torch.exp(torch.empty(K, device=device).uniform_(-0.7, 0.7, generator=gen))
     h = (area * aspect).sqrt().clamp(max=1.0) * 256
     w = (area / aspect).sqrt().clamp(max=1.0) * 256
@@ -196,7 +200,8 @@ def make_proposals(K: int, gen: torch.Generator, device) -> Tensor:
     return m.to(BF16)
 
 
-def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int = 1234, device="cuda") -> dict:
+def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int = 1234, device="cuda",
+                area_range: Tuple[float, float] = (0.01, 0.4)) -> dict:
     """ReasonSeg-shaped synthetic `input_dict` (keys of reference utils/dataset.py:150-170 that the
     forward reads).  Token layout per SURVEY §8d: [bos, .., <im_start>, IMAGE, <im_end>, text.., [SEG], '.', eos]."""
     assert t_text >= 8
@@ -217,7 +222,7 @@ def make_inputs(cfg: LisaCfg, batch: int, n_props: int, t_text: int, seed: int =
         "attention_masks": torch.ones(batch, t_text, dtype=torch.bool, device=dev),
         "offset": torch.arange(batch + 1), "masks_list": [None] * batch, "label_list": [None] * batch,
         "resize_list": [(S, S)] * batch,
-        "sam_segs_list": [make_proposals(n_props, g, dev) for _ in range(batch)],
+        "sam_segs_list": [make_proposals(n_props, g, dev, area_range) for _ in range(batch)],
         "sam_ious_list": None, "sam_iops_list": None, "inference": True,
     }
 
