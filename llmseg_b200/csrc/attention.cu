@@ -442,79 +442,93 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
 }
 
 // =============================================================================================
-// v2: two 128-query tiles per CTA ("ping-pong"), one CTA per SM.
+// v3: 64-key score tiles DOUBLE-BUFFERED in TMEM.
 //
-// The v1 kernel above serialises  S -> softmax -> PV -> next S  inside a CTA and relies on two
-// co-resident CTAs to overlap; ncu (profiles/r01a..r01f) shows its softmax warps parked on the S
-// barrier for ~40 % of their time and the tensor pipe ~37 % active.  Here one MMA-issuing thread
-// interleaves the two query tiles
-//        ... PV0(j)  S0(j+1)  PV1(j)  S1(j+1)  PV0(j+1) ...
-// so that while softmax group g works on S_g(j) the tensor core runs the other tile's MMAs, and a
-// group's next score tile is already being computed when its P is consumed.  K/V tiles are
-// double-buffered and shared by both query tiles (half the K/V smem traffic per query row).
-//   TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,256+HD)  O1 [384,384+HD)
-//   warps: 0 TMA producer, 1 MMA issuer + TMEM alloc, 2..9 softmax group 0, 10..17 softmax group 1
+// v1 above serialises  S(j) -> softmax(j) -> PV(j) -> S(j+1)  inside a CTA (one score buffer) and leans on the
+// second CTA of the SM for overlap: ncu (profiles/r02_summary.md, r02o) had the tensor pipe 53 % and the MUFU
+// 61 % active, 21.7 % of all samples softmax warps waiting for their next score tile and the MMA warp waiting
+// for P 61 % of its time.  Here a CTA keeps TWO score buffers of 64 keys (TMEM columns [0,64) and [64,128),
+// O behind them: 128 + HD <= 256 columns, so two CTAs still share an SM) and the MMA warp runs one tile ahead:
+//
+//        S(0)  S(1) PV(0)  S(2) PV(1)  S(3) PV(2) ...
+//
+// S(j+1) is computed under softmax(j), so the softmax warps — the MUFU / TMEM-read side, which bounds this
+// kernel at ~1024 clk per 128x128 scores against 896 clk of MMAs at head_dim 80 — go from one tile straight to
+// the next.  tcgen05.mma executes in issue order, so S(j+2) overwriting the buffer P(j) was read from needs no
+// barrier; PV(j-1) may still be in flight when softmax(j) starts, so the (rare) O rescale waits for it.
+//   warp 0      TMA producer: Q (+qext, kext) once, then K(j) / V^T(j) through a 2-3 stage ring
+//   warp 1      TMEM allocator + MMA issuer (one elected lane, warp-uniform loop)
+//   warps 2..5  softmax: thread = one query row x the tile's 64 keys (no cross-warp exchange, no named
+//               barrier); single pass over S against the running max, lazy O rescale (max grew by > 2^8)
 // =============================================================================================
+constexpr int BN3 = 64;
+
 template <int HD, int EXT>
-struct ACfg2 {
-  static constexpr int Q0_BYTES = 128 * 128;
+struct A3Cfg {
+  static constexpr int Q0_BYTES = 128 * 128;                                     // [128 x 64] SW128
   static constexpr int Q1_BYTES = HD == 80 ? 128 * 32 : (HD == 128 ? 128 * 128 : 0);
   static constexpr int QX_BYTES = EXT == 1 ? 128 * 64 : (EXT == 2 ? 128 * 128 : 0);
-  static constexpr int QT_BYTES = Q0_BYTES + Q1_BYTES + QX_BYTES;  // one query tile (+ its ext columns)
-  static constexpr int E_BYTES = EXT ? 16384 : 0;
-  static constexpr int K_BYTES = Q0_BYTES + Q1_BYTES;
-  static constexpr int V_CHUNK = HD * 128;
-  static constexpr int V_BYTES = 2 * V_CHUNK;
-  static constexpr int OFF_Q = 0;                        // 2 query tiles
-  static constexpr int OFF_E = OFF_Q + 2 * QT_BYTES;
-  static constexpr int OFF_K = OFF_E + E_BYTES;          // 2 stages
-  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;      // 2 stages
-  static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
-  static constexpr int OFF_XCH = OFF_BAR + 256;          // per group: float[2][2][128] + float[2][128]
-  static constexpr int SMEM_BYTES = OFF_XCH + 2 * 3072 + 1024;
-  static constexpr int Q_TX = 2 * QT_BYTES + E_BYTES;
-  static constexpr int TMEM_COLS = 512;
+  static constexpr int E_BYTES = EXT == 1 ? 256 * 64 : (EXT == 2 ? 64 * 128 : 0);  // EXT1: [256 x 32] SW64; EXT2: [64 x 64] SW128
+  static constexpr int K0_BYTES = BN3 * 128;                                     // [64 x 64] SW128
+  static constexpr int K1_BYTES = HD == 80 ? BN3 * 32 : (HD == 128 ? BN3 * 128 : 0);
+  static constexpr int V_BYTES = HD * 128;                                       // [HD x 64 keys] SW128
+  static constexpr int STAGE_BYTES = K0_BYTES + K1_BYTES + V_BYTES;
+  static constexpr int STAGES = HD == 128 ? 2 : 3;
+  static constexpr int OFF_Q0 = 0;
+  static constexpr int OFF_Q1 = OFF_Q0 + Q0_BYTES;
+  static constexpr int OFF_QX = OFF_Q1 + Q1_BYTES;
+  static constexpr int OFF_E = OFF_QX + QX_BYTES;
+  static constexpr int OFF_ST = OFF_E + E_BYTES;
+  static constexpr int OFF_BAR = OFF_ST + STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int Q_TX = Q0_BYTES + Q1_BYTES + QX_BYTES + E_BYTES;
+  static constexpr int K_TX = K0_BYTES + K1_BYTES;
+  static constexpr int V_TX = V_BYTES;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int O_COL = 128;
+  static_assert(OFF_ST % 1024 == 0 && STAGE_BYTES % 1024 == 0 && (K0_BYTES + K1_BYTES) % 1024 == 0, "swizzle atoms");
+  static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
 };
 
 template <int HD, int EXT>
-__global__ void __launch_bounds__(576, 1)
-attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+__global__ void __launch_bounds__(192, 2)
+attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
              const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
              const __grid_constant__ CUtensorMap tmE, const AttnDev p) {
-  using C = ACfg2<HD, EXT>;
+  using C = A3Cfg<HD, EXT>;
+  constexpr int ST = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* bar_q = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* bar_s = bars + 9;     // [2] per softmax group
-  uint64_t* bar_p = bars + 11;    // [2] per softmax group
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_full = bars + 1;          // [ST]
+  uint64_t* k_empty = bars + 1 + ST;    // [ST]
+  uint64_t* v_full = bars + 1 + 2 * ST; // [ST]
+  uint64_t* v_empty = bars + 1 + 3 * ST;
+  uint64_t* bar_s = bars + 1 + 4 * ST;  // [2] score buffer (j & 1) holds S(j)
+  uint64_t* bar_p = bar_s + 2;          // [2] P(j) written over it (4 elected arrivals)
+  uint64_t* bar_pv = bar_p + 2;         // PV(j) complete (one completion per tile)
+  uint64_t* bar_done = bar_pv + 1;      // every PV complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * BM);
+  const int q0 = blockIdx.x * BM;
   const int bh = blockIdx.y;
   const int b = bh / p.heads;
 
-  int kv_limit = p.seq;
-  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
-  int kv_hi = kv_limit;
-  if (p.causal) kv_hi = min(kv_hi, q0 + 2 * BM);
-  const int n_tiles = (kv_hi + BN - 1) / BN;
-
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQa);
     tma_prefetch_desc(&tmKa);
     tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 11; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 256);
-    mbar_init(&bar_p[1], 256);
+    for (int i = 0; i < 1 + 4 * ST + 2; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bar_p[0], 4);
+    mbar_init(&bar_p[1], 4);
+    mbar_init(bar_pv, 1);
+    mbar_init(bar_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
@@ -524,201 +538,176 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
 
+  int kv_limit = p.seq;
+  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
+  int kv_hi = kv_limit;
+  if (p.causal) kv_hi = min(kv_hi, q0 + BM);
+  const int n_tiles = (kv_hi + BN3 - 1) / BN3;
+
   if (warp == 0) {
     // ================================ TMA producer ================================
-    // (warp-uniform loops, elected-lane issue: see attn_kernel)
     const bool issuer = elect_one();
     if (issuer) {
       mbar_expect_tx(bar_q, C::Q_TX);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        uint8_t* sq = smem + C::OFF_Q + t * C::QT_BYTES;
-        const int r0 = q0 + t * BM;
-        tma_load_3d(sq, &tmQa, bar_q, 0, r0, bh);
-        if (HD == 80) tma_load_3d(sq + C::Q0_BYTES, &tmQb, bar_q, 64, r0, bh);
-        if (HD == 128) tma_load_3d(sq + C::Q0_BYTES, &tmQa, bar_q, 64, r0, bh);
-        if (EXT) tma_load_3d(sq + C::Q0_BYTES + C::Q1_BYTES, &tmQx, bar_q, 0, r0, bh);
-      }
-      if (EXT == 1) {
+      tma_load_3d(smem + C::OFF_Q0, &tmQa, bar_q, 0, q0, bh);
+      if (HD == 80) tma_load_3d(smem + C::OFF_Q1, &tmQb, bar_q, 64, q0, bh);
+      if (HD == 128) tma_load_3d(smem + C::OFF_Q1, &tmQa, bar_q, 64, q0, bh);
+      if (EXT) {
+        tma_load_3d(smem + C::OFF_QX, &tmQx, bar_q, 0, q0, bh);
         tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
-        tma_load_2d(smem + C::OFF_E + 8192, &tmE, bar_q, 0, 128);
       }
-      if (EXT == 2) tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
     }
     __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const int key0 = j * BN;
-      uint8_t* sk = smem + C::OFF_K + st * C::K_BYTES;
-      uint8_t* sv = smem + C::OFF_V + st * C::V_BYTES;
-      mbar_wait(&k_empty[st], ph ^ 1);
+      const int key0 = j * BN3;
+      uint8_t* st = smem + C::OFF_ST + s * C::STAGE_BYTES;
+      mbar_wait(&k_empty[s], ph ^ 1);
       if (issuer) {
-        mbar_expect_tx(&k_full[st], C::K_BYTES);
-        tma_load_3d(sk, &tmKa, &k_full[st], 0, key0, bh);
-        if (HD == 80) tma_load_3d(sk + C::Q0_BYTES, &tmKb, &k_full[st], 64, key0, bh);
-        if (HD == 128) tma_load_3d(sk + C::Q0_BYTES, &tmKa, &k_full[st], 64, key0, bh);
+        mbar_expect_tx(&k_full[s], C::K_TX);
+        tma_load_3d(st, &tmKa, &k_full[s], 0, key0, bh);
+        if (HD == 80) tma_load_3d(st + C::K0_BYTES, &tmKb, &k_full[s], 64, key0, bh);
+        if (HD == 128) tma_load_3d(st + C::K0_BYTES, &tmKa, &k_full[s], 64, key0, bh);
       }
       __syncwarp();
-      mbar_wait(&v_empty[st], ph ^ 1);
+      mbar_wait(&v_empty[s], ph ^ 1);
       if (issuer) {
-        mbar_expect_tx(&v_full[st], C::V_BYTES);
-        tma_load_3d(sv, &tmV, &v_full[st], key0, 0, bh);
-        tma_load_3d(sv + C::V_CHUNK, &tmV, &v_full[st], key0 + 64, 0, bh);
+        mbar_expect_tx(&v_full[s], C::V_TX);
+        tma_load_3d(st + C::K0_BYTES + C::K1_BYTES, &tmV, &v_full[s], key0, 0, bh);
       }
       __syncwarp();
+      if (++s == ST) {
+        s = 0;
+        ph ^= 1;
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
-      const bool issuer = elect_one();
-      const uint32_t sE = smem_u32(smem + C::OFF_E);
-      // S_g(j) = [q_g|qext_g] . [k_j|kext]^T   into TMEM columns [128g, 128g+128)
-      auto issue_s = [&](int g, int j) {
-        if (p.dbg == 3 && j > 0) return;
-        const uint32_t sq = smem_u32(smem + C::OFF_Q + g * C::QT_BYTES);
-        const uint32_t sk = smem_u32(smem + C::OFF_K + (j & 1) * C::K_BYTES);
-        const uint32_t tS = tmem_base + g * 128;
-        const uint32_t sqx = sq + C::Q0_BYTES + C::Q1_BYTES;
-        const uint64_t dQ0 = umma_smem_desc(sq, 1024, UMMA_SW128), dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
-        const uint64_t dQ1s = umma_smem_desc(sq + C::Q0_BYTES, 256, UMMA_SW32);
-        const uint64_t dK1s = umma_smem_desc(sk + C::Q0_BYTES, 256, UMMA_SW32);
-        const uint64_t dQ1 = umma_smem_desc(sq + C::Q0_BYTES, 1024, UMMA_SW128);
-        const uint64_t dK1 = umma_smem_desc(sk + C::Q0_BYTES, 1024, UMMA_SW128);
-        const uint64_t dQXw = umma_smem_desc(sqx, 512, UMMA_SW64), dEw = umma_smem_desc(sE + j * 8192, 512, UMMA_SW64);
-        const uint64_t dQXg = umma_smem_desc(sqx, 1024, UMMA_SW128), dEg = umma_smem_desc(sE, 1024, UMMA_SW128);
-        if (issuer) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
-          if (HD == 80) umma_ss(tS, dQ1s, dK1s, idesc_s, 1);
-          if (HD == 128) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tS, dQ1 + 2 * k, dK1 + 2 * k, idesc_s, 1);
-          }
-          if (EXT == 1) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) umma_ss(tS, dQXw + 2 * k, dEw + 2 * k, idesc_s, 1);
-          }
-          if (EXT == 2) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tS, dQXg + 2 * k, dEg + 2 * k, idesc_s, 1);
-          }
-        }
-        __syncwarp();
-      };
-      // O_g += P_g(j) . V_j ; P_g sits at S_g columns [0,32) (keys 0..63) and [64,96) (keys 64..127)
-      auto issue_pv = [&](int g, int j) {
-        if (p.dbg == 3 && j > 0) return;
-        const uint32_t sv = smem_u32(smem + C::OFF_V + (j & 1) * C::V_BYTES);
-        const uint32_t tS = tmem_base + g * 128;
-        const uint32_t tO = tmem_base + 256 + g * 128;
-        const uint64_t dV0 = umma_smem_desc(sv, 1024, UMMA_SW128);
-        const uint64_t dV1 = umma_smem_desc(sv + C::V_CHUNK, 1024, UMMA_SW128);
-        if (issuer) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_ts(tO, tS + (k >> 2) * 64 + (k & 3) * 8, (k < 4 ? dV0 : dV1) + 2 * (k & 3), idesc_o, (j | k) != 0);
-        }
-        __syncwarp();
-      };
-      auto commit = [&](uint64_t* bar) {
-        if (issuer) umma_commit(bar);
-        __syncwarp();
-      };
-      mbar_wait(bar_q, 0);
-      mbar_wait(&k_full[0], 0);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN3);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
+    const bool issuer = elect_one();
+    const uint32_t sQ0 = smem_u32(smem + C::OFF_Q0), sQ1 = smem_u32(smem + C::OFF_Q1);
+    const uint32_t sQX = smem_u32(smem + C::OFF_QX), sE = smem_u32(smem + C::OFF_E);
+    const uint32_t sSt = smem_u32(smem + C::OFF_ST);
+    const uint32_t tO = tmem_base + C::O_COL;
+    const uint64_t dQ0 = umma_smem_desc(sQ0, 1024, UMMA_SW128);
+    const uint64_t dQ1s = umma_smem_desc(sQ1, 256, UMMA_SW32);
+    const uint64_t dQ1 = umma_smem_desc(sQ1, 1024, UMMA_SW128);
+    const uint64_t dQXw = umma_smem_desc(sQX, 512, UMMA_SW64), dEw = umma_smem_desc(sE, 512, UMMA_SW64);
+    const uint64_t dQXg = umma_smem_desc(sQX, 1024, UMMA_SW128), dEg = umma_smem_desc(sE, 1024, UMMA_SW128);
+    int ks = 0, vs = 0;          // ring positions of the next K / V tile to consume
+    uint32_t kph = 0, vph = 0;
+    auto issue_s = [&](int j) {
+      const uint32_t sk = sSt + ks * C::STAGE_BYTES;
+      const uint32_t tS = tmem_base + (j & 1) * BN3;
+      mbar_wait(&k_full[ks], kph);
       tc_fence_after();
-      issue_s(0, 0);
-      commit(&bar_s[0]);
-      issue_s(1, 0);
-      commit(&bar_s[1]);
-      commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = j & 1;            // bar_p / bar_s complete once per tile
-        const uint32_t kvph = (j >> 1) & 1;   // 2-stage K/V rings
-        const bool more = j + 1 < n_tiles;
-        // ---- query tile 0 ----
-        mbar_wait(&bar_p[0], ph);
-        mbar_wait(&v_full[st], kvph);
-        tc_fence_after();
-        issue_pv(0, j);
-        if (more) {
-          mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s(0, j + 1);
+      if (issuer) {
+        const uint64_t dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
+        if (HD == 80) umma_ss(tS, dQ1s, umma_smem_desc(sk + C::K0_BYTES, 256, UMMA_SW32), idesc_s, 1);
+        if (HD == 128) {
+          const uint64_t dK1 = umma_smem_desc(sk + C::K0_BYTES, 1024, UMMA_SW128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ1 + 2 * k, dK1 + 2 * k, idesc_s, 1);
         }
-        commit(&bar_s[0]);  // S0(j+1) ready — or, after the last tile, O0 complete
-        // ---- query tile 1 ----
-        mbar_wait(&bar_p[1], ph);
-        tc_fence_after();
-        issue_pv(1, j);
-        commit(&v_empty[st]);
-        if (more) {
-          issue_s(1, j + 1);
-          commit(&k_empty[st ^ 1]);
+        if (EXT == 1) {  // kext rows [64j, 64j+64) of the [256 x 32] one-hot table: 64 rows x 64 B = 4096 B per tile
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_ss(tS, dQXw + 2 * k, dEw + (uint64_t)(j * 256 + 2 * k), idesc_s, 1);
         }
-        commit(&bar_s[1]);
+        if (EXT == 2) {  // a 64-key tile is one grid row: the same 64 x 64 identity for every tile
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tS, dQXg + 2 * k, dEg + 2 * k, idesc_s, 1);
+        }
+        umma_commit(&k_empty[ks]);
+        umma_commit(&bar_s[j & 1]);
       }
+      __syncwarp();
+      if (++ks == ST) {
+        ks = 0;
+        kph ^= 1;
+      }
+    };
+    auto issue_pv = [&](int j) {
+      const uint32_t sv = sSt + vs * C::STAGE_BYTES + C::K0_BYTES + C::K1_BYTES;
+      const uint32_t tP = tmem_base + (j & 1) * BN3;
+      mbar_wait(&bar_p[j & 1], (uint32_t)((j >> 1) & 1));
+      mbar_wait(&v_full[vs], vph);
+      tc_fence_after();
+      if (issuer) {
+        const uint64_t dV = umma_smem_desc(sv, 1024, UMMA_SW128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(tO, tP + k * 8, dV + 2 * k, idesc_o, (j | k) != 0);
+        umma_commit(&v_empty[vs]);
+        umma_commit(bar_pv);
+      }
+      __syncwarp();
+      if (++vs == ST) {
+        vs = 0;
+        vph ^= 1;
+      }
+    };
+    mbar_wait(bar_q, 0);
+    issue_s(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_s(j + 1);
+      issue_pv(j);
     }
+    if (issuer) umma_commit(bar_done);
+    __syncwarp();
   } else {
-    // ================================ softmax groups ================================
-    const int g = warp >= 10 ? 1 : 0;          // query tile / softmax group
-    const int wg = warp - 2 - 8 * g;           // 0..7 inside the group
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may touch
-    const int half = wg >> 2;                  // which 64-key half of the score tile
+    // ================================ softmax / correction / epilogue ================================
+    const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
-    const int q_row = q0 + g * BM + row_in_tile;
+    const int q_row = q0 + row_in_tile;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t tS_mine = t_row + g * 128 + half * 64;
-    const uint32_t tO = t_row + 256 + g * 128;
-    float* xmax = reinterpret_cast<float*>(smem + C::OFF_XCH + g * 3072);  // [2 parity][2 half][128]
-    float* xsum = xmax + 512;                                              // [2 half][128]
-    const int bar_id = 1 + g;
-    constexpr int O_CHUNKS = HD / 16;
-    const int oc0 = half == 0 ? 0 : (O_CHUNKS + 1) / 2;
-    const int oc1 = half == 0 ? (O_CHUNKS + 1) / 2 : O_CHUNKS;
-    const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;
+    const uint32_t tO = t_row + C::O_COL;
+    const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;  // key valid iff key < lim
     const bf16* rb = nullptr;
     if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
     const float c1 = p.c1;
     float m = -INFINITY, l = 0.f;
-    const int q_tile0 = q0 + g * BM;
+    float add_next = 0.f;
+    if (EXT == 2) add_next = __bfloat162float(rb[0]) * LOG2E;
 
     for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t ph = j & 1;
-      const int key0 = j * BN + half * 64;
-      float add = 0.f;
-      if (EXT == 2) add = __bfloat162float(rb[2 * j + half]) * LOG2E;
-      const bool need_mask = (key0 + 64 > kv_limit) || (p.causal && key0 + 63 > q_tile0);
-      mbar_wait(&bar_s[g], ph);
+      const int sb = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int key0 = j * BN3;
+      const uint32_t tS = t_row + sb * BN3;
+      const float add = add_next;
+      if (EXT == 2 && j + 1 < n_tiles) add_next = __bfloat162float(rb[j + 1]) * LOG2E;
+      const bool need_mask = (key0 + BN3 > kv_limit) || (p.causal && key0 + BN3 - 1 > q0);
+      mbar_wait(&bar_s[sb], ph);
       tc_fence_after();
-
-      float mx, lsum = 0.f;
-      uint32_t pk[32];
+      float lsum = 0.f;
       if (j == 0) {
-        mx = need_mask ? softmax_row_max<true>(tS_mine, c1, add, key0, lim)
-                       : softmax_row_max<false>(tS_mine, c1, add, key0, lim);
+        const float mx = need_mask ? softmax_row_max<true>(tS, c1, add, key0, lim)
+                                   : softmax_row_max<false>(tS, c1, add, key0, lim);
+        m = mx;
+        const float addm = add - ((m == -INFINITY) ? 0.f : m);
+        lsum = need_mask ? softmax_exp_store<true>(tS, c1, addm, key0, lim)
+                         : softmax_exp_store<false>(tS, c1, addm, key0, lim);
       } else {
+        // fast path: P against the RUNNING max while tracking this tile's max; S is read from TMEM once
         const float m_fast = (m == -INFINITY) ? 0.f : m;
-        mx = (need_mask ? softmax_exp_regs<true>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)
-                        : softmax_exp_regs<false>(tS_mine, c1, add - m_fast, key0, lim, lsum, pk, p.dbg)) +
-             m_fast;
-        if (p.dbg == 1 || p.dbg == 2) mx = m;  // keep the fast path
-      }
-      xmax[(ph * 2 + half) * 128 + row_in_tile] = mx;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, xmax[(ph * 2 + (half ^ 1)) * 128 + row_in_tile]);
-      const float m_new = fmaxf(m, mx);
-
-      if (j == 0 || __any_sync(0xffffffffu, m_new > m + 8.0f)) {
-        if (j > 0) {
-          float f = ex2(m - m_new);
+        uint32_t pk[32];
+        const float mx_rel = need_mask ? softmax_exp_regs<true>(tS, c1, add - m_fast, key0, lim, lsum, pk)
+                                       : softmax_exp_regs<false>(tS, c1, add - m_fast, key0, lim, lsum, pk);
+        const bool grow = (m == -INFINITY) ? (mx_rel > -INFINITY) : (mx_rel > 8.0f);
+        if (__any_sync(0xffffffffu, grow)) {
+          // some row's max grew by more than 2^8: rescale O (after PV(j-1), which may still be running) and
+          // recompute this tile's P against the new max
+          mbar_wait(bar_pv, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+          const float g = fmaxf(mx_rel, 0.f);
+          const float m_new = (m == -INFINITY) ? mx_rel : m + g;
+          float f = (m == -INFINITY) ? 1.f : ex2(-g);
           if (m_new == -INFINITY) f = 1.f;
 #pragma unroll 1
-          for (int c = oc0; c < oc1; ++c) {
+          for (int c = 0; c < HD / 16; ++c) {
             uint32_t r[16];
             tmem_ld16(tO + c * 16, r);
             tmem_ld_wait();
@@ -727,36 +716,35 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
             tmem_st16(tO + c * 16, r);
           }
           l *= f;
+          m = m_new;
+          const float addm = add - ((m == -INFINITY) ? 0.f : m);
+          lsum = need_mask ? softmax_exp_store<true>(tS, c1, addm, key0, lim)
+                           : softmax_exp_store<false>(tS, c1, addm, key0, lim);
+        } else {
+          tmem_st32(tS, pk);
         }
-        m = m_new;
-        const float addm = add - ((m == -INFINITY) ? 0.f : m);
-        lsum = need_mask ? softmax_exp_store<true>(tS_mine, c1, addm, key0, lim)
-                         : softmax_exp_store<false>(tS_mine, c1, addm, key0, lim);
-      } else if (p.dbg != 4) {
-        tmem_st16(tS_mine, pk);
-        tmem_st16(tS_mine + 16, pk + 16);
       }
       l += lsum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar_p[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[sb]);
     }
 
-    // ---- epilogue: O / l -> bf16 -> out[b*seq + q_row, h*HD + d] ----
-    mbar_wait(&bar_s[g], n_tiles & 1);
+    // ---- epilogue: O / l → bf16 → out[b*seq + q_row, h*HD + d] ----
+    mbar_wait(bar_done, 0);
     tc_fence_after();
-    xsum[half * 128 + row_in_tile] = l;
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    l += xsum[(half ^ 1) * 128 + row_in_tile];
     const float inv_l = l > 0.f ? 1.0f / l : 0.f;
     const int h = bh - b * p.heads;
-    bf16* orow = p.out + ((size_t)b * p.seq + q_row) * p.ldo + h * HD;
+    long long out_r = (long long)b * p.seq + q_row;
+    if (p.out_row_map != nullptr) out_r = q_row < p.seq ? p.out_row_map[out_r] : -1;
+    bf16* orow = p.out + (size_t)(out_r < 0 ? 0 : out_r) * p.ldo + h * HD;
 #pragma unroll 1
-    for (int c = oc0; c < oc1; ++c) {
+    for (int c = 0; c < HD / 16; ++c) {
       uint32_t r[16];
       tmem_ld16(tO + c * 16, r);
       tmem_ld_wait();
-      if (q_row < p.seq) {
+      if (q_row < p.seq && out_r >= 0) {
         uint4 o0, o1;
         o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
         o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
@@ -1226,16 +1214,6 @@ int launch_attn_win(const llmseg_attn_params* p, cudaStream_t stream) {
   return 0;
 }
 
-// LLMSEG_ATTN_V2=0|1: select the two-query-tile kernel
-bool use_attn_v2() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("LLMSEG_ATTN_V2");
-    mode = e ? atoi(e) : 0;
-  }
-  return mode == 1;
-}
-
 template <int HD, int EXT>
 int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   using C = ACfg<HD, EXT>;
@@ -1294,20 +1272,6 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
     d.dbg = dbg;
   }
 
-  if (use_attn_v2() && p->out_row_map == nullptr) {
-    using C2 = ACfg2<HD, EXT>;
-    auto kern2 = attn2_kernel<HD, EXT>;
-    static bool attr2_done = false;
-    if (!attr2_done) {
-      LLMSEG_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES));
-      attr2_done = true;
-    }
-    dim3 grid2((p->seq + 2 * BM - 1) / (2 * BM), BH);
-    kern2<<<grid2, 576, C2::SMEM_BYTES, stream>>>(tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d);
-    LLMSEG_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1);
-    return 0;
-  }
   auto kern = attn_kernel<HD, EXT>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1326,6 +1290,85 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d));
   g_launches.fetch_add(1);
   return 0;
+}
+
+// LLMSEG_ATTN_V1=1 (read per call: A/B runs flip it between launches) keeps the single-buffer kernel
+bool use_attn_v1() {
+  const char* e = getenv("LLMSEG_ATTN_V1");
+  return e != nullptr && atoi(e) == 1;
+}
+
+template <int HD, int EXT>
+int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
+  using C = A3Cfg<HD, EXT>;
+  const int BH = p->batch * p->heads;
+  CUtensorMap tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE;
+  {
+    uint64_t dims[3] = {(uint64_t)HD, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)HD * 2, (uint64_t)p->seq_pad * HD * 2};
+    uint32_t qa[3] = {64, 128, 1}, ka[3] = {64, BN3, 1};
+    if (int e = make_tmap_bf16(&tmQa, p->q, 3, dims, str, qa, 128)) return e;
+    if (int e = make_tmap_bf16(&tmKa, p->k, 3, dims, str, ka, 128)) return e;
+    tmQb = tmQa;
+    tmKb = tmKa;
+    if (HD == 80) {
+      uint32_t qb[3] = {16, 128, 1}, kb[3] = {16, BN3, 1};
+      if (int e = make_tmap_bf16(&tmQb, p->q, 3, dims, str, qb, 32)) return e;
+      if (int e = make_tmap_bf16(&tmKb, p->k, 3, dims, str, kb, 32)) return e;
+    }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p->seq_pad, (uint64_t)HD, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)p->seq_pad * 2, (uint64_t)p->seq_pad * HD * 2};
+    uint32_t box[3] = {BN3, (uint32_t)HD, 1};
+    if (int e = make_tmap_bf16(&tmV, p->vt, 3, dims, str, box, 128)) return e;
+  }
+  tmQx = tmQa;
+  tmE = tmQa;
+  if (EXT) {
+    const int xc = EXT == 1 ? 32 : 64;
+    uint64_t dims[3] = {(uint64_t)xc, (uint64_t)p->seq_pad, (uint64_t)BH};
+    uint64_t str[2] = {(uint64_t)xc * 2, (uint64_t)p->seq_pad * xc * 2};
+    uint32_t box[3] = {(uint32_t)xc, 128, 1};
+    if (int e = make_tmap_bf16(&tmQx, p->qext, 3, dims, str, box, xc * 2)) return e;
+    uint64_t edims[2] = {(uint64_t)xc, (uint64_t)(EXT == 1 ? 256 : 128)};
+    uint64_t estr[1] = {(uint64_t)xc * 2};
+    uint32_t ebox[2] = {(uint32_t)xc, (uint32_t)(EXT == 1 ? 256 : 64)};
+    if (int e = make_tmap_bf16(&tmE, p->kext, 2, edims, estr, ebox, xc * 2)) return e;
+  }
+  AttnDev d{};
+  d.out = static_cast<bf16*>(p->out);
+  d.ldo = p->ldo;
+  d.heads = p->heads;
+  d.seq = p->seq;
+  d.seq_pad = p->seq_pad;
+  d.c1 = p->scale * LOG2E;
+  d.causal = p->causal;
+  d.kv_len = p->kv_len;
+  d.row_bias = static_cast<const bf16*>(p->row_bias);
+  d.out_row_map = p->out_row_map;
+  auto kern = attn3_kernel<HD, EXT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((p->seq + BM - 1) / BM, BH);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_attr(attr, 0);
+  LLMSEG_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE, d));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+template <int HD, int EXT>
+int launch_attn_any(const llmseg_attn_params* p, cudaStream_t stream) {
+  return use_attn_v1() ? launch_attn<HD, EXT>(p, stream) : launch_attn3<HD, EXT>(p, stream);
 }
 
 }  // namespace
@@ -1354,12 +1397,12 @@ extern "C" int llmseg_attention(const llmseg_attn_params* p, void* stream_) {
                    LLMSEG_ESHAPE, "llmseg_attention: ext_cols=%d inconsistent with seq=%d / row_bias", ext,
                    p->seq);
   }
-  if (hd == 64 && ext == 0) return launch_attn<64, 0>(p, stream);
-  if (hd == 128 && ext == 0) return launch_attn<128, 0>(p, stream);
-  if (hd == 80 && ext == 0) return launch_attn<80, 0>(p, stream);
+  if (hd == 64 && ext == 0) return launch_attn_any<64, 0>(p, stream);
+  if (hd == 128 && ext == 0) return launch_attn_any<128, 0>(p, stream);
+  if (hd == 80 && ext == 0) return launch_attn_any<80, 0>(p, stream);
   if (hd == 80 && ext == 32 && p->seq >= 192 && p->seq <= 208 && p->kv_len == nullptr && use_attn_win())
     return launch_attn_win(p, stream);
-  if (hd == 80 && ext == 32) return launch_attn<80, 1>(p, stream);
-  if (hd == 80 && ext == 64) return launch_attn<80, 2>(p, stream);
+  if (hd == 80 && ext == 32) return launch_attn_any<80, 1>(p, stream);
+  if (hd == 80 && ext == 64) return launch_attn_any<80, 2>(p, stream);
   return set_error(LLMSEG_ESHAPE, "llmseg_attention: unsupported head_dim=%d ext_cols=%d", hd, ext);
 }
