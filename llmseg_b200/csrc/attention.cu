@@ -114,23 +114,27 @@ __device__ __forceinline__ float softmax_exp_regs(uint32_t t_s, float c1, float 
     tmem_ld32(t_s + 32, rr + 32);
     tmem_ld_wait();
   }
+  // packed pairs (FFMA2 / FADD2): this loop is issue-bound — trading half of the ex2 for an FMA-pipe polynomial made
+  // every variant of the kernel 10-20 % SLOWER (profiles/round2_attn.md), so instructions are what to save here
+  const float2 c2 = make_float2(c1, c1), a2 = make_float2(addm, addm);
+  float2 ls = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const uint32_t* r = rr + c * 32;
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
-      float t0 = fmaf(__uint_as_float(r[e]), c1, addm);
-      float t1 = fmaf(__uint_as_float(r[e + 1]), c1, addm);
+      float2 t = ffma2(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, a2);
       if (MASK) {
-        if (key0 + c * 32 + e >= lim) t0 = -INFINITY;
-        if (key0 + c * 32 + e + 1 >= lim) t1 = -INFINITY;
+        if (key0 + c * 32 + e >= lim) t.x = -INFINITY;
+        if (key0 + c * 32 + e + 1 >= lim) t.y = -INFINITY;
       }
-      mx = fmaxf(mx, fmaxf(t0, t1));
-      const float p0 = dbg == 1 ? t0 * 0.01f : ex2(t0), p1 = dbg == 1 ? t1 * 0.01f : ex2(t1);
-      lsum += p0 + p1;
+      mx = fmaxf(mx, fmaxf(t.x, t.y));
+      const float p0 = dbg == 1 ? t.x * 0.01f : ex2(t.x), p1 = dbg == 1 ? t.y * 0.01f : ex2(t.y);
+      ls = fadd2(ls, make_float2(p0, p1));
       pk[c * 16 + (e >> 1)] = pack_bf16(p0, p1);
     }
   }
+  lsum += ls.x + ls.y;
   return mx;
 }
 
@@ -441,6 +445,30 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CU
   }
 }
 
+// v3 fast path, one 32-column chunk already in registers: P = exp2(s*c1 + addm) packed into pk16[16]; tracks the
+// chunk's max exponent argument (two chains) and the row sum (two chains: a single FADD chain of 64 was latency).
+template <bool MASK>
+__device__ __forceinline__ void softmax_exp_chunk(const uint32_t* r, float c1, float addm, int key0, int lim,
+                                                  float& mx0, float& mx1, float& l0, float& l1, uint32_t* pk16) {
+  const float2 c2 = make_float2(c1, c1), a2 = make_float2(addm, addm);
+  float2 ls = make_float2(l0, l1);
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    float2 t = ffma2(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, a2);
+    if (MASK) {
+      if (key0 + e >= lim) t.x = -INFINITY;
+      if (key0 + e + 1 >= lim) t.y = -INFINITY;
+    }
+    mx0 = fmaxf(mx0, t.x);
+    mx1 = fmaxf(mx1, t.y);
+    const float p0 = ex2(t.x), p1 = ex2(t.y);
+    ls = fadd2(ls, make_float2(p0, p1));
+    pk16[e >> 1] = pack_bf16(p0, p1);
+  }
+  l0 = ls.x;
+  l1 = ls.y;
+}
+
 // =============================================================================================
 // v3: 64-key score tiles DOUBLE-BUFFERED in TMEM.
 //
@@ -671,6 +699,15 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
     float m = -INFINITY, l = 0.f;
     float add_next = 0.f;
     if (EXT == 2) add_next = __bfloat162float(rb[0]) * LOG2E;
+    // The TMEM -> register path (64 B/clk per SM: 512 clk for a CTA's 128 x 64 fp32 tile) and the MUFU (512 clk for
+    // its 8192 ex2) are the two bounds of this loop, and ncu on the first v3 (profiles/round2_attn3.md) showed each
+    // softmax warp running them one after the other: load all 64 columns, wait, then 64 ex2 — 1858 clk per tile and
+    // warp, MUFU 57 % busy.  So the loop is software-pipelined: the tile's second 32 columns are in flight while the
+    // first 32 are exponentiated, and the first 32 columns of the NEXT tile (whose MMA finished long ago) are
+    // requested before the second half is touched (v4 below; here, with P aliasing S, the next tile's scores are not
+    // complete early enough for that).
+    uint32_t ra[32], rc[32];
+    const bool pre = false;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
@@ -680,10 +717,10 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
       const float add = add_next;
       if (EXT == 2 && j + 1 < n_tiles) add_next = __bfloat162float(rb[j + 1]) * LOG2E;
       const bool need_mask = (key0 + BN3 > kv_limit) || (p.causal && key0 + BN3 - 1 > q0);
-      mbar_wait(&bar_s[sb], ph);
-      tc_fence_after();
       float lsum = 0.f;
       if (j == 0) {
+        mbar_wait(&bar_s[sb], ph);
+        tc_fence_after();
         const float mx = need_mask ? softmax_row_max<true>(tS, c1, add, key0, lim)
                                    : softmax_row_max<false>(tS, c1, add, key0, lim);
         m = mx;
@@ -691,11 +728,25 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
         lsum = need_mask ? softmax_exp_store<true>(tS, c1, addm, key0, lim)
                          : softmax_exp_store<false>(tS, c1, addm, key0, lim);
       } else {
+        if (!pre) {
+          mbar_wait(&bar_s[sb], ph);
+          tc_fence_after();
+          tmem_ld32(tS, ra);
+        }
         // fast path: P against the RUNNING max while tracking this tile's max; S is read from TMEM once
         const float m_fast = (m == -INFINITY) ? 0.f : m;
+        const float addm = add - m_fast;
         uint32_t pk[32];
-        const float mx_rel = need_mask ? softmax_exp_regs<true>(tS, c1, add - m_fast, key0, lim, lsum, pk)
-                                       : softmax_exp_regs<false>(tS, c1, add - m_fast, key0, lim, lsum, pk);
+        float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        tmem_ld_wait();
+        tmem_ld32(tS + 32, rc);
+        if (need_mask) softmax_exp_chunk<true>(ra, c1, addm, key0, lim, mx0, mx1, l0, l1, pk);
+        else softmax_exp_chunk<false>(ra, c1, addm, key0, lim, mx0, mx1, l0, l1, pk);
+        tmem_ld_wait();
+        if (need_mask) softmax_exp_chunk<true>(rc, c1, addm, key0 + 32, lim, mx0, mx1, l0, l1, pk + 16);
+        else softmax_exp_chunk<false>(rc, c1, addm, key0 + 32, lim, mx0, mx1, l0, l1, pk + 16);
+        const float mx_rel = fmaxf(mx0, mx1);
+        lsum = l0 + l1;
         const bool grow = (m == -INFINITY) ? (mx_rel > -INFINITY) : (mx_rel > 8.0f);
         if (__any_sync(0xffffffffu, grow)) {
           // some row's max grew by more than 2^8: rescale O (after PV(j-1), which may still be running) and
@@ -717,9 +768,9 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
           }
           l *= f;
           m = m_new;
-          const float addm = add - ((m == -INFINITY) ? 0.f : m);
-          lsum = need_mask ? softmax_exp_store<true>(tS, c1, addm, key0, lim)
-                           : softmax_exp_store<false>(tS, c1, addm, key0, lim);
+          const float addm2 = add - ((m == -INFINITY) ? 0.f : m);
+          lsum = need_mask ? softmax_exp_store<true>(tS, c1, addm2, key0, lim)
+                           : softmax_exp_store<false>(tS, c1, addm2, key0, lim);
         } else {
           tmem_st32(tS, pk);
         }
@@ -1292,12 +1343,6 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   return 0;
 }
 
-// LLMSEG_ATTN_V1=1 (read per call: A/B runs flip it between launches) keeps the single-buffer kernel
-bool use_attn_v1() {
-  const char* e = getenv("LLMSEG_ATTN_V1");
-  return e != nullptr && atoi(e) == 1;
-}
-
 template <int HD, int EXT>
 int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
   using C = A3Cfg<HD, EXT>;
@@ -1347,14 +1392,20 @@ int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
   d.kv_len = p->kv_len;
   d.row_bias = static_cast<const bf16*>(p->row_bias);
   d.out_row_map = p->out_row_map;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((p->seq + BM - 1) / BM, BH);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr4[1];
+  cfg.attrs = attr4;
+  cfg.numAttrs = pdl_attr(attr4, 0);
   auto kern = attn3_kernel<HD, EXT>;
   static bool attr_done = false;
   if (!attr_done) {
     LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((p->seq + BM - 1) / BM, BH);
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
@@ -1366,9 +1417,16 @@ int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
   return 0;
 }
 
+// Which kernel: measured on one box, interleaved (profiles/round2_attn.md) — the double-buffered 64-key kernel wins
+// where the sequence is short or the head wide (LLaMA causal T=319: 36 -> 28 us, T=767: 33 -> 28, CLIP 20 -> 17,
+// DINOv2 4097 tokens 880 -> 825 us); the SAM global layers (rel-pos extension columns: 13 instead of 9 score MMAs
+// per 128 keys, and twice the softmax warps per SM to hide their latencies) stay 8-10 % faster on the 128-key kernel.
+// LLMSEG_ATTN_V1 = 1 / 0 forces one of them (read per call: A/B runs flip it between launches).
 template <int HD, int EXT>
 int launch_attn_any(const llmseg_attn_params* p, cudaStream_t stream) {
-  return use_attn_v1() ? launch_attn<HD, EXT>(p, stream) : launch_attn3<HD, EXT>(p, stream);
+  const char* e = getenv("LLMSEG_ATTN_V1");
+  const bool v1 = e != nullptr ? atoi(e) == 1 : EXT != 0;
+  return v1 ? launch_attn<HD, EXT>(p, stream) : launch_attn3<HD, EXT>(p, stream);
 }
 
 }  // namespace

@@ -20,7 +20,7 @@ REF = Path("/root/reference")
 GOLD = ROOT / "tests" / "golden"
 
 sys.path.insert(0, str(ROOT))
-from oracle import clip_llama, dinov2, lisa_forward, sam_encoder, selector  # noqa: E402
+from oracle import clip_llama, dinov2, lisa_forward, sam_amg, sam_encoder, selector  # noqa: E402
 
 
 def checksum(sd) -> float:
@@ -259,6 +259,121 @@ def gold_splice():
     print("[splice] index arithmetic ok")
 
 
+def gold_sam_amg():
+    """SAM-Everything: the reference's own PromptEncoder + MaskDecoder on seeded point prompts, and its
+    own SamAutomaticMaskGenerator.generate() end to end (image encoder replaced by a stub that returns a seeded
+    embedding: the ViT-H encoder is pinned separately by sam_*.pt) — against oracle/sam_amg.py."""
+    import numpy as np
+    sys.path.insert(0, str(REF))
+    from model.segment_anything import SamAutomaticMaskGenerator  # type: ignore
+    from model.segment_anything.modeling import MaskDecoder, PromptEncoder, Sam, TwoWayTransformer  # type: ignore
+
+    seed = 11
+    sd = sam_amg.random_state_dict(seed)
+
+    class StubEncoder(torch.nn.Module):
+        img_size = 1024
+
+        def __init__(self, emb):
+            super().__init__()
+            self.emb = emb
+
+        def forward(self, x):
+            return self.emb
+
+    g = torch.Generator().manual_seed(seed + 1)
+    # a smooth random field + noise: mask logits with coherent regions, so boxes / NMS / areas are exercised
+    low = torch.randn(1, 256, 8, 8, generator=g)
+    emb = F.interpolate(low, size=(64, 64), mode="bilinear", align_corners=False) + 0.3 * torch.randn(1, 256, 64, 64, generator=g)
+    sam = Sam(image_encoder=StubEncoder(emb),
+              prompt_encoder=PromptEncoder(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024),
+                                           mask_in_chans=16),
+              mask_decoder=MaskDecoder(num_multimask_outputs=3,
+                                       transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
+                                       transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256),
+              pixel_mean=[123.675, 116.28, 103.53], pixel_std=[58.395, 57.12, 57.375]).eval()
+    # The vendored predictor calls `prompt_encoder(points=, boxes=, masks=)` (predictor.py:233-237) while LISA's fork of
+    # the encoder added a required `text_embeds` argument (prompt_encoder.py:128-134) — the reference's own proposal
+    # scripts therefore run the pip `segment_anything` package, whose encoder has no such argument.  Default it to None.
+    _pe_forward = sam.prompt_encoder.forward
+    sam.prompt_encoder.forward = lambda points, boxes, masks, text_embeds=None: _pe_forward(points, boxes, masks, text_embeds)
+    res = sam.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("image_encoder", "prompt_encoder.mask_downscaling", "pixel_")) for k in res.missing_keys), res.missing_keys
+    # (1) point prompts -> low-res mask logits + IoU predictions
+    pts = torch.tensor([[100.0, 200.0], [512.5, 512.5], [900.0, 40.0], [16.0, 1000.0], [700.25, 333.0]])
+    with torch.no_grad():
+        sparse, dense = sam.prompt_encoder(points=(pts[:, None, :], torch.ones(5, 1, dtype=torch.int)), boxes=None, masks=None,
+                                           text_embeds=None)
+        low_ref, iou_ref = sam.mask_decoder(image_embeddings=emb, image_pe=sam.prompt_encoder.get_dense_pe(),
+                                            sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                                            multimask_output=True)
+        low, iou = sam_amg.predict_points(emb, pts, sd)
+        e_sparse = (sam_amg.embed_points(pts, sd) - sparse).abs().max().item()
+    e_low, e_iou = (low - low_ref).abs().max().item(), (iou - iou_ref).abs().max().item()
+    print(f"[sam_amg] oracle vs reference PromptEncoder/MaskDecoder: sparse {e_sparse:.2e} masks {e_low:.2e} (|masks| max "
+          f"{low_ref.abs().max().item():.2f}) iou {e_iou:.2e}")
+    assert e_sparse < 1e-5 and e_low < 2e-3 and e_iou < 1e-4
+    # (2) the reference's generator end to end: 8 x 8 point grid.  Random decoder weights give masks that span the
+    # image, so at the default box-NMS threshold a single mask survives; the second configuration (threshold 1.0:
+    # nothing is suppressed) keeps every mask that passes the IoU / stability filters, which pins the per-mask
+    # records; the suppression rule itself is pinned against torchvision on random boxes in (4).
+    image = np.zeros((1024, 1024, 3), dtype=np.uint8)
+    runs = {}
+    for tag, nms_thr in (("nms07", 0.7), ("nms10", 1.0)):
+        kw = dict(points_per_side=8, points_per_batch=16, pred_iou_thresh=-0.6, stability_score_thresh=0.5,
+                  stability_score_offset=1.0, box_nms_thresh=nms_thr)
+        amg = SamAutomaticMaskGenerator(sam, crop_n_layers=0, min_mask_region_area=0, output_mode="binary_mask", **kw)
+        with torch.no_grad():
+            anns = amg.generate(image)
+            data = sam_amg.generate(emb, sd, **kw)
+        print(f"[sam_amg:{tag}] reference generate(): {len(anns)} masks; oracle: {data['masks'].shape[0]}")
+        assert len(anns) == data["masks"].shape[0] and len(anns) >= 1
+        ref_masks = torch.from_numpy(np.stack([a["segmentation"] for a in anns]))
+        ref_iou = torch.tensor([a["predicted_iou"] for a in anns])
+        ref_stab = torch.tensor([a["stability_score"] for a in anns])
+        ref_area = torch.tensor([a["area"] for a in anns])
+        ref_box = torch.tensor([a["bbox"] for a in anns])           # XYWH
+        ref_pts = torch.tensor([a["point_coords"][0] for a in anns])
+        assert torch.equal(ref_masks, data["masks"]), "oracle masks differ from the reference generator's"
+        assert (ref_iou - data["iou_preds"]).abs().max().item() < 1e-4 and (ref_stab - data["stability"]).abs().max().item() < 1e-5
+        assert torch.equal(ref_area, data["areas"]) and (ref_pts - data["points"]).abs().max().item() < 1e-3
+        b = data["boxes"].float()
+        assert torch.equal(ref_box, torch.stack([b[:, 0], b[:, 1], b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], dim=-1))
+        runs[tag] = {"kw": kw, "n_masks": len(anns), "ref_iou": ref_iou, "ref_stability": ref_stab, "ref_area": ref_area,
+                     "ref_box_xywh": ref_box, "ref_points": ref_pts}
+    assert runs["nms10"]["n_masks"] >= 8
+    # (3) LLM-Seg's consumer side: largest masks first, antialiased bilinear resize to 256 x 256
+    soft, order = sam_amg.llmseg_proposals(data, top_k=50)
+    lo, w = sam_amg.aa_downsample_weights(1024, 256)
+    m0 = data["masks"][order[0]].double()
+    rows = torch.stack([(m0[int(lo[i]):int(lo[i]) + w.shape[1]] * w[i, :m0[int(lo[i]):int(lo[i]) + w.shape[1]].shape[0], None]).sum(0)
+                        for i in range(256)])
+    sep = torch.stack([(rows[:, int(lo[i]):int(lo[i]) + w.shape[1]] * w[i, :rows[:, int(lo[i]):int(lo[i]) + w.shape[1]].shape[1]]).sum(1)
+                       for i in range(256)], dim=1)
+    e_aa = (sep.float() - soft[0]).abs().max().item()
+    print(f"[sam_amg] explicit antialias filter vs F.interpolate(antialias=True): max|d| = {e_aa:.2e}")
+    assert e_aa < 1e-5
+    # (4) the suppression rule against torchvision's batched_nms (what automatic_mask_generator.py:256-262 calls)
+    from torchvision.ops.boxes import batched_nms
+    gb = torch.Generator().manual_seed(seed + 2)
+    xy = torch.rand(300, 2, generator=gb) * 900
+    wh = torch.rand(300, 2, generator=gb) * 300 + 4
+    boxes = torch.cat([xy, xy + wh], dim=1).round()
+    boxes[100:140] = boxes[:40] + torch.randint(-6, 7, (40, 4), generator=gb).float()      # near-duplicates
+    scores = torch.rand(300, generator=gb)
+    scores[200:210] = scores[0]                                                          # ties
+    keep_tv = batched_nms(boxes, scores, torch.zeros(300), 0.7)
+    keep_or = sam_amg.nms(boxes, scores, 0.7)
+    assert torch.equal(keep_tv, keep_or), "oracle NMS differs from torchvision batched_nms"
+    print(f"[sam_amg] NMS vs torchvision: {len(keep_or)} of 300 boxes kept, identical order")
+    keep = min(6, data["masks"].shape[0])
+    torch.save({"seed": seed, "emb_seed": seed + 1, "weights_checksum": checksum(sd), "emb": emb.to(torch.bfloat16),
+                "points": pts, "low_res": low_ref[:2].to(torch.float16), "iou": iou_ref, "runs": runs,
+                "mask_rows_sum": ref_masks.sum(-1).to(torch.int16)[:keep], "soft_top": soft[:keep].to(torch.float16),
+                "soft_order": order, "nms_boxes": boxes, "nms_scores": scores, "nms_keep": keep_tv}, GOLD / "sam_amg.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
@@ -274,6 +389,7 @@ def main():
     gold_llama()
     gold_dinov2()
     gold_splice()
+    gold_sam_amg()
     print("golden fixtures written to", GOLD)
 
 

@@ -21,27 +21,29 @@ ops.relpos_prep(q, rel, bh=B * H, seq=S, seq_pad=S, head_dim=hd, grid=64, inv_sc
 out = torch.empty(B * S, H * hd, device=dev, dtype=torch.bfloat16); kext = ops.make_kext(64, dev)
 fl = 4 * B * H * S * S * hd
 outs = {}
-for v1 in ("1", "0", "1", "0"):      # interleaved A/B: single-buffer kernel (v1) vs double-buffered 64-key tiles (v3)
-    os.environ["LLMSEG_ATTN_V1"] = v1
+def variant(v):   # v1: single 128-key score buffer, 8 softmax warps; v3: two 64-key buffers, 4 softmax warps
+    os.environ["LLMSEG_ATTN_V1"] = "1" if v == "v1" else "0"
+for v in ("v1", "v3", "v1", "v3"):      # interleaved
+    variant(v)
     o = torch.empty_like(out)
     us = t(lambda: ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale, qext=qext, kext=kext, row_bias=rb, ext_cols=64))
-    outs[v1] = o
-    print(f"global attention B={B} {'v1' if v1 == '1' else 'v3'}: {us:8.1f} us  {fl / us / 1e6:6.0f} TF/s", flush=True)
-print(f"global attention v3 vs v1 max|d| = {(outs['0'].float() - outs['1'].float()).abs().max().item():.5f}", flush=True)
-os.environ["LLMSEG_ATTN_V1"] = "0"
+    outs[v] = o
+    print(f"global attention B={B} {v}: {us:8.1f} us  {fl / us / 1e6:6.0f} TF/s", flush=True)
+print(f"global attention max|d| v3-v1 {(outs['v3'].float() - outs['v1'].float()).abs().max().item():.5f}", flush=True)
+os.environ.pop("LLMSEG_ATTN_V1")
 # LLaMA causal (T=319, hd 128), CLIP (257, hd 64), DINOv2 (4097, hd 64) through both kernels
 for name, nb, Hh, hdd, Sx, causal in (("llama causal T=319", B, 32, 128, 319, True), ("clip 257", B, 16, 64, 257, False),
                                       ("dinov2 4097", B, 16, 64, 4097, False), ("llama causal T=767", 2, 32, 128, 767, True)):
     Sp = (Sx + 7) // 8 * 8
     qq = torch.randn(nb * Hh, Sp, hdd, device=dev).bfloat16(); kk = torch.randn_like(qq); vv = torch.randn(nb * Hh, hdd, Sp, device=dev).bfloat16()
     res = {}
-    for v1 in ("1", "0"):
-        os.environ["LLMSEG_ATTN_V1"] = v1
+    for v in ("v1", "v3"):
+        variant(v)
         oo = torch.zeros(nb * Sx, Hh * hdd, device=dev, dtype=torch.bfloat16)
         us = t(lambda: ops.attention(qq, kk, vv, oo, batch=nb, heads=Hh, head_dim=hdd, seq=Sx, seq_pad=Sp, scale=hdd ** -0.5, causal=causal))
-        res[v1] = (us, oo)
-    print(f"{name:22s} v1 {res['1'][0]:7.1f} us   v3 {res['0'][0]:7.1f} us   max|d| {(res['0'][1].float() - res['1'][1].float()).abs().max().item():.5f}", flush=True)
-os.environ["LLMSEG_ATTN_V1"] = "0"
+        res[v] = (us, oo)
+    print(f"{name:22s} v1 {res['v1'][0]:7.1f} us   v3 {res['v3'][0]:7.1f} us   max|d| {(res['v3'][1].float() - res['v1'][1].float()).abs().max().item():.5f}", flush=True)
+os.environ.pop("LLMSEG_ATTN_V1")
 S, Sp, nb = 196, 200, 25 * B
 q = torch.randn(nb * H, Sp, hd, device=dev).bfloat16(); k = torch.randn_like(q); vt = torch.randn(nb * H, hd, Sp, device=dev).bfloat16()
 rel = ops.make_rel_hw((torch.randn(27, hd, device=dev) * 0.1).bfloat16(), (torch.randn(27, hd, device=dev) * 0.1).bfloat16())
