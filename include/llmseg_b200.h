@@ -285,6 +285,47 @@ int llmseg_lm_cross_entropy(const void* logits, int ld, const int64_t* input_ids
 int llmseg_dice_bce_loss(const float* logits, const float* targets, int n_masks, int hw,
                          float num_masks, float* workspace, float* out2, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SAM-Everything proposal generation: what surrounds llmseg_gemm when SAM's prompt encoder + mask
+ * decoder + automatic mask generator run on the image features of llmseg's own SAM encoder, and LLM-Seg's resize of
+ * the resulting masks to soft 256 x 256 proposals.  Replaces (reference model/segment_anything/...):
+ *   point_tokens        modeling/prompt_encoder.py:73-90,186-195 + the token concatenation of mask_decoder.py:123-131
+ *                       points fp32 [P,2] (x,y) input-frame pixels, gauss fp32 [2,128], out_tokens bf16 [5,256]
+ *                       (iou_token ; mask_tokens), point_embed = point_embeddings[1], -> tokens bf16 [P,7,256]
+ *   tok2img_attention   modeling/transformer.py:222-242 for 7 token queries x 4096 image keys, 8 heads x 16:
+ *                       q bf16 [P*7, ldq] (128 cols used), k / v bf16 rows of prompt p at k + p*k_batch_stride
+ *                       (0: every prompt shares one image's keys), -> out bf16 [P*7, ldo] (128 cols)
+ *   img2tok_attention   same Attention for 4096 image queries x 7 token keys: q rows of prompt p at
+ *                       q + p*q_batch_stride (0: shared), k / v bf16 [P*7, ld], -> out bf16 [P*4096, ldo]
+ *   ln64_gelu           LayerNorm2d(64) + GELU (mask_decoder.py:56-62, common.py:31-43) on rows of 64 bf16
+ *   mask_logits         mask_decoder.py:143-157 on the un-shuffled 2x2 ConvTranspose outputs: up2 bf16 [P*16384,128]
+ *                       (row = prompt, token y, token x, dy, dx; col = dy2, dx2, channel), hyper bf16 [P,4,32]
+ *                       -> low_res fp32 [P,3,256,256] (mask tokens 1..3: multimask output, mask_decoder.py:101-104)
+ *   mask_stats          modeling/sam.py:155-166 (4x bilinear up-sampling, evaluated on the fly) + utils/amg.py:156-176,
+ *                       303-346: stats int32 [n,8] = {area, #(> t+o), #(> t-o), 1023-x0, 1023-y0, x1, y1, 0} of
+ *                       candidate cand[i] (NULL: i) — stability = [1]/[2], box valid when area > 0
+ *   box_nms             torchvision nms as automatic_mask_generator.py:256-262 calls it: boxes fp32 [n,4] XYXY sorted
+ *                       by score (descending, stable), keep[i] = 0 if an earlier kept box has IoU > threshold
+ *   mask_soft           utils/dataset.py:620-622 (antialiased bilinear 1024 -> 256) of the binarised up-sampled mask:
+ *                       -> out bf16 [n,256,256]
+ *   mask_binarize       the binary masks themselves: -> out uint8 [n,1024,1024]
+ * ------------------------------------------------------------------------------------------ */
+int llmseg_point_tokens(const float* points, int n_prompts, const float* gauss, const void* out_tokens,
+                        const void* point_embed, const void* not_a_point, float img_size, void* tokens, void* stream);
+int llmseg_tok2img_attention(const void* q, int ldq, const void* k, int ldk, long long k_batch_stride, const void* v,
+                             int ldv, long long v_batch_stride, void* out, int ldo, int n_prompts, void* stream);
+int llmseg_img2tok_attention(const void* q, int ldq, long long q_batch_stride, const void* k, int ldk, const void* v,
+                             int ldv, void* out, int ldo, int n_prompts, void* stream);
+int llmseg_ln64_gelu(const void* in, void* out, const void* gamma, const void* beta, long long rows, float eps,
+                     void* stream);
+int llmseg_mask_logits(const void* up2, const void* hyper, int n_prompts, float* low_res, void* stream);
+int llmseg_mask_stats(const float* low_res, const int32_t* cand, int n_cand, float threshold, float offset,
+                      int32_t* stats, void* stream);
+int llmseg_box_nms(const float* boxes_sorted, int n, float iou_threshold, int32_t* keep, void* stream);
+int llmseg_mask_soft(const float* low_res, const int32_t* cand, int n_cand, float threshold, void* out, void* stream);
+int llmseg_mask_binarize(const float* low_res, const int32_t* cand, int n_cand, float threshold, uint8_t* out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

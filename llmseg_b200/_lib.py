@@ -96,6 +96,18 @@ def _declare(lib):
                                             C.c_int64, C.c_int64, c_void_p, c_void_p, c_void_p]
     lib.llmseg_dice_bce_loss.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
                                          c_void_p, c_void_p]
+    ll = C.c_longlong
+    lib.llmseg_point_tokens.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]
+    lib.llmseg_tok2img_attention.argtypes = [c_void_p, c_int, c_void_p, c_int, ll, c_void_p, c_int, ll, c_void_p, c_int,
+                                             c_int, c_void_p]
+    lib.llmseg_img2tok_attention.argtypes = [c_void_p, c_int, ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                             c_int, c_void_p]
+    lib.llmseg_ln64_gelu.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, ll, c_float, c_void_p]
+    lib.llmseg_mask_logits.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.llmseg_mask_stats.argtypes = [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p]
+    lib.llmseg_box_nms.argtypes = [c_void_p, c_int, c_float, c_void_p, c_void_p]
+    lib.llmseg_mask_soft.argtypes = [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]
+    lib.llmseg_mask_binarize.argtypes = [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]
 
 
 # every symbol include/llmseg_b200.h declares (tests/test_abi.py checks header <-> .so <-> this list)
@@ -105,6 +117,8 @@ SYMBOLS = [
     "llmseg_patchify", "llmseg_embed_splice", "llmseg_add_rows_bcast", "llmseg_gather_rows", "llmseg_fill_kv_rows", "llmseg_im2col3x3",
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss", "llmseg_selector_losses", "llmseg_lm_cross_entropy",
+    "llmseg_point_tokens", "llmseg_tok2img_attention", "llmseg_img2tok_attention", "llmseg_ln64_gelu", "llmseg_mask_logits",
+    "llmseg_mask_stats", "llmseg_box_nms", "llmseg_mask_soft", "llmseg_mask_binarize",
 ]
 
 

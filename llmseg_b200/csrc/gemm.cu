@@ -684,6 +684,130 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compile-time variants of the CTA-pair kernel's PLAIN epilogue.  ncu on the SAM lin1 GEMM (profiles/r02_summary.md,
+// r02e) had 8.6 % of all samples on instruction-cache misses and 7.9 % on branch resolution inside the one epilogue
+// body that serves every (bias, activation, residual, statistics, staging) combination, with the MMA warp waiting for
+// `tmem_empty` 13 % of its time.  The combinations that carry the step get their own straight-line body:
+//   1  bias + GELU, folded norm, staged TMA store                      SAM / DINOv2 MLP lin1
+//   2  bias + TMA residual + row statistics, staged TMA store          SAM / DINOv2 proj and lin2 (folded norms next)
+//   3  TMA residual, no bias, staged TMA store                         LLaMA o_proj / down_proj, CLIP-less text branch
+//   0  generic (every option a runtime test) — everything else
+// The variants also read TMEM one chunk ahead (the next 32 columns are in flight while this chunk is worked on).
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+struct EpiX {
+  static constexpr bool bias = EPI == 1 || EPI == 2;
+  static constexpr bool gelu = EPI == 1;
+  static constexpr bool res = EPI == 2 || EPI == 3;
+  static constexpr bool stats = EPI == 2;
+};
+
+template <int EPI>
+__device__ __forceinline__ void epi_plain_x(const uint32_t* r, float rs, const uint4* bias4, float2& st_s, float2& st_ss,
+                                            uint8_t* stage_row, int chunk0, int swz, const uint8_t* res_row, int res_swz) {
+  using X = EpiX<EPI>;
+  const float2 rs2 = make_float2(rs, rs);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    float2 v[4];
+    if (X::bias) {
+      const uint4 b = bias4[j >> 3];
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        v[e] = ffma2(make_float2(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1])), rs2, unpack_bf16(bw[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = make_float2(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1]));
+    }
+    if (X::gelu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = gelu2(v[e]);
+    }
+    if (X::res) {
+      const uint4 b = *reinterpret_cast<const uint4*>(res_row + (((j >> 3) ^ res_swz) << 4));
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = fadd2(v[e], unpack_bf16(bw[e]));
+    }
+    if (X::stats) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        st_s = fadd2(st_s, v[e]);
+        st_ss = ffma2(v[e], v[e], st_ss);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0].x, v[0].y);
+    o.y = pack_bf16(v[1].x, v[1].y);
+    o.z = pack_bf16(v[2].x, v[2].y);
+    o.w = pack_bf16(v[3].x, v[3].y);
+    *reinterpret_cast<uint4*>(stage_row + (((chunk0 + (j >> 3)) ^ swz) << 4)) = o;
+  }
+}
+
+// one epilogue warp's share (32 rows x BN/2 columns) of a finished tile, variants 1-3 (pair kernel, BN = 256,
+// N % 64 == 0, rows not scattered, C through staged TMA stores, residual through the TMA landing buffers)
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_plain_fast(const GemmDev& p, uint32_t taddr, int m_blk, int n_blk, int quarter,
+                                                    int chalf, int lane, float rs, const SkOwner sk, uint8_t* epi_stage,
+                                                    const CUtensorMap* tmC, uint8_t* res_stage, uint64_t* res_bar,
+                                                    const CUtensorMap* tmR, uint32_t* res_ph) {
+  using X = EpiX<EPI>;
+  constexpr int NC = BN / 32 / 2;   // 32-column chunks per warp
+  const int row = m_blk * BM + quarter * 32 + lane;
+  const bool live = row < p.M;
+  const int c0 = chalf * NC;
+  float2 st_s = make_float2(0.f, 0.f), st_ss = make_float2(0.f, 0.f);
+  uint32_t r[2][32];
+  tmem_ld32(taddr + c0 * 32, r[0]);
+#pragma unroll
+  for (int ci = 0; ci < NC; ++ci) {
+    const int c = c0 + ci;
+    const int n0 = n_blk * BN + c * 32;
+    uint4 bias4[4];
+    if (X::bias) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) bias4[g] = n0 + g * 8 < p.N ? ldg16(p.bias + n0 + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+    tmem_ld_wait();
+    if (ci + 1 < NC) tmem_ld32(taddr + (c + 1) * 32, r[(ci + 1) & 1]);   // next chunk in flight under this one
+    if (sk.n_peers > 0) sk_accumulate(p, BN, r[ci & 1], c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
+    if (X::res && n0 < p.N) {
+      mbar_wait(&res_bar[ci & 1], (*res_ph >> (ci & 1)) & 1u);
+      *res_ph ^= 1u << (ci & 1);
+    }
+    if ((c & 1) == 0) {
+      // the previous tile store of this warp must have drained the staging tile before it is rewritten
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+    if (live && n0 < p.N)
+      epi_plain_x<EPI>(r[ci & 1], rs, bias4, st_s, st_ss, epi_stage + lane * 128, (c & 1) * 4, lane & 7,
+                       res_stage + (ci & 1) * 2048 + lane * 64, (lane >> 1) & 3);
+    if (X::res) {
+      // every lane has consumed its row of this landing buffer: refill it with the block two steps ahead
+      __syncwarp();
+      const int n0n = n0 + 64;
+      if (lane == 0 && ci + 2 < NC && n0n < p.N) {
+        mbar_expect_tx(&res_bar[ci & 1], 2048);
+        tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, m_blk * BM + quarter * 32);
+      }
+    }
+    if ((c & 1) == 1) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, epi_stage, n_blk * BN + (c - 1) * 32, m_blk * BM + quarter * 32);
+        bulk_commit();
+      }
+    }
+  }
+  if (X::stats && live)
+    p.stats_out[(size_t)row * p.stats_parts_out + n_blk * 2 + chalf] = make_float2(st_s.x + st_s.y, st_ss.x + st_ss.y);
+}
+
 template <int BN, int MODE, bool ROPE>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -879,7 +1003,7 @@ struct Cfg2 {
 // and the extra warps do not buy latency hiding that matters.
 constexpr int G2_EPI_WARPS = 8;
 constexpr int G2_THREADS = 128 + G2_EPI_WARPS * 32;
-template <int BN, int MODE, bool ROPE>
+template <int BN, int MODE, bool ROPE, int EPI = 0>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmDev p) {
@@ -1134,10 +1258,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");
         }
-        epilogue_tile<BN, MODE, ROPE, G2_EPI_WARPS / 4>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
-                                                        smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC,
-                                                        smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2,
-                                                        &tmR, &res_ph);
+        if constexpr (EPI != 0)
+          epilogue_plain_fast<BN, EPI>(p, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
+                                       smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC,
+                                       smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2, &tmR, &res_ph);
+        else
+          epilogue_tile<BN, MODE, ROPE, G2_EPI_WARPS / 4>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
+                                                          smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC,
+                                                          smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2,
+                                                          &tmR, &res_ph);
         if (own.n_peers > 0) {
           asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");  // every reader of the partials is done
           if (warp == 4 && lane == 0)
@@ -1170,10 +1299,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int BN, int MODE, bool ROPE>
+template <int BN, int MODE, bool ROPE, int EPI = 0>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
             const GemmDev& d, int grid, cudaStream_t stream) {
-  auto kern = gemm2_kernel<BN, MODE, ROPE>;
+  auto kern = gemm2_kernel<BN, MODE, ROPE, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
     LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
@@ -1274,6 +1403,11 @@ bool tma_store_enabled() {
 // LLMSEG_GEMM_TMA_RES=0: residual tiles are read with per-lane global loads again (and the ring keeps all stages)
 bool tma_res_enabled() {
   const char* e = getenv("LLMSEG_GEMM_TMA_RES");  // read per call: scripts/gpu_gemm_ab.py flips it between launches
+  return e == nullptr || atoi(e) != 0;
+}
+// LLMSEG_GEMM_EPI=0 routes every PLAIN problem through the generic epilogue again (read per call: A/B runs)
+bool epi_variants_enabled() {
+  const char* e = getenv("LLMSEG_GEMM_EPI");
   return e == nullptr || atoi(e) != 0;
 }
 // LLMSEG_GEMM_STREAMK=0 disables the stream-K tail (A/B measurements)
@@ -1472,6 +1606,18 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
       return rope ? launch2<BN_, LLMSEG_GEMM_QKV, true>(tmA, tmB, tmC, tmR, d, pgrid, stream)              \
                   : launch2<BN_, LLMSEG_GEMM_QKV, false>(tmA, tmB, tmC, tmR, d, pgrid, stream);            \
   }
+    // straight-line epilogue variants (see EpiX): BN = 256, PLAIN, staged TMA store, whole 64-column groups
+    if (bn == 256 && p->mode == LLMSEG_GEMM_PLAIN && d.tma_store && p->N % 64 == 0 && epi_variants_enabled()) {
+      const bool res = p->residual != nullptr;
+      if (p->act == LLMSEG_ACT_GELU && !res && p->stats_out == nullptr && p->bias != nullptr)
+        return launch2<256, LLMSEG_GEMM_PLAIN, false, 1>(tmA, tmB, tmC, tmR, d, pgrid, stream);
+      if (p->act == LLMSEG_ACT_NONE && res && d.tma_res && p->stats_out != nullptr && p->bias != nullptr &&
+          p->row_stats == nullptr)
+        return launch2<256, LLMSEG_GEMM_PLAIN, false, 2>(tmA, tmB, tmC, tmR, d, pgrid, stream);
+      if (p->act == LLMSEG_ACT_NONE && res && d.tma_res && p->stats_out == nullptr && p->bias == nullptr &&
+          p->row_stats == nullptr)
+        return launch2<256, LLMSEG_GEMM_PLAIN, false, 3>(tmA, tmB, tmC, tmR, d, pgrid, stream);
+    }
     if (bn == 256) {
       LLMSEG_GEMM2_DISPATCH(256)
     } else {

@@ -232,6 +232,11 @@ class LisaEngine:
         self.llama = LlamaDecoder(_sub(sd, "model."), self.cfg.llama, self.device, max_seq=max_seq,
                                   lm_head=sd.get("lm_head.weight"))
         self.selector = Selector(_sub(sd, "model."), self.device)
+        # SAM-Everything proposal generation: built when the checkpoint carries SAM's decoder
+        self.proposals = None
+        if "model.visual_model.mask_decoder.iou_token.weight" in sd and self.cfg.image_encoder == "sam":
+            from .proposals import SamProposalGenerator
+            self.proposals = SamProposalGenerator(sd, self.device)
         self.use_cuda_graph = use_cuda_graph
         self.overlap_branches = os.environ.get("LLMSEG_OVERLAP", "1") != "0"
         self._side_stream = torch.cuda.Stream(device=self.device)    # text branch
@@ -278,6 +283,21 @@ class LisaEngine:
         tok = self.dino.patch_tokens(pixel_values.to(self.device, BF16))
         g = self.cfg.dino.grid
         return tok.view(tok.shape[0], g, g, -1).permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def generate_proposals(self, images: Tensor, **kwargs) -> List[dict]:
+        """SAM-Everything on the kernels: images [B,3,1024,1024] -> one record per image whose "segs"
+        ([K,256,256] bf16 soft masks, largest first) is what `model_forward` takes as `sam_segs_list[i]` — the step the
+        reference pre-computes offline with SamAutomaticMaskGenerator (prepare_datasets/*.py) and then re-reads and
+        resizes per sample (utils/sam_mask_reader.py:69-113, utils/dataset.py:620-622).  Needs the SAM prompt-encoder /
+        mask-decoder weights in the state dict (`model.visual_model.{prompt_encoder,mask_decoder}.*`).
+        kwargs: see proposals.SamProposalGenerator.generate."""
+        if self.cfg.image_encoder != "sam":
+            raise RuntimeError("proposal generation runs on the SAM ViT-H features (image_encoder='sam')")
+        if self.proposals is None:
+            raise RuntimeError("the state dict this model was built from holds no SAM prompt-encoder / mask-decoder weights")
+        tok = self.sam.forward(images.to(self.device, BF16))
+        return [self.proposals.generate(tok[i].contiguous(), **kwargs) for i in range(tok.shape[0])]
 
     @torch.no_grad()
     def model_forward(self, images: Tensor, images_clip: Tensor, input_ids: Tensor, labels: Optional[Tensor] = None,
@@ -694,6 +714,8 @@ class LISAForCausalLM(torch.nn.Module):
         enc = "model.visual_model.image_encoder." if e.cfg.image_encoder == "sam" else "model.visual_model_dinov2."
         keep = ("model.vision_tower.", "model.mm_projector.", "model.embed_tokens.", "model.layers.", "model.norm.",
                 "model.text_hidden_fcs.", "model.lisa_", "lm_head.", enc)
+        if e.proposals is not None:
+            keep += ("model.visual_model.prompt_encoder.", "model.visual_model.mask_decoder.")
         for k in (self._ref_sd or {}):
             kk = k[len("base_model.model."):] if k.startswith("base_model.model.") else k
             if kk.startswith(keep):

@@ -479,3 +479,111 @@ def dice_bce_loss(logits: torch.Tensor, targets: torch.Tensor, num_masks: float)
     check(_lib.lib().llmseg_dice_bce_loss(logits.data_ptr(), targets.data_ptr(), n, hw, float(num_masks),
                                           ws.data_ptr(), out.data_ptr(), _stream()), "dice_bce_loss")
     return out
+
+
+# ---- SAM-Everything proposal generation (csrc/amg.cu; include/llmseg_b200.h) ---------------------------------
+def _req_f32(*ts):
+    for t in ts:
+        if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError("expected a contiguous fp32 CUDA tensor")
+
+
+def _req_i32(t):
+    if t is not None and not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise TypeError("expected a contiguous int32 CUDA tensor")
+
+
+def point_tokens(points: torch.Tensor, gauss: torch.Tensor, out_tokens: torch.Tensor, point_embed: torch.Tensor,
+                 not_a_point: torch.Tensor, img_size: float) -> torch.Tensor:
+    """points fp32 [P,2] (x, y) -> decoder tokens bf16 [P*7, 256] (iou, 4 mask tokens, point, padding point)."""
+    _req_f32(points, gauss)
+    _req_bf16(out_tokens, point_embed, not_a_point)
+    P = points.shape[0]
+    out = torch.empty((P * 7, 256), dtype=torch.bfloat16, device=points.device)
+    check(_lib.lib().llmseg_point_tokens(points.data_ptr(), P, gauss.data_ptr(), out_tokens.data_ptr(),
+                                         point_embed.data_ptr(), not_a_point.data_ptr(), float(img_size), out.data_ptr(),
+                                         _stream()), "point_tokens")
+    return out
+
+
+def tok2img_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_prompts: int, shared_kv: bool) -> torch.Tensor:
+    """q [P*7, 128] (view), k / v [4096 or P*4096, 128] (column views of a wider buffer allowed) -> [P*7, 128]."""
+    _req_bf16(q, k, v)
+    out = torch.empty((n_prompts * 7, 128), dtype=torch.bfloat16, device=q.device)
+    kbs = 0 if shared_kv else 4096 * k.stride(0)
+    vbs = 0 if shared_kv else 4096 * v.stride(0)
+    check(_lib.lib().llmseg_tok2img_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), kbs, v.data_ptr(),
+                                              v.stride(0), vbs, out.data_ptr(), out.stride(0), n_prompts, _stream()),
+          "tok2img_attention")
+    return out
+
+
+def img2tok_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_prompts: int, shared_q: bool) -> torch.Tensor:
+    """q [4096 or P*4096, 128] (view), k / v [P*7, 128] -> [P*4096, 128]."""
+    _req_bf16(q, k, v)
+    out = torch.empty((n_prompts * 4096, 128), dtype=torch.bfloat16, device=q.device)
+    qbs = 0 if shared_q else 4096 * q.stride(0)
+    check(_lib.lib().llmseg_img2tok_attention(q.data_ptr(), q.stride(0), qbs, k.data_ptr(), k.stride(0), v.data_ptr(),
+                                              v.stride(0), out.data_ptr(), out.stride(0), n_prompts, _stream()),
+          "img2tok_attention")
+    return out
+
+
+def ln64_gelu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """In place on a contiguous bf16 buffer viewed as rows of 64: GELU(LayerNorm(row))."""
+    _req_bf16(x, gamma, beta)
+    assert x.is_contiguous() and x.numel() % 64 == 0
+    check(_lib.lib().llmseg_ln64_gelu(x.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x.numel() // 64,
+                                      float(eps), _stream()), "ln64_gelu")
+    return x
+
+
+def mask_logits(up2: torch.Tensor, hyper: torch.Tensor, n_prompts: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """up2 bf16 [P*16384, 128], hyper bf16 [P,4,32] -> low-res logits fp32 [P,3,256,256]."""
+    _req_bf16(up2, hyper)
+    assert up2.is_contiguous() and hyper.is_contiguous() and up2.shape == (n_prompts * 16384, 128)
+    if out is None:
+        out = torch.empty((n_prompts, 3, 256, 256), dtype=torch.float32, device=up2.device)
+    check(_lib.lib().llmseg_mask_logits(up2.data_ptr(), hyper.data_ptr(), n_prompts, out.data_ptr(), _stream()), "mask_logits")
+    return out
+
+
+def mask_stats(low_res: torch.Tensor, cand: Optional[torch.Tensor] = None, threshold: float = 0.0,
+               offset: float = 1.0) -> torch.Tensor:
+    """low_res fp32 [n,256,256] -> int32 [n,8] = {area, #(>t+o), #(>t-o), 1023-x0, 1023-y0, x1, y1, 0}."""
+    _req_f32(low_res)
+    _req_i32(cand)
+    n = low_res.shape[0] if cand is None else cand.numel()
+    stats = torch.empty((n, 8), dtype=torch.int32, device=low_res.device)
+    check(_lib.lib().llmseg_mask_stats(low_res.data_ptr(), _ptr(cand), n, float(threshold), float(offset), stats.data_ptr(),
+                                       _stream()), "mask_stats")
+    return stats
+
+
+def box_nms(boxes_sorted: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """boxes fp32 [n,4] XYXY sorted by score (descending) -> keep int32 [n]."""
+    _req_f32(boxes_sorted)
+    keep = torch.empty(boxes_sorted.shape[0], dtype=torch.int32, device=boxes_sorted.device)
+    check(_lib.lib().llmseg_box_nms(boxes_sorted.data_ptr(), boxes_sorted.shape[0], float(iou_threshold), keep.data_ptr(),
+                                    _stream()), "box_nms")
+    return keep
+
+
+def mask_soft(low_res: torch.Tensor, cand: torch.Tensor, threshold: float = 0.0) -> torch.Tensor:
+    """-> bf16 [n,256,256]: antialiased 1024 -> 256 resize of the binarised 4x up-sampled masks of the candidates."""
+    _req_f32(low_res)
+    _req_i32(cand)
+    out = torch.empty((cand.numel(), 256, 256), dtype=torch.bfloat16, device=low_res.device)
+    check(_lib.lib().llmseg_mask_soft(low_res.data_ptr(), cand.data_ptr(), cand.numel(), float(threshold), out.data_ptr(),
+                                      _stream()), "mask_soft")
+    return out
+
+
+def mask_binarize(low_res: torch.Tensor, cand: torch.Tensor, threshold: float = 0.0) -> torch.Tensor:
+    """-> uint8 [n,1024,1024] binary masks of the candidates."""
+    _req_f32(low_res)
+    _req_i32(cand)
+    out = torch.empty((cand.numel(), 1024, 1024), dtype=torch.uint8, device=low_res.device)
+    check(_lib.lib().llmseg_mask_binarize(low_res.data_ptr(), cand.data_ptr(), cand.numel(), float(threshold),
+                                          out.data_ptr(), _stream()), "mask_binarize")
+    return out

@@ -220,28 +220,35 @@ def nms(boxes: Tensor, scores: Tensor, thr: float) -> Tensor:
 
 def generate(image_embedding: Tensor, sd: Dict[str, Tensor], *, points_per_side: int = 32, points_per_batch: int = 64,
              pred_iou_thresh: float = 0.88, stability_score_thresh: float = 0.95, stability_score_offset: float = 1.0,
-             box_nms_thresh: float = 0.7, size: int = IMG) -> dict:
+             box_nms_thresh: float = 0.7, size: int = IMG, decoded: Optional[Tuple[Tensor, Tensor]] = None) -> dict:
     """`SamAutomaticMaskGenerator.generate` (automatic_mask_generator.py:141-322) with crop_n_layers = 0 and
     min_mask_region_area = 0 (the class defaults) on the features of one square image:
-    -> {"masks" bool [M,size,size], "boxes" XYXY, "iou_preds", "stability", "points", "areas"} after the box NMS."""
-    pts = point_grid(points_per_side, size).to(image_embedding.device)
-    acc: Dict[str, List[Tensor]] = {k: [] for k in ("masks", "iou_preds", "stability", "points")}
+    -> {"masks" bool [M,size,size], "boxes" XYXY, "iou_preds", "stability", "points", "areas", "candidates"} after the
+    box NMS ("candidates": index 3 * prompt + mask of every record).  decoded = (low-res logits [P,3,256,256], IoU
+    predictions [P,3]) replaces the mask decoder (tests: post-processing of another implementation's logits)."""
+    pts = point_grid(points_per_side, size).to(image_embedding.device if decoded is None else decoded[0].device)
+    acc: Dict[str, List[Tensor]] = {k: [] for k in ("masks", "iou_preds", "stability", "points", "candidates")}
     for i in range(0, pts.shape[0], points_per_batch):
         p = pts[i:i + points_per_batch]
-        low, iou = predict_points(image_embedding, p, sd)
+        if decoded is None:
+            low, iou = predict_points(image_embedding, p, sd)
+        else:
+            low, iou = decoded[0][i:i + points_per_batch], decoded[1][i:i + points_per_batch]
         logits = upsample_logits(low, size).flatten(0, 1)                  # [3P, size, size]
         iou = iou.flatten(0, 1).float()
         rep = p.repeat_interleave(3, dim=0)       # MaskData repeats the points per mask (np.repeat, :283)
+        cid = torch.arange(3 * i, 3 * i + logits.shape[0], device=logits.device)
         keep = iou > pred_iou_thresh if pred_iou_thresh > 0.0 else torch.ones_like(iou, dtype=torch.bool)
-        logits, iou, rep = logits[keep], iou[keep], rep[keep]
+        logits, iou, rep, cid = logits[keep], iou[keep], rep[keep], cid[keep]
         stab = stability_score(logits, 0.0, stability_score_offset)
         if stability_score_thresh > 0.0:
             keep = stab >= stability_score_thresh
-            logits, iou, rep, stab = logits[keep], iou[keep], rep[keep], stab[keep]
+            logits, iou, rep, stab, cid = logits[keep], iou[keep], rep[keep], stab[keep], cid[keep]
         acc["masks"].append(logits > 0.0)
         acc["iou_preds"].append(iou)
         acc["stability"].append(stab)
         acc["points"].append(rep)
+        acc["candidates"].append(cid)
     data = {k: torch.cat(v, dim=0) for k, v in acc.items()}
     data["boxes"] = mask_to_box(data["masks"])
     keep = nms(data["boxes"], data["iou_preds"], box_nms_thresh).to(data["boxes"].device)

@@ -156,3 +156,32 @@ def test_host_pos_embed_resampling_matches_oracle(golden_dir):
         mine = _resample_pos_embed(pe, 9, off)
         assert torch.allclose(mine, dinov2.interpolate_pos_embed(pe, 9, off)[0], atol=1e-6)
     assert torch.equal(_resample_pos_embed(pe, 5, 0.1), pe[0])
+
+
+def test_sam_amg_oracle_matches_reference_golden(golden_dir):
+    """oracle/sam_amg.py against the outputs of the reference's own PromptEncoder / MaskDecoder /
+    SamAutomaticMaskGenerator (tests/golden/sam_amg.pt, written by oracle/make_golden.py): decoder logits and IoU
+    predictions for 5 point prompts, the generator's records for an 8 x 8 point grid at two NMS thresholds, the soft
+    256 x 256 proposals of the largest masks, and the suppression rule against torchvision's batched_nms."""
+    from oracle import sam_amg
+    fx = torch.load(golden_dir / "sam_amg.pt", weights_only=False)
+    sd = sam_amg.random_state_dict(fx["seed"])
+    assert abs(sum(float(v.double().abs().sum()) for v in sd.values()) - fx["weights_checksum"]) < 1e-6 * fx["weights_checksum"]
+    emb = fx["emb"].float()
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    with torch.no_grad():
+        low, iou = sam_amg.predict_points(emb, fx["points"], sd)
+    # the fixture stores the embedding in bf16 and the logits in fp16: compare at that resolution
+    assert (iou - fx["iou"]).abs().max().item() < 2e-2
+    assert (low[:2] - fx["low_res"].float()).abs().max().item() < 0.02 * float(fx["low_res"].float().abs().max())
+    assert torch.equal(sam_amg.nms(fx["nms_boxes"], fx["nms_scores"], 0.7), fx["nms_keep"])
+    run = fx["runs"]["nms07"]
+    with torch.no_grad():
+        data = sam_amg.generate(emb, sd, **run["kw"])
+    # (bf16 embedding: a borderline candidate may flip; the default-threshold run keeps the single dominant mask)
+    assert data["masks"].shape[0] == run["n_masks"]
+    assert (data["areas"] - run["ref_area"]).abs().max().item() <= 0.01 * float(run["ref_area"].max())
+    soft, order = sam_amg.llmseg_proposals(data, top_k=50)
+    assert soft.shape == (run["n_masks"], 256, 256) and float(soft.min()) >= 0.0 and float(soft.max()) <= 1.0 + 1e-6
+    lo, w = sam_amg.aa_downsample_weights(1024, 256)
+    assert int(lo[0]) == 0 and int(lo[1]) == 2 and int(lo[255]) == 1018 and abs(float(w[7].sum()) - 1.0) < 1e-12
