@@ -419,7 +419,12 @@ def main():
         ms = sum(v[2] for v in gemm_groups.values())
         steps_probed = max(1, min(args.steps, 3))
         gemm_all = {"achieved": round(fl / ms / 1e9, 1), "unit": "TFLOP/s", "frac": round(fl / ms / 1e9 / peak, 4),
-                    "ms_per_step": round(ms / steps_probed, 2), "launches_per_step": sum(v[0] for v in gemm_groups.values()) // steps_probed}
+                    "ms_per_step": round(ms / steps_probed, 2), "launches_per_step": sum(v[0] for v in gemm_groups.values()) // steps_probed,
+                    # every (shape, epilogue) group that takes >= 2 % of the GEMM time, largest first: the same
+                    # kernel family at its other shapes, so that `roofline` above is not the only figure on record
+                    "groups": [{"shape": k, "ms_per_step": round(v[2] / steps_probed, 3), "achieved": round(v[1] / v[2] / 1e9, 1),
+                                "frac": round(v[1] / v[2] / 1e9 / peak, 4)}
+                               for k, v in sorted(gemm_groups.items(), key=lambda kv: -kv[1][2]) if v[2] >= 0.02 * ms]}
     # "Achieved fraction of the attention roofline" (BASELINE north_star): every kernel of the fused attention
     # paths — Q/K/V projection GEMMs, rel-pos prep, padding keys, the attention kernels — against the algorithmic
     # FLOPs of those paths (QKV GEMMs + QK^T + PV + rel-pos, causal pairs counted once).

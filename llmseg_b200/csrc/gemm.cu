@@ -625,6 +625,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       }
       if (live && col < p.N) epi_qkv_rope(p, lo, hi, out_row, col);
     }
+  } else if (MODE == LLMSEG_GEMM_SWIGLU || MODE == LLMSEG_GEMM_QKV) {
+    // SwiGLU / Q-K-V split: straight-line over the warp's chunks, TMEM read one chunk ahead (the next 32 columns are
+    // in flight while this chunk is transformed and stored) — same restructuring as epilogue_plain_fast
+    constexpr int NC = BN / 32 / NP;
+    const int c0 = chalf * NC;
+    uint32_t r[2][32];
+    tmem_ld32(taddr + c0 * 32, r[0]);
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+      const int c = c0 + ci;
+      const int n0 = n_blk * BN + c * 32;
+      EpiPrefetch pf;
+      if (MODE == LLMSEG_GEMM_QKV) epi_prefetch(p, pf, 0, n0, live);
+      tmem_ld_wait();
+      if (ci + 1 < NC) tmem_ld32(taddr + (c + 1) * 32, r[(ci + 1) & 1]);
+      if (sk.n_peers > 0) sk_accumulate(p, BN, r[ci & 1], c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
+      if (fold) row_scale(r[ci & 1], rs);
+      if (live && n0 < p.N) {
+        if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r[ci & 1], out_row, n0);
+        else epi_qkv(p, r[ci & 1], out_row, n0, pf);
+      }
+    }
   } else {
     // Residual through TMA (pair kernel): the warp's 32-row x 32-column residual blocks land in two 2 KB
     // 64B-swizzled buffers, two blocks ahead of their use; ncu had the epilogue warps parked ~30 % of their

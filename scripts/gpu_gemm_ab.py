@@ -31,6 +31,19 @@ for label, M, N, K in (("sam lin1", 32768, 5120, 1280), ("dino fc1", 32776, 4096
     os.environ.pop(name, None)
     fl = 2.0 * M * N * K
     print(f"{label:13s} {M}x{N}x{K}: {name}=0 {best['0']:7.1f} us ({fl/best['0']/1e6:5.0f} TF/s)   =1 {best['1']:7.1f} us ({fl/best['1']/1e6:5.0f} TF/s)   {100*(best['0']/best['1']-1):+5.1f} %", flush=True)
+# residual, no bias, no statistics: LLaMA o_proj / down_proj with the text branch's norms un-folded (epilogue variant 3)
+for label, M, N, K in (("llama o_proj*", 2552, 4096, 4096), ("llama down*", 2552, 4096, 11008)):
+    a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    x = torch.randn(M, N, device=dev).bfloat16()
+    fn = lambda: ops.gemm(a, w, None, residual=x, out=x)
+    best = {"0": 1e9, "1": 1e9}
+    for r in range(rounds):
+        for v in ("0", "1"):
+            os.environ[name] = v
+            best[v] = min(best[v], t(fn))
+    os.environ.pop(name, None)
+    fl = 2.0 * M * N * K
+    print(f"{label:13s} {M}x{N}x{K}: {name}=0 {best['0']:7.1f} us ({fl/best['0']/1e6:5.0f} TF/s)   =1 {best['1']:7.1f} us ({fl/best['1']/1e6:5.0f} TF/s)   {100*(best['0']/best['1']-1):+5.1f} %", flush=True)
 for label, M, N, K, rms in cases:
     a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
     b = None if rms else torch.randn(N, device=dev).bfloat16()

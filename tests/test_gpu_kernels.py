@@ -91,6 +91,49 @@ def test_gemm_streamk_tail(cuda_lib, M, N, K, mode):
         assert (sk - ref).abs().max().item() <= _ulp_tol(ref)
 
 
+@pytest.mark.parametrize("variant", ["gelu", "res_stats", "res"])
+def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
+    """The straight-line epilogue variants of the CTA-pair kernel (csrc/gemm.cu EpiX 1-3: bias + GELU (+ folded norm),
+    bias + TMA residual + row statistics, TMA residual alone) against the generic epilogue on the same problem —
+    bit-equal outputs and statistics (same arithmetic, only the control flow is resolved at compile time) — and
+    against torch within the usual GEMM bound.  M x N = 2100 x 1280: 17 row tiles, a ragged last one."""
+    from llmseg_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(21)
+    M, N, K = 2100, 1280, 640
+    a = _bf(torch.randn(M, K, generator=g, device=DEV))
+    w = _bf(torch.randn(N, K, generator=g, device=DEV) / K ** 0.5)
+    b = _bf(torch.randn(N, generator=g, device=DEV))
+    x0 = _bf(torch.randn(M, N, generator=g, device=DEV))
+
+    def run():
+        if variant == "gelu":
+            st = ops.norm_stats(a, 1e-6)
+            return ops.gemm(a, w, b, act="gelu", row_stats=st), None
+        x = x0.clone()
+        if variant == "res_stats":
+            so = ops.gemm_stats_buffer(M, N, M, 1e-6)
+            ops.gemm(a, w, b, residual=x, out=x, stats_out=so)
+            return x, so.final.clone()
+        ops.gemm(a, w, None, residual=x, out=x)
+        return x, None
+    monkeypatch.setenv("LLMSEG_GEMM_EPI", "0")
+    y0, s0 = run()
+    monkeypatch.setenv("LLMSEG_GEMM_EPI", "1")
+    y1, s1 = run()
+    assert torch.equal(y0, y1)
+    if s0 is not None:
+        assert torch.equal(s0, s1)
+    af, wf = a.float(), w.float()
+    if variant == "gelu":
+        mean, var = af.mean(1, keepdim=True), af.var(1, unbiased=False, keepdim=True)
+        ref = torch.nn.functional.gelu((af * torch.rsqrt(var + 1e-6)) @ wf.T + b.float())
+    elif variant == "res_stats":
+        ref = af @ wf.T + b.float() + x0.float()
+    else:
+        ref = af @ wf.T + x0.float()
+    assert (y1.float() - ref).abs().max().item() <= 2 ** -7 * float(ref.abs().max()) + 2e-2
+
+
 def test_gemm_swiglu(cuda_lib):
     from llmseg_b200 import ops
     g = torch.Generator().manual_seed(1)
