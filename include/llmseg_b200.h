@@ -11,7 +11,10 @@
  *   - all pointers are DEVICE pointers unless the name says host; bf16 = 2-byte bfloat16
  *   - nothing allocates or frees caller memory; work is enqueued on `stream` (a cudaStream_t
  *     passed as void*) and is asynchronous
- *   - thread-safe for distinct streams; no global mutable state
+ *   - thread-safe for distinct streams.  Process-wide state is limited to: the launch counter behind
+ *     llmseg_launch_count() (atomic), the thread-local text behind llmseg_last_error(), one-time function
+ *     attributes (dynamic shared-memory opt-in per kernel) and the LLMSEG_* environment switches, which are read
+ *     once or per call (DESIGN.md lists them) — nothing a concurrent caller on another stream can observe changing
  *   - sm_100 only: any other device returns LLMSEG_EARCH (there is no CPU / other-arch fallback)
  */
 #ifndef LLMSEG_B200_H_

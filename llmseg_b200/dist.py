@@ -43,6 +43,9 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_PACK_TEMPLATES: dict = {}
+
+
 def packed_width(k_max: int, c_cap: int = 1) -> int:
     return (c_cap + 1) * k_max + 3
 
@@ -56,17 +59,31 @@ def pack_logits(sim: Tensor, iou: Tensor, best: Tensor, ks: List[int], k_max: in
     the fixed-size all-gather (pass sim=None with ks=[] for a rank that owns no image)."""
     dev = device if sim is None else sim.device
     w = packed_width(k_max, c_cap)
-    out = torch.zeros((b_max, w), dtype=torch.float32, device=dev)
-    out[:, :c_cap * k_max] = float("-inf")
-    out[:, w - 2] = -1.0
     b = len(ks)
+    convs = [1] * b if convs is None else [int(c) for c in convs]
+    # the padding / meta columns depend only on the shapes: built once per shape and cloned, so that a step issues no
+    # host-to-device copy (a pageable H2D copy blocks the CPU until the stream has drained: one forward of run-ahead lost)
+    key = (tuple(ks), tuple(convs), k_max, b_max, c_cap, str(dev))
+    tmpl = _PACK_TEMPLATES.get(key)
+    if tmpl is None:
+        if b > b_max or (b and max(ks) > k_max):
+            raise ValueError(f"pack_logits: {b} images / K={max(ks)} exceed the packed shape (b_max={b_max}, k_max={k_max})")
+        if b and max(convs) > c_cap:
+            raise ValueError(f"pack_logits: conversations per image {convs} exceed c_cap={c_cap}")
+        t = torch.zeros((b_max, w), dtype=torch.float32)
+        t[:, :c_cap * k_max] = float("-inf")
+        t[:, w - 2] = -1.0
+        if b:
+            t[:b, w - 2] = torch.tensor(ks, dtype=torch.float32)
+            t[:b, w - 1] = torch.tensor(convs, dtype=torch.float32)
+        if len(_PACK_TEMPLATES) > 64:
+            _PACK_TEMPLATES.clear()
+        tmpl = _PACK_TEMPLATES[key] = t.to(dev)
+    out = tmpl.clone()
     if b == 0:
         return out
-    if b > b_max or max(ks) > k_max:
-        raise ValueError(f"pack_logits: {b} images / K={max(ks)} exceed the packed shape (b_max={b_max}, k_max={k_max})")
-    convs = [1] * b if convs is None else [int(c) for c in convs]
-    if max(convs) > c_cap or sum(convs) != sim.shape[0]:
-        raise ValueError(f"pack_logits: conversations per image {convs} vs {sim.shape[0]} similarity rows, c_cap={c_cap}")
+    if sum(convs) != sim.shape[0]:
+        raise ValueError(f"pack_logits: conversations per image {convs} vs {sim.shape[0]} similarity rows")
     k = min(sim.shape[1], k_max)
     if convs == [1] * b:
         out[:b, :k] = sim[:, :k]
@@ -78,8 +95,6 @@ def pack_logits(sim: Tensor, iou: Tensor, best: Tensor, ks: List[int], k_max: in
                 r += 1
     out[:b, c_cap * k_max:c_cap * k_max + k] = iou[:, :k]
     out[:b, w - 3] = best.to(torch.float32)
-    out[:b, w - 2] = torch.tensor(ks, dtype=torch.float32, device=dev)
-    out[:b, w - 1] = torch.tensor(convs, dtype=torch.float32, device=dev)
     return out
 
 

@@ -41,8 +41,10 @@ FOLD_NORM_TEXT = _FOLD in ("all", "1")
 # weights — and it moves bf16 rounding points (the statistics come from the bf16 rows instead of the fp32 epilogue).
 LAST_LAYER_ROWS = os.environ.get("LLMSEG_LAST_LAYER_ROWS", "0") != "0"
 # SAM windowed layers: private k / vT buffers per layer with the constant padding rows written once (see SamEncoder).
+# The buffers (5.7 GB at batch 8) belong to the CALLER's plan (`private` argument of SamEncoder.forward): they are freed
+# when that plan — and the CUDA graph that bakes their addresses in — is evicted, instead of accumulating per batch size.
 KV_PREFILL = os.environ.get("LLMSEG_KV_PREFILL", "1") != "0"
-KV_PREFILL_MAX_BYTES = 24 << 30
+KV_PREFILL_MAX_BYTES = 8 << 30
 
 
 def _dev(t: Tensor, device) -> Tensor:
@@ -128,7 +130,6 @@ class SamEncoder:
         self.kext_glb = ops.make_kext(64, device)
         self.scratch = _Scratch(device)
         self._maps: Dict[int, tuple] = {}
-        self._kv_filled = set()   # (layer, windows) whose private k / vT padding rows already hold the bias
 
     def _window_maps(self, B: int):
         """win_src[r]: image token feeding window row r (or -1 = zero padding token);
@@ -155,8 +156,10 @@ class SamEncoder:
             self._maps[B] = (m.to(dev), nw * nw, tok2win.to(dev), pad_wins.to(dev))
         return self._maps[B]
 
-    def forward(self, images: Tensor) -> Tensor:
-        """[B,3,1024,1024] bf16 -> token-major neck output [B, 4096, out_chans] bf16 (NHWC)."""
+    def forward(self, images: Tensor, private: Optional[dict] = None) -> Tensor:
+        """[B,3,1024,1024] bf16 -> token-major neck output [B, 4096, out_chans] bf16 (NHWC).
+        private: a dict owned by the caller's per-batch-size plan; with it (and LLMSEG_KV_PREFILL) every windowed
+        layer keeps its own k / vT buffers there, padding rows written once."""
         cfg = self.cfg
         B = images.shape[0]
         g, D, H, hd = cfg.grid, cfg.embed_dim, self.heads, self.hd
@@ -185,10 +188,16 @@ class SamEncoder:
                 # KV_PREFILL every windowed layer owns its k / vT buffers (2 x 102 MB per layer at batch 8, 5.7 GB
                 # for the 28 layers — HBM is not the scarce resource here), the padding rows are written once and
                 # the per-forward fill_kv_rows launch (35 us x 28) disappears from the step.
-                prefill = KV_PREFILL and 2 * nb * H * sw_pad * hd * 2 * len(self.blocks) <= KV_PREFILL_MAX_BYTES
-                tag = str(li) if prefill else ""
-                k = self.scratch.zeros("k" + tag, nb * H, sw_pad, hd)
-                vt = self.scratch.zeros("vt" + tag, nb * H, hd, sw_pad)
+                prefill = (private is not None and KV_PREFILL and
+                           2 * nb * H * sw_pad * hd * 2 * len(self.blocks) <= KV_PREFILL_MAX_BYTES)
+                if prefill:
+                    if ("k", li) not in private:
+                        private[("k", li)] = torch.zeros((nb * H, sw_pad, hd), dtype=BF16, device=self.device)
+                        private[("vt", li)] = torch.zeros((nb * H, hd, sw_pad), dtype=BF16, device=self.device)
+                    k, vt = private[("k", li)], private[("vt", li)]
+                else:
+                    k = self.scratch.zeros("k", nb * H, sw_pad, hd)
+                    vt = self.scratch.zeros("vt", nb * H, hd, sw_pad)
                 qext = self.scratch.zeros("qext_w", nb * H, sw_pad, 32)
                 if self.fold:
                     wq, bq = blk["f_qkv"]
@@ -200,11 +209,11 @@ class SamEncoder:
                     ops.gemm_qkv(h, blk["w_qkv"], blk["b_qkv"], q, k, vt, heads=H, head_dim=hd, seq_in=sw,
                                  seq_pad=sw_pad, row_map=tok2win)
                     o = h  # reuse the LN output buffer for the attention output (same shape)
-                if not (prefill and (tag, nb) in self._kv_filled):
+                if not (prefill and ("filled", li) in private):
                     ops.fill_kv_rows(k, vt, blk["b_qkv"], win_map, batch=nb, heads=H, head_dim=hd, seq_in=sw,
                                      seq_pad=sw_pad, seq_ids=pad_wins)
                     if prefill and not torch.cuda.is_current_stream_capturing():
-                        self._kv_filled.add((tag, nb))
+                        private[("filled", li)] = True
                 ops.relpos_prep(q, blk["rel_hw"], bh=nb * H, seq=sw, seq_pad=sw_pad, head_dim=hd, grid=ws,
                                 inv_scale=1.0 / scale, qext=qext)
                 ops.attention(q, k, vt, o, batch=nb, heads=H, head_dim=hd, seq=sw, seq_pad=sw_pad, scale=scale,
@@ -379,7 +388,7 @@ class Dinov2Encoder:
                           rows_out=B * (T - 1))
         return y.view(B, T - 1, -1)
 
-    def forward(self, images: Tensor) -> Tensor:
+    def forward(self, images: Tensor, private: Optional[dict] = None) -> Tensor:
         """[B,3,S,S] bf16 -> token-major `lisa_dino_conv` output [B, g*g, out_chans] bf16 (NHWC)."""
         x, stA, B, T = self._blocks(images)
         if self.fold:

@@ -492,6 +492,7 @@ class LisaEngine:
             (B,) = key
             S = self.image_size
             plan["images"] = torch.empty((B, 3, S, S), dtype=BF16, device=dev)
+            plan["private"] = {}     # per-plan encoder buffers (SAM k / vT with pre-written padding rows)
         elif stage == "text":
             N, Tb, n_clip, identity = key
             Sc = cfg.clip.image_size
@@ -528,7 +529,7 @@ class LisaEngine:
             if use_graph:
                 ip["graph"].replay()
                 return ip["out"]
-            return self.image_encoder.forward(ip["images"])
+            return self.image_encoder.forward(ip["images"], private=ip["private"])
 
         if self.overlap_branches:
             side = self._side_stream
@@ -606,7 +607,7 @@ class LisaEngine:
         if tp["graph"] is None:
             cap(tp, self._side_stream, lambda: self._text_branch(tp))
         if ip["graph"] is None:
-            cap(ip, self._cap_stream, lambda: self.image_encoder.forward(ip["images"]))
+            cap(ip, self._cap_stream, lambda: self.image_encoder.forward(ip["images"], private=ip["private"]))
         if sp["graph"] is None or sp.get("graph_inputs") != ip["out"].data_ptr():
             # the selector graph bakes in the address of the image features it was captured against (one image
             # plan per batch size: this only changes when that plan was evicted and rebuilt) and reads the text

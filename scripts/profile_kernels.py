@@ -27,6 +27,13 @@ if which == "attn_global":
     kext = ops.make_kext(64, dev)
     for _ in range(iters):
         ops.attention(q, k, vt, out, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale, qext=qext, kext=kext, row_bias=rb, ext_cols=64)
+elif which == "attn_llama":      # LLaMA-7B causal attention at T = 319 (64-token prompts): 32 heads x 128, batch B
+    Hh, hdd, S = 32, 128, 319
+    Sp = (S + 7) // 8 * 8
+    q = torch.randn(B * Hh, Sp, hdd, device=dev).bfloat16(); k = torch.randn_like(q); vt = torch.randn(B * Hh, hdd, Sp, device=dev).bfloat16()
+    out = torch.empty(B * S, Hh * hdd, device=dev, dtype=torch.bfloat16)
+    for _ in range(iters):
+        ops.attention(q, k, vt, out, batch=B, heads=Hh, head_dim=hdd, seq=S, seq_pad=Sp, scale=hdd ** -0.5, causal=True)
 elif which == "attn_window":
     S, S_pad, nb = 196, 200, 25 * B
     q, k, vt = qkv_bufs(nb, S, S_pad)
