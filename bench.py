@@ -319,6 +319,30 @@ def main():
         b1 = {"workload": "configs[1]: batch=1 full fwd, host inputs", "ms_per_image": round(b1_ms, 3),
               "value": round(1e3 / b1_ms, 3), "unit": "images/s"}
 
+    # SAM-Everything proposal generation on the same SAM encoder: features -> prompt encoder -> mask
+    # decoder over the reference's default 32 x 32 point grid -> statistics / filters / NMS -> top-50 soft proposals.
+    # Timed per image with the host-side filter / sort and its device syncs INSIDE the region (rank 0, N = 1).
+    prop = None
+    if rank == 0 and world == 1 and args.encoder == "sam" and not args.no_extra_configs:
+        from llmseg_b200 import proposals as lsp
+        gen = lsp.SamProposalGenerator(synthetic.sam_decoder_state_dict(8, dev), dev)
+        tok = model.sam.forward(inp["images"][:1])[0].contiguous()
+        kw = dict(pred_iou_thresh=-10.0, stability_score_thresh=0.5, box_nms_thresh=0.7)   # random weights: keep the
+        gen.generate(tok, **kw)                                                            # filters busy, not empty
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rec = gen.generate(tok, **kw)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / 3 * 1e3
+        prop = {"workload": "SAM-Everything on one image's SAM features: 1024 point prompts x 3 masks (32 x 32 grid, "
+                            "batches of 256), filters + box NMS + top-50 soft proposals [K,256,256]",
+                "ms_per_image": round(ms, 2), "images_per_s": round(1e3 / ms, 2), "launches_per_image": (_lib.launch_count() - n0) // 3,
+                "proposals": int(rec["segs"].shape[0]), "masks_after_nms": rec["n_masks"]}
+        del gen, tok
+        torch.cuda.empty_cache()
+
     # dominant-kernel timing: the same steps launched eagerly (graph nodes cannot carry timing events) with
     # CUDA events, on the launching stream, around every GEMM launch (the tcgen05 GEMM kernel is ~75 % of
     # the step) and every SAM global-attention launch.
@@ -414,7 +438,11 @@ def main():
     if gemm_groups:
         # dominant (kernel, shape): the GEMM group with the largest share of the step
         top = max(gemm_groups, key=lambda k: gemm_groups[k][2])
-        roof = roof_of(top, f"gemm2_kernel (tcgen05 CTA-pair GEMM): {top}", "gemm_mlp1_b8" if "5120x1280" in top else "")
+        tkey = "gemm_mlp1_b8" if "5120x1280" in top else ("gemm_swiglu_b8" if "swiglu" in top and "22016x4096" in top else "")
+        roof = roof_of(top, f"gemm2_kernel (tcgen05 CTA-pair GEMM): {top}", tkey)
+        if traffic_db.get(tkey, {}).get("tensor_pipe_pct") is not None:
+            roof["tensor_pipe_pct"] = traffic_db[tkey]["tensor_pipe_pct"]
+            roof["traffic_source"] = traffic_db[tkey].get("source")
         fl = sum(v[1] for v in gemm_groups.values())
         ms = sum(v[2] for v in gemm_groups.values())
         steps_probed = max(1, min(args.steps, 3))
@@ -467,7 +495,7 @@ def main():
         "attention_roofline": fused_attn,
         "batch1": b1,
         "configs3": extra.get("configs3"), "configs4": extra.get("configs4"),
-        "gather_check": gather_check, "per_rank": per_rank,
+        "gather_check": gather_check, "per_rank": per_rank, "proposals": prop,
     }
     if roof_attn is not None:
         # BASELINE.json's second metric: tensor-pipe utilisation of the fused attention kernels, from the committed
@@ -514,6 +542,16 @@ def main():
                 f"batch{B}_as_{B}_calls_ms": round(tb, 2), f"batch{B}_images_per_s": round(B * 1e3 / tb, 2),
                 "ours_over_eager_batch1": round(t1 / b1["ms_per_image"], 2) if b1 else None,
                 f"ours_over_eager_batch{B}": round(value / (B * 1e3 / tb), 2)}
+            if prop is not None:
+                # the mask generator's eager counterpart: the oracle restatement of SamAutomaticMaskGenerator in fp32
+                # PyTorch ops on the same GPU, 64 prompts per batch like the reference's default
+                from oracle import sam_amg
+                osd = {k[len("model.visual_model."):]: v.float() for k, v in synthetic.sam_decoder_state_dict(8, dev).items()}
+                emb = torch.randn(1, 256, 64, 64, device=dev)
+                with torch.no_grad():
+                    tg = ms_of(lambda: sam_amg.generate(emb, osd, pred_iou_thresh=-10.0, stability_score_thresh=0.5), 1)
+                line["proposals"]["eager_gpu_ms_per_image"] = round(tg, 1)
+                line["proposals"]["ours_over_eager"] = round(tg / line["proposals"]["ms_per_image"], 2)
             del sd
             torch.cuda.empty_cache()
         # (2) the same algorithm on the host CPU: one REAL full-depth single-image forward

@@ -158,10 +158,69 @@ def selector_state_dict(hidden: int, seed: int, device, prefix: str = "model.") 
     return sd
 
 
-def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda", with_lm_head: bool = False) -> Dict[str, Tensor]:
-    """Full random-init state dict with the reference's key names (SURVEY §8b), bf16 on `device`.
-    with_lm_head adds `lm_head.weight` (only the training forward reads it)."""
+def sam_decoder_state_dict(seed: int, device, prefix: str = "model.visual_model.") -> Dict[str, Tensor]:
+    """SAM prompt encoder + mask decoder (reference model/segment_anything/modeling/{prompt_encoder,mask_decoder,
+    transformer}.py shapes and names).  The hyper-networks' output layers are scaled so that mask logits span +-20 like a
+    trained decoder's (the stability score of the mask generator needs logits well beyond its +-1 offsets)."""
+    G = _Gen(seed, device)
+    E = 256
     sd: Dict[str, Tensor] = {}
+
+    def lin(name, out_f, in_f, gain=1.0):
+        sd[prefix + name + ".weight"] = G.rn(out_f, in_f, std=gain * in_f ** -0.5)
+        sd[prefix + name + ".bias"] = G.rn(out_f, std=0.05)
+
+    def ln(name, dim):
+        sd[prefix + name + ".weight"] = G.rn(dim, std=0.1, mean=1.0)
+        sd[prefix + name + ".bias"] = G.rn(dim, std=0.1)
+
+    g = torch.Generator(device=device).manual_seed(seed + 99)
+    sd[prefix + "prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"] = torch.randn(2, E // 2, generator=g, device=device)
+    for i in range(4):
+        sd[prefix + f"prompt_encoder.point_embeddings.{i}.weight"] = G.rn(1, E, std=0.5)
+    sd[prefix + "prompt_encoder.not_a_point_embed.weight"] = G.rn(1, E, std=0.5)
+    sd[prefix + "prompt_encoder.no_mask_embed.weight"] = G.rn(1, E, std=0.5)
+    t = "mask_decoder.transformer."
+    for i in range(2):
+        p = f"{t}layers.{i}."
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            lin(p + "self_attn." + proj, E, E)
+        for att in ("cross_attn_token_to_image", "cross_attn_image_to_token"):
+            for proj in ("q_proj", "k_proj", "v_proj"):
+                lin(p + att + "." + proj, E // 2, E)
+            lin(p + att + ".out_proj", E, E // 2)
+        for n in ("norm1", "norm2", "norm3", "norm4"):
+            ln(p + n, E)
+        lin(p + "mlp.lin1", 2048, E)
+        lin(p + "mlp.lin2", E, 2048)
+    for proj in ("q_proj", "k_proj", "v_proj"):
+        lin(t + "final_attn_token_to_image." + proj, E // 2, E)
+    lin(t + "final_attn_token_to_image.out_proj", E, E // 2)
+    ln(t + "norm_final_attn", E)
+    d = "mask_decoder."
+    sd[prefix + d + "iou_token.weight"] = G.rn(1, E, std=0.5)
+    sd[prefix + d + "mask_tokens.weight"] = G.rn(4, E, std=0.5)
+    sd[prefix + d + "output_upscaling.0.weight"] = G.rn(E, 64, 2, 2, std=E ** -0.5)
+    sd[prefix + d + "output_upscaling.0.bias"] = G.rn(64, std=0.05)
+    ln(d + "output_upscaling.1", 64)
+    sd[prefix + d + "output_upscaling.3.weight"] = G.rn(64, 32, 2, 2, std=64 ** -0.5)
+    sd[prefix + d + "output_upscaling.3.bias"] = G.rn(32, std=0.05)
+    for i in range(4):
+        for j, (o, k) in enumerate(((E, E), (E, E), (32, E))):
+            lin(f"{d}output_hypernetworks_mlps.{i}.layers.{j}", o, k, gain=8.0 if j == 2 else 1.0)
+    for j, (o, k) in enumerate(((E, E), (E, E), (4, E))):
+        lin(f"{d}iou_prediction_head.layers.{j}", o, k)
+    return sd
+
+
+def lisa_state_dict(cfg: LisaCfg, seed: int = 0, device="cuda", with_lm_head: bool = False,
+                    with_sam_decoder: bool = False) -> Dict[str, Tensor]:
+    """Full random-init state dict with the reference's key names (SURVEY §8b), bf16 on `device`.
+    with_lm_head adds `lm_head.weight` (only the training forward reads it); with_sam_decoder adds SAM's prompt
+    encoder + mask decoder (`model.visual_model.{prompt_encoder,mask_decoder}.*`: proposal generation)."""
+    sd: Dict[str, Tensor] = {}
+    if with_sam_decoder:
+        sd.update(sam_decoder_state_dict(seed + 8, device))
     if with_lm_head:
         sd["lm_head.weight"] = _Gen(seed + 7, device).rn(cfg.llama.vocab, cfg.llama.hidden, std=cfg.llama.hidden ** -0.5)
     if cfg.image_encoder == "dinov2":

@@ -96,3 +96,59 @@ def test_select_proposals_rules():
     assert select_proposals(out, threshold=0.5) == [(1, [0, 2]), (0, [])]
     out["best_index"] = torch.tensor([1, 0], dtype=torch.int32)
     assert select_proposals(out, threshold=0.5) == [(1, [0, 2]), (0, [])]
+
+
+def test_plan_buckets_and_lru():
+    """Host logic of the plan cache (no GPU): prompt lengths bucket to 32 tokens, proposal counts to 32 / 64 / 128,
+    the per-stage LRU keeps `cap` plans and evicts the least recently used."""
+    from llmseg_b200 import lisa
+    assert [lisa.bucket_tokens(t) for t in (1, 32, 33, 64, 65, 512)] == [32, 32, 64, 64, 96, 512]
+    assert [lisa.bucket_props(k) for k in (1, 32, 33, 50, 64, 65, 128)] == [32, 32, 64, 64, 64, 128, 128]
+    with pytest.raises(ValueError):
+        lisa.bucket_props(129)
+    lru = lisa._LRU(2)
+    lru.put("a", 1)
+    lru.put("b", 2)
+    assert lru.get("a") == 1          # refreshes "a"
+    lru.put("c", 3)                    # evicts "b"
+    assert lru.get("b") is None and lru.get("a") == 1 and lru.get("c") == 3 and len(lru) == 2
+
+
+def test_reference_constructor_surface_without_weights():
+    """`LISAForCausalLM(config, **kwargs)` (reference model/LISA.py:144-170) is an nn.Module before any weights exist:
+    config mapping, eval/train, no-op device moves, a clear error on forward, LoRA merge rules."""
+    from llmseg_b200 import lisa
+    hf = {"hidden_size": 4096, "num_hidden_layers": 3, "num_attention_heads": 32, "intermediate_size": 11008,
+          "vocab_size": 32003, "rms_norm_eps": 1e-5, "mm_vision_select_layer": -2}
+    m = lisa.LISAForCausalLM(hf, seg_token_idx=32001, train_mask_decoder=True, out_dim=256, vision_pretrained=None,
+                             vision_tower="openai/clip-vit-large-patch14", use_mm_start_end=True)
+    assert isinstance(m, torch.nn.Module) and m.cfg.llama.layers == 3 and m.cfg.llama.eps == 1e-5 and m.cfg.seg_token_idx == 32001
+    assert m.training and not m.eval().training and m.to("cpu") is m and m.bfloat16() is m and m.get_model() is m
+    assert list(m.parameters()) == []
+    with pytest.raises(RuntimeError):
+        m(images=None)
+    with pytest.raises(RuntimeError):
+        m.state_dict()
+    with pytest.raises(ValueError):
+        lisa.cfg_from_hf_config(dict(hf, num_key_value_heads=8))
+    with pytest.raises(ValueError):
+        lisa.cfg_from_hf_config(hf, out_dim=128)
+    # LoRA pairs: merged with the caller's alpha; a pair without its base weight or its partner is an error
+    w, a, b = torch.randn(8, 6), torch.randn(2, 6), torch.randn(8, 2)
+    sd = {"base_model.model.x.q_proj.weight": w, "base_model.model.x.q_proj.lora_A.default.weight": a,
+          "base_model.model.x.q_proj.lora_B.default.weight": b, "base_model.model.y.weight": torch.ones(1)}
+    out = lisa.strip_peft_prefix(sd, lora_alpha=32.0)
+    assert set(out) == {"x.q_proj.weight", "y.weight"}
+    assert torch.allclose(out["x.q_proj.weight"], w + (32.0 / 2) * (b @ a), atol=1e-5)
+    with pytest.raises(KeyError):
+        lisa.strip_peft_prefix({k: v for k, v in sd.items() if not k.endswith("q_proj.weight")})
+    with pytest.raises(KeyError):
+        lisa.strip_peft_prefix({k: v for k, v in sd.items() if "lora_B" not in k})
+
+
+def test_proposal_point_grid_matches_oracle():
+    """The generator's point grid (reference utils/amg.py:179-186) equals the oracle's."""
+    from llmseg_b200 import proposals
+    from oracle import sam_amg
+    for n in (1, 8, 32):
+        assert torch.allclose(torch.from_numpy(proposals.point_grid(n)), sam_amg.point_grid(n), atol=1e-4)
