@@ -26,14 +26,19 @@ Tensor = torch.Tensor
 BF16 = torch.bfloat16
 # LayerNorm / RMSNorm in front of a projection can be folded into that GEMM (ops.fold_norm + ops.norm_stats):
 # the norm pass over the residual stream becomes a statistics-only read.  LLMSEG_FOLD_NORM selects where:
-#   "image" (default)  SAM / DINOv2 only      "all" / "1"  every encoder      "0"  nowhere (the reference's literal op order)
+#   "sam" (default)  SAM ViT-H only    "image"  SAM + DINOv2    "all" / "1"  every encoder    "0"  nowhere (the reference's literal op order)
 # Why not everywhere: folding moves a bf16 rounding from the normalised ACTIVATIONS (independent per token, averaged
 # away by attention) to the gamma-scaled WEIGHTS (the same perturbation for every token, so it adds up coherently).
 # tests/parity_bisect.py (profiles/round2_parity_bisect.md): with the text branch folded, its contribution to the
 # |pred_similarity - fp32 oracle| error is 3x larger (1.2e-3 vs 0.4e-3 mean) — the level of the reference's own bf16
 # path — while the image branch's contribution is negligible either way (2e-4), and the image branch is where the
 # norm passes cost time (64 x [32768, 1280] at batch 8 vs 64 x [2552, 4096]).
-_FOLD = os.environ.get("LLMSEG_FOLD_NORM", "image").lower()
+# DINOv2 (variant B) feeds the selector through ONE folded GEMM (final norm + lisa_dino_conv) after 24 LayerScale'd
+# blocks, and there folding does show at the outputs: full depth, similarity 2.9e-3 folded vs 1.5e-3 un-folded against
+# the fp32 oracle (reference bf16 path: 1.2e-3; profiles/round2_parity_bisect.md) — so "sam" (the default) folds the SAM
+# encoder only; "image" adds DINOv2, "all" / "1" every encoder, "0" none.
+_FOLD = os.environ.get("LLMSEG_FOLD_NORM", "sam").lower()
+FOLD_NORM_SAM = _FOLD in ("sam", "image", "all", "1")
 FOLD_NORM_IMAGE = _FOLD in ("image", "all", "1")
 FOLD_NORM_TEXT = _FOLD in ("all", "1")
 # Row-restricted tail of the last LLaMA layer (exact: row-wise ops commute with the [SEG] gather).  Off by default:
@@ -88,7 +93,7 @@ class _Scratch:
 class SamEncoder:
     def __init__(self, sd: Dict[str, Tensor], cfg, device, prefix: str = ""):
         self.cfg, self.device = cfg, device
-        self.fold = FOLD_NORM_IMAGE
+        self.fold = FOLD_NORM_SAM
         D = cfg.embed_dim
         self.heads, self.hd = cfg.num_heads, cfg.embed_dim // cfg.num_heads
         if self.hd != 80:

@@ -44,6 +44,21 @@ elif which == "attn_window":
     kext = ops.make_kext(14, dev)
     for _ in range(iters):
         ops.attention(q, k, vt, out, batch=nb, heads=H, head_dim=hd, seq=S, seq_pad=S_pad, scale=scale, qext=qext, kext=kext, ext_cols=32)
+elif which == "gemm_qkv_sam":    # SAM windowed layer's QKV projection as the encoder runs it: folded norm + bias + window scatter
+    from llmseg_b200.encoders import SamEncoder
+    S, ws = 4096, 14
+    x = torch.randn(B * S, 1280, device=dev).bfloat16(); w = (torch.randn(3840, 1280, device=dev) / 1280 ** 0.5).bfloat16()
+    bias = torch.randn(3840, device=dev).bfloat16()
+    enc = SamEncoder.__new__(SamEncoder)
+    from llmseg_b200.lisa import SamCfg
+    enc.cfg, enc.device, enc._maps = SamCfg(), torch.device(dev), {}
+    win_map, n_win, tok2win, pad_wins = enc._window_maps(B)
+    nb, sw, sw_pad = B * n_win, ws * ws, 200
+    q = torch.zeros(nb * H, sw_pad, hd, device=dev, dtype=torch.bfloat16); k = torch.zeros_like(q)
+    vt = torch.zeros(nb * H, hd, sw_pad, device=dev, dtype=torch.bfloat16)
+    st = ops.norm_stats(x, 1e-6)
+    for _ in range(iters):
+        ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad, row_map=tok2win, row_stats=st)
 elif which.startswith("gemm"):
     shapes = {"gemm_qkv": (4096 * B, 3840, 1280), "gemm_mlp1": (4096 * B, 5120, 1280), "gemm_mlp2": (4096 * B, 1280, 5120),
               "gemm_llama_gu": (319 * B, 22016, 4096), "gemm_llama_down": (319 * B, 4096, 11008),

@@ -39,7 +39,7 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     from llmseg_b200 import encoders, lisa, ops, synthetic
     from oracle import clip_llama as o_cl, lisa_forward as o_lf, sam_encoder as o_sam, selector as o_sel
-    encoders.FOLD_NORM_IMAGE = args.fold_norm in ("image", "all")
+    encoders.FOLD_NORM_SAM = encoders.FOLD_NORM_IMAGE = args.fold_norm in ("image", "all")
     encoders.FOLD_NORM_TEXT = args.fold_norm == "all"
     dev = "cuda"
     sam_d, clip_l, llama_l = (int(v) for v in args.depth.split(","))
