@@ -304,6 +304,11 @@ int llmseg_dice_bce_loss(const float* logits, const float* targets, int n_masks,
  *   mask_logits         mask_decoder.py:143-157 on the un-shuffled 2x2 ConvTranspose outputs: up2 bf16 [P*16384,128]
  *                       (row = prompt, token y, token x, dy, dx; col = dy2, dx2, channel), hyper bf16 [P,4,32]
  *                       -> low_res fp32 [P,3,256,256] (mask tokens 1..3: multimask output, mask_decoder.py:101-104)
+ *   upscale_logits      the three steps above in one kernel (mask_decoder.py:56-64,139-157): up1 bf16 [P*4096, 256] =
+ *                       ConvTranspose #1 as a GEMM with its bias (row = prompt, token; col = dy, dx, 64 channels), gamma /
+ *                       beta bf16 [64] of the LayerNorm2d, w2 bf16 [128,64] (row = dy2, dx2, channel) and b2 bf16 [128] of
+ *                       ConvTranspose #2, hyper bf16 [P,4,32] -> low_res fp32 [P,3,256,256].  ln64_gelu + llmseg_gemm +
+ *                       mask_logits stay exported: they are the un-fused path the tests compare against
  *   mask_stats          modeling/sam.py:155-166 (4x bilinear up-sampling, evaluated on the fly) + utils/amg.py:156-176,
  *                       303-346: stats int32 [n,8] = {area, #(> t+o), #(> t-o), 1023-x0, 1023-y0, x1, y1, 0} of
  *                       candidate cand[i] (NULL: i) — stability = [1]/[2], box valid when area > 0
@@ -322,6 +327,8 @@ int llmseg_img2tok_attention(const void* q, int ldq, long long q_batch_stride, c
 int llmseg_ln64_gelu(const void* in, void* out, const void* gamma, const void* beta, long long rows, float eps,
                      void* stream);
 int llmseg_mask_logits(const void* up2, const void* hyper, int n_prompts, float* low_res, void* stream);
+int llmseg_upscale_logits(const void* up1, const void* gamma, const void* beta, float eps, const void* w2, const void* b2,
+                          const void* hyper, int n_prompts, float* low_res, void* stream);
 int llmseg_mask_stats(const float* low_res, const int32_t* cand, int n_cand, float threshold, float offset,
                       int32_t* stats, void* stream);
 int llmseg_box_nms(const float* boxes_sorted, int n, float iou_threshold, int32_t* keep, void* stream);

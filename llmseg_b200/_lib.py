@@ -104,6 +104,8 @@ def _declare(lib):
                                              c_int, c_void_p]
     lib.llmseg_ln64_gelu.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, ll, c_float, c_void_p]
     lib.llmseg_mask_logits.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.llmseg_upscale_logits.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                          c_void_p]
     lib.llmseg_mask_stats.argtypes = [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p]
     lib.llmseg_box_nms.argtypes = [c_void_p, c_int, c_float, c_void_p, c_void_p]
     lib.llmseg_mask_soft.argtypes = [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]
@@ -118,6 +120,7 @@ SYMBOLS = [
     "llmseg_maskpool_workspace", "llmseg_maskpool", "llmseg_small_attention", "llmseg_select",
     "llmseg_align_iou_loss", "llmseg_dice_bce_loss", "llmseg_selector_losses", "llmseg_lm_cross_entropy",
     "llmseg_point_tokens", "llmseg_tok2img_attention", "llmseg_img2tok_attention", "llmseg_ln64_gelu", "llmseg_mask_logits",
+    "llmseg_upscale_logits",
     "llmseg_mask_stats", "llmseg_box_nms", "llmseg_mask_soft", "llmseg_mask_binarize",
 ]
 

@@ -169,53 +169,212 @@ tok2img_attn_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// image -> token attention.  grid (4096 / 32, P); 256 threads = 32 image tokens x 8 heads
+// token -> image attention, tensor-core version.  grid (P); 256 threads = 8 warps, ONE HEAD PER WARP: the warp walks the
+// 4096 keys of its head in 32-key chunks that arrive through a warp-private cp.async ring (no block barrier in the
+// loop), S = Q K^T and O += P V are mma.sync m16n8k16 (7 live query rows of 16; head_dim 16 = one k-step), softmax is
+// the usual online form on the 8 live scores a lane holds per chunk.  ~60 registers instead of 234, so 24 warps per SM
+// keep ~100 KB of K / V in flight per SM — the thread-per-key kernel above ran 8 warps per SM at 1.2 TB/s.
 // ---------------------------------------------------------------------------------------------
+constexpr int T2I_CHUNK = 32;                       // keys per chunk
+constexpr int T2I_STAGES = 4;
+constexpr int T2I_STAGE_BYTES = T2I_CHUNK * 32 * 2;  // K rows then V rows, 32 B (16 bf16) each
+constexpr int T2I_SMEM = 8 * T2I_STAGES * T2I_STAGE_BYTES;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col); rows 8..15 of A are zero here (a1 = a3 = 0)
+__device__ __forceinline__ void mma16816(float* d, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 3)
+tok2img_attn_mma_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk, long long k_bs,
+                        const bf16* __restrict__ v, int ldv, long long v_bs, bf16* __restrict__ out, int ldo) {
+  extern __shared__ __align__(128) uint8_t t2i_smem[];
+  const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qr = lane >> 2, qc = (lane & 3) * 2;     // fragment row (query / key-in-block / dim) and column pair
+  const uint32_t ring = smem_u32(t2i_smem) + h * (T2I_STAGES * T2I_STAGE_BYTES);
+  // A fragment of Q (rows 7..15 are zero padding): a0 = Q[qr][qc, qc+1], a2 = Q[qr][qc+8, qc+9]
+  uint32_t qa0 = 0, qa2 = 0;
+  if (qr < NTOK) {
+    const bf16* qp = q + (size_t)(p * NTOK + qr) * ldq + h * 16 + qc;
+    qa0 = *reinterpret_cast<const uint32_t*>(qp);
+    qa2 = *reinterpret_cast<const uint32_t*>(qp + 8);
+  }
+  // a lane pair fetches one key's 32-byte head slice: 16 keys per instruction, whole sectors
+  const int lk = lane >> 1, lh = lane & 1;
+  const bf16* kp = k + (size_t)p * k_bs + (size_t)lk * ldk + h * 16 + lh * 8;
+  const bf16* vp = v + (size_t)p * v_bs + (size_t)lk * ldv + h * 16 + lh * 8;
+  const uint32_t st_off = lk * 32 + lh * 16;
+  auto fetch = [&](int chunk) {
+    const uint32_t dst = ring + (chunk % T2I_STAGES) * T2I_STAGE_BYTES + st_off;
+    const size_t key0 = (size_t)chunk * T2I_CHUNK;
+    cp_async16(dst, kp + key0 * ldk);
+    cp_async16(dst + 16 * 32, kp + (key0 + 16) * ldk);
+    cp_async16(dst + T2I_CHUNK * 32, vp + key0 * ldv);
+    cp_async16(dst + T2I_CHUNK * 32 + 16 * 32, vp + (key0 + 16) * ldv);
+  };
+  constexpr int NCH = IMG_TOK / T2I_CHUNK;
+#pragma unroll
+  for (int c = 0; c < T2I_STAGES - 1; ++c) {
+    fetch(c);
+    cp_async_commit();
+  }
+  // ldmatrix lane addresses inside a stage.  K (non-transposed; matrices: keys 0-7 x dims 0-7 | keys 0-7 x dims 8-15 |
+  // keys 8-15 x dims 0-7 | keys 8-15 x dims 8-15 -> B fragments of two 8-key blocks), V (transposed; matrices: keys 0-7 x
+  // dims 0-7 | keys 8-15 x dims 0-7 | keys 0-7 x dims 8-15 | keys 8-15 x dims 8-15 -> B fragments of the two dim blocks)
+  const int mi = lane >> 3, mr = lane & 7;
+  const uint32_t k_lm = ((mi >> 1) * 8 + mr) * 32 + (mi & 1) * 16;
+  const uint32_t v_lm = T2I_CHUNK * 32 + ((mi & 1) * 8 + mr) * 32 + (mi >> 1) * 16;
+  constexpr float C1 = 0.25f * 1.4426950408889634f;   // 1/sqrt(16) * log2(e)
+  float m = -INFINITY, l = 0.f;
+  float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};   // O[qr][qc..] for dims 0-7 / 8-15 (d[2], d[3]: padding rows)
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    cp_async_wait<T2I_STAGES - 2>();
+    __syncwarp();
+    if (c + T2I_STAGES - 1 < NCH) fetch(c + T2I_STAGES - 1);
+    cp_async_commit();
+    const uint32_t st = ring + (c % T2I_STAGES) * T2I_STAGE_BYTES;
+    float s[4][4];
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {   // 16 keys per ldmatrix
+      uint32_t kf[4];
+      ldmatrix_x4(st + kb * 16 * 32 + k_lm, kf);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[kb * 2][e] = s[kb * 2 + 1][e] = 0.f;
+      mma16816(s[kb * 2], qa0, qa2, kf[0], kf[1]);
+      mma16816(s[kb * 2 + 1], qa0, qa2, kf[2], kf[3]);
+    }
+    // live scores of this lane: s[nb][0], s[nb][1] = query qr x keys nb*8 + qc, qc+1
+    float mx = fmaxf(fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1])), fmaxf(fmaxf(s[2][0], s[2][1]), fmaxf(s[3][0], s[3][1])));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m, mx * C1);
+    const float alpha = ex2(m - m_new);   // m = -inf on the first chunk: exp2(-inf) = 0
+    m = m_new;
+    uint32_t pa[4];
+    float ls = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      const float p0 = ex2(fmaf(s[nb][0], C1, -m_new)), p1 = ex2(fmaf(s[nb][1], C1, -m_new));
+      ls += p0 + p1;
+      pa[nb] = pack_bf16(p0, p1);
+    }
+    l = fmaf(l, alpha, ls);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      o0[e] *= alpha;
+      o1[e] *= alpha;
+    }
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      uint32_t vf[4];
+      ldmatrix_x4_trans(st + kb * 16 * 32 + v_lm, vf);
+      mma16816(o0, pa[kb * 2], pa[kb * 2 + 1], vf[0], vf[1]);
+      mma16816(o1, pa[kb * 2], pa[kb * 2 + 1], vf[2], vf[3]);
+    }
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (qr < NTOK) {
+    const float inv = 1.f / l;
+    bf16* op = out + (size_t)(p * NTOK + qr) * ldo + h * 16 + qc;
+    *reinterpret_cast<uint32_t*>(op) = pack_bf16(o0[0] * inv, o0[1] * inv);
+    *reinterpret_cast<uint32_t*>(op + 8) = pack_bf16(o1[0] * inv, o1[1] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// image -> token attention.  grid (4096 / I2T_TOK, P); 256 threads = 8 warps, ONE HEAD PER WARP and one image token
+// per lane, so every K / V read from shared memory is a warp-uniform 128-bit broadcast (a thread-per-(token, head)
+// layout put 4 heads of a warp on the same bank: 4-way conflicts on 224 loads per thread made the kernel
+// shared-memory bound at 0.6 TB/s).  Each block walks I2T_TOK tokens so the 7 KB K/V staging is paid once per 256 rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int I2T_TOK = 256;
 __global__ void __launch_bounds__(256)
 img2tok_attn_kernel(const bf16* __restrict__ q, int ldq, long long q_bs, const bf16* __restrict__ k, int ldk,
                     const bf16* __restrict__ v, int ldv, bf16* __restrict__ out, int ldo) {
   const int p = blockIdx.y;
-  const int tok = blockIdx.x * 32 + (threadIdx.x >> 3), h = threadIdx.x & 7;
-  __shared__ float ks[NTOK][128];
-  __shared__ float vs[NTOK][128];
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(16) float ks[NTOK][128];
+  __shared__ __align__(16) float vs[NTOK][128];
   for (int i = threadIdx.x; i < NTOK * 128; i += 256) {
     const int j = i >> 7, c = i & 127;
-    ks[j][c] = __bfloat162float(k[(size_t)(p * NTOK + j) * ldk + c]);
+    ks[j][c] = __bfloat162float(k[(size_t)(p * NTOK + j) * ldk + c]) * 0.25f;   // 1/sqrt(16) folded into K
     vs[j][c] = __bfloat162float(v[(size_t)(p * NTOK + j) * ldv + c]);
   }
   __syncthreads();
-  float qf[16];
-  load16(q + (size_t)p * q_bs + (size_t)tok * ldq + h * 16, qf);
-  float s[NTOK], m = -INFINITY;
+  const bf16* qp = q + (size_t)p * q_bs + h * 16;
+  bf16* op = out + (size_t)p * IMG_TOK * ldo + h * 16;
+#pragma unroll 2
+  for (int it = 0; it < I2T_TOK / 32; ++it) {
+    const int tok = blockIdx.x * I2T_TOK + it * 32 + lane;
+    float qf[16];
+    load16(qp + (size_t)tok * ldq, qf);
+    float s[NTOK], m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < NTOK; ++j) {
-    float a = 0.f;
+    for (int j = 0; j < NTOK; ++j) {
+      float a = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) a = fmaf(qf[d], ks[j][h * 16 + d], a);
-    s[j] = a * 0.25f;
-    m = fmaxf(m, s[j]);
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[j][h * 16 + d4 * 4]);
+        a = fmaf(qf[d4 * 4 + 0], kk.x, a);
+        a = fmaf(qf[d4 * 4 + 1], kk.y, a);
+        a = fmaf(qf[d4 * 4 + 2], kk.z, a);
+        a = fmaf(qf[d4 * 4 + 3], kk.w, a);
+      }
+      s[j] = a;
+      m = fmaxf(m, a);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+      s[j] = __expf(s[j] - m);
+      l += s[j];
+    }
+    const float inv = 1.f / l;
+    float o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NTOK; ++j) {
+#pragma unroll
+      for (int d4 = 0; d4 < 4; ++d4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[j][h * 16 + d4 * 4]);
+        o[d4 * 4 + 0] = fmaf(s[j], vv.x, o[d4 * 4 + 0]);
+        o[d4 * 4 + 1] = fmaf(s[j], vv.y, o[d4 * 4 + 1]);
+        o[d4 * 4 + 2] = fmaf(s[j], vv.z, o[d4 * 4 + 2]);
+        o[d4 * 4 + 3] = fmaf(s[j], vv.w, o[d4 * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] *= inv;
+    uint4 w0, w1;
+    w0.x = pack_bf16(o[0], o[1]); w0.y = pack_bf16(o[2], o[3]); w0.z = pack_bf16(o[4], o[5]); w0.w = pack_bf16(o[6], o[7]);
+    w1.x = pack_bf16(o[8], o[9]); w1.y = pack_bf16(o[10], o[11]); w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+    uint4* dst = reinterpret_cast<uint4*>(op + (size_t)tok * ldo);
+    dst[0] = w0;
+    dst[1] = w1;
   }
-  float l = 0.f;
-#pragma unroll
-  for (int j = 0; j < NTOK; ++j) {
-    s[j] = __expf(s[j] - m);
-    l += s[j];
-  }
-  const float inv = 1.f / l;
-  float o[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    float a = 0.f;
-#pragma unroll
-    for (int j = 0; j < NTOK; ++j) a = fmaf(s[j], vs[j][h * 16 + d], a);
-    o[d] = a * inv;
-  }
-  uint4 w0, w1;
-  w0.x = pack_bf16(o[0], o[1]); w0.y = pack_bf16(o[2], o[3]); w0.z = pack_bf16(o[4], o[5]); w0.w = pack_bf16(o[6], o[7]);
-  w1.x = pack_bf16(o[8], o[9]); w1.y = pack_bf16(o[10], o[11]); w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
-  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)p * IMG_TOK + tok) * ldo + h * 16);
-  dst[0] = w0;
-  dst[1] = w1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -309,6 +468,176 @@ mask_logits_kernel(const bf16* __restrict__ up2, const bf16* __restrict__ hyper,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused tail of the mask decoder's output up-scaling (mask_decoder.py:139-164): for one (prompt, token row ty) the block
+// takes the 256 un-shuffled rows of ConvTranspose #1 (64 tokens x 4 sub-pixels, 64 channels; bias already added by the
+// GEMM), applies LayerNorm2d(64) + GELU, multiplies by ConvTranspose #2 as a [256 x 64] x [64 x 128] product on
+// mma.sync (columns = 4 sub-sub-pixels x 32 channels), adds its bias, GELU, and contracts the 32 channels with the three
+// hyper-network vectors of the prompt — 4 rows x 256 pixels of low-res logits per mask leave the block.  Replaces
+// ln64_gelu + a 4 M x 128 x 64 GEMM + mask_logits: 0.27 + 0.54 + 1.07 + 1.07 GB of HBM traffic per 256 prompts become
+// one 0.27 GB read, and the ConvTranspose #2 activations are never rounded to bf16.
+// Shared memory: X [256 x 64] and W2 [128 x 64] bf16 with the 16-byte chunks of a row XOR-swizzled by (row & 7)
+// (ldmatrix conflict-free), the output staging tile, and the small vectors.
+// ---------------------------------------------------------------------------------------------
+constexpr int UPF_X_BYTES = 256 * 128, UPF_W_BYTES = 128 * 128, UPF_STAGE_BYTES = 3 * 4 * LOW * 4;
+constexpr int UPF_VEC_FLOATS = 64 + 64 + 128 + 96;
+constexpr int UPF_SMEM = UPF_X_BYTES + UPF_W_BYTES + UPF_STAGE_BYTES + UPF_VEC_FLOATS * 4;
+
+__device__ __forceinline__ void mma16816_full(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+upscale_logits_kernel(const bf16* __restrict__ u1, const bf16* __restrict__ gamma, const bf16* __restrict__ beta, float eps,
+                      const bf16* __restrict__ w2, const bf16* __restrict__ b2, const bf16* __restrict__ hyper,
+                      float* __restrict__ low) {
+  extern __shared__ __align__(128) uint8_t upf_smem[];
+  const int ty = blockIdx.x, p = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* xs = upf_smem;
+  uint8_t* ws = upf_smem + UPF_X_BYTES;
+  float (*stage)[4][LOW] = reinterpret_cast<float (*)[4][LOW]>(upf_smem + UPF_X_BYTES + UPF_W_BYTES);
+  float* gam = reinterpret_cast<float*>(upf_smem + UPF_X_BYTES + UPF_W_BYTES + UPF_STAGE_BYTES);
+  float* bet = gam + 64;
+  float* bias2 = bet + 64;
+  float* hy = bias2 + 128;   // [3][32]
+  const uint32_t xs_u = smem_u32(xs), ws_u = smem_u32(ws);
+  // ---- loads: the block's 256 u1 rows are contiguous (32 KB); W2 is 16 KB (L2-resident across blocks)
+  const bf16* src = u1 + ((size_t)p * IMG_TOK + (size_t)ty * 64) * 256;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = tid + i * 256, row = q >> 3, c = q & 7;
+    cp_async16(xs_u + row * 128 + ((c ^ (row & 7)) << 4), src + (size_t)q * 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = tid + i * 256, row = q >> 3, c = q & 7;
+    cp_async16(ws_u + row * 128 + ((c ^ (row & 7)) << 4), w2 + (size_t)q * 8);
+  }
+  cp_async_commit();
+  if (tid < 64) {
+    gam[tid] = __bfloat162float(gamma[tid]);
+    bet[tid] = __bfloat162float(beta[tid]);
+  }
+  if (tid < 128) bias2[tid] = __bfloat162float(b2[tid]);
+  if (tid >= 128 && tid < 224) {
+    const int i = tid - 128;
+    hy[i] = __bfloat162float(hyper[((size_t)p * 4 + 1 + (i >> 5)) * 32 + (i & 31)]);
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- LayerNorm2d(64) + GELU in place: 8 lanes per row, 8 channels per lane (arithmetic of ln64_gelu_kernel)
+  {
+    const int part = tid & 7;
+#pragma unroll 2
+    for (int pass = 0; pass < 8; ++pass) {
+      const int row = pass * 32 + (tid >> 3);
+      uint4* cell = reinterpret_cast<uint4*>(xs + row * 128 + ((part ^ (row & 7)) << 4));
+      const uint4 raw = *cell;
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      float x[8], sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = unpack_bf16(w[i]);
+        x[2 * i] = v.x;
+        x[2 * i + 1] = v.y;
+        sm += v.x + v.y;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      const float mean = sm * (1.f / 64.f);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] -= mean;
+        ss = fmaf(x[i], x[i], ss);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rstd = rsqrtf(ss * (1.f / 64.f) + eps);
+      uint32_t o4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = part * 8 + 2 * i;
+        const float2 y = gelu2(make_float2(fmaf(x[2 * i] * rstd, gam[c], bet[c]), fmaf(x[2 * i + 1] * rstd, gam[c + 1], bet[c + 1])));
+        o4[i] = pack_bf16(y.x, y.y);
+      }
+      *cell = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+  __syncthreads();
+  // ---- [32 rows of this warp] x [64 ch] x W2^T, two 64-column halves; epilogue per half
+  const int mi = lane >> 3, mr = lane & 7;
+  const int qr = lane >> 2, qc = (lane & 3) * 2;
+#pragma unroll 1
+  for (int nh = 0; nh < 2; ++nh) {
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        // matrices: rows 0-7 / k 0-7, rows 8-15 / k 0-7, rows 0-7 / k 8-15, rows 8-15 / k 8-15  ->  a0..a3
+        const int row = warp * 32 + mt * 16 + (mi & 1) * 8 + mr, kc = ks * 2 + (mi >> 1);
+        ldmatrix_x4(xs_u + row * 128 + ((kc ^ (row & 7)) << 4), a[mt]);
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        // matrices: n-tile 2np / k 0-7, 2np / k 8-15, 2np+1 / k 0-7, 2np+1 / k 8-15  ->  (b0, b1) of two n-tiles
+        const int n = nh * 64 + (np * 2 + (mi >> 1)) * 8 + mr, kc = ks * 2 + (mi & 1);
+        uint32_t b[4];
+        ldmatrix_x4(ws_u + n * 128 + ((kc ^ (n & 7)) << 4), b);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma16816_full(acc[mt][np * 2], a[mt], b[0], b[1]);
+          mma16816_full(acc[mt][np * 2 + 1], a[mt], b[2], b[3]);
+        }
+      }
+    }
+    // lane holds, per (mt, row half rh, n-tile nt): columns nh*64 + nt*8 + qc, +1  ->  sub-sub-pixel s = nh*2 + nt/4,
+    // channels (nt & 3)*8 + qc, +1
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int nt = pl * 4 + t, col = nh * 64 + nt * 8 + qc, c = t * 8 + qc;
+            const float2 g = gelu2(make_float2(acc[mt][nt][rh * 2] + bias2[col], acc[mt][nt][rh * 2 + 1] + bias2[col + 1]));
+            d0 = fmaf(g.x, hy[c], d0); d0 = fmaf(g.y, hy[c + 1], d0);
+            d1 = fmaf(g.x, hy[32 + c], d1); d1 = fmaf(g.y, hy[32 + c + 1], d1);
+            d2 = fmaf(g.x, hy[64 + c], d2); d2 = fmaf(g.y, hy[64 + c + 1], d2);
+          }
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+          }
+          const int R = warp * 32 + mt * 16 + rh * 8 + qr;   // row of the block: token tx = R / 4, sub-pixel R % 4
+          const int s2 = nh * 2 + pl;
+          const int yy = 2 * ((R >> 1) & 1) + (s2 >> 1), xx = 4 * (R >> 2) + 2 * (R & 1) + (s2 & 1);
+          const int m = lane & 3;
+          if (m < 3) stage[m][yy][xx] = m == 0 ? d0 : (m == 1 ? d1 : d2);
+        }
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * 4 * LOW; i += 256) {
+    const int m = i / (4 * LOW), r = (i / LOW) & 3, x = i & (LOW - 1);
+    low[(((size_t)p * 3 + m) * LOW + 4 * ty + r) * LOW + x] = stage[m][r][x];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 4x bilinear up-sampling (align_corners = False) of a 256 x 256 logit map, evaluated per output pixel the way
 // ATen's upsample_bilinear2d does: src = 0.25 (dst + 0.5) - 0.5 clamped at 0, neighbours i0, i0 + (i0 < 255).
 // ---------------------------------------------------------------------------------------------
@@ -347,30 +676,60 @@ mask_stats_kernel(const float* __restrict__ low, const int* __restrict__ cand, i
   }
   __syncthreads();
   int area = 0, hi_c = 0, lo_c = 0, mnx = 0, mny = 0, mxx = 0, mxy = 0;
-  // thread owns 4 hi-res columns (the taps of a column are computed once)
+  // thread owns 4 hi-res columns (the taps of a column are computed once).  Four consecutive hi-res rows share their two
+  // low-res rows, so the horizontal half of the interpolation is kept per low-res row (h0 / h1, same expression as
+  // up_at) and a hi-res pixel costs one vertical blend and three compares; the box is tracked as "any pixel in this
+  // column / row" flags instead of four max updates per pixel.
   const int x0 = threadIdx.x * 4;
   Tap tx[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) tx[j] = tap_of(x0 + j);
+  const float thr_hi = thr + off, thr_lo = thr - off;
+  int cur0 = -1, cur1 = -1;
+  unsigned colany = 0;
+  float h0[4], h1[4];
   for (int r = 0; r < ROWS; ++r) {
     const int y = chunk * ROWS + r;
     const Tap ty = tap_of(y);
-    const float* r0 = tile[ty.i0 - lr0];
-    const float* r1 = tile[ty.i1 - lr0];
+    if (ty.i0 != cur0) {   // block-uniform branches: the row taps depend on y only
+      if (ty.i0 == cur1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h0[j] = h1[j];
+      } else {
+        const float* r0 = tile[ty.i0 - lr0];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h0[j] = tx[j].l0 * r0[tx[j].i0] + tx[j].l1 * r0[tx[j].i1];
+      }
+      cur0 = ty.i0;
+    }
+    if (ty.i1 != cur1) {
+      const float* r1 = tile[ty.i1 - lr0];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h1[j] = tx[j].l0 * r1[tx[j].i0] + tx[j].l1 * r1[tx[j].i1];
+      cur1 = ty.i1;
+    }
+    bool rowany = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v = up_at(r0, r1, ty, tx[j]);
-      hi_c += v > thr + off;
-      lo_c += v > thr - off;
-      if (v > thr) {
-        ++area;
-        mnx = max(mnx, HI - 1 - (x0 + j));
-        mny = max(mny, HI - 1 - y);
-        mxx = max(mxx, x0 + j);
-        mxy = max(mxy, y);
-      }
+      const float v = ty.l0 * h0[j] + ty.l1 * h1[j];
+      hi_c += v > thr_hi;
+      lo_c += v > thr_lo;
+      const bool in = v > thr;
+      area += in;
+      colany |= (unsigned)in << j;
+      rowany |= in;
+    }
+    if (rowany) {
+      mny = max(mny, HI - 1 - y);
+      mxy = max(mxy, y);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if ((colany >> j) & 1u) {
+      mnx = max(mnx, HI - 1 - (x0 + j));
+      mxx = max(mxx, x0 + j);
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     area += __shfl_xor_sync(0xffffffffu, area, o);
@@ -538,9 +897,23 @@ extern "C" int llmseg_tok2img_attention(const void* q, int ldq, const void* k, i
   LLMSEG_REQUIRE(ldk % 8 == 0 && ldv % 8 == 0 && k_batch_stride % 8 == 0 && v_batch_stride % 8 == 0 &&
                      ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
                  LLMSEG_EALIGN, "llmseg_tok2img_attention: k / v rows must be 16-byte aligned");
-  tok2img_attn_kernel<<<dim3(n_prompts, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, k_batch_stride, static_cast<const bf16*>(v),
-      ldv, v_batch_stride, static_cast<bf16*>(out), ldo);
+  LLMSEG_REQUIRE(ldq % 2 == 0 && ldo % 2 == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out)) & 3) == 0,
+                 LLMSEG_EALIGN, "llmseg_tok2img_attention: q / out rows must be 4-byte aligned");
+  const char* v1 = getenv("LLMSEG_T2I_V1");   // thread-per-key CUDA-core kernel (A/B runs and tests)
+  if (v1 != nullptr && atoi(v1) != 0) {
+    tok2img_attn_kernel<<<dim3(n_prompts, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, k_batch_stride, static_cast<const bf16*>(v),
+        ldv, v_batch_stride, static_cast<bf16*>(out), ldo);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      LLMSEG_CUDA(cudaFuncSetAttribute(tok2img_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2I_SMEM));
+      attr_set = true;
+    }
+    tok2img_attn_mma_kernel<<<n_prompts, 256, T2I_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, k_batch_stride, static_cast<const bf16*>(v),
+        ldv, v_batch_stride, static_cast<bf16*>(out), ldo);
+  }
   AMG_LAUNCHED();
 }
 
@@ -551,7 +924,7 @@ extern "C" int llmseg_img2tok_attention(const void* q, int ldq, long long q_batc
   LLMSEG_REQUIRE(ldq % 8 == 0 && ldo % 8 == 0 && q_batch_stride % 8 == 0 &&
                      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                  LLMSEG_EALIGN, "llmseg_img2tok_attention: q / out rows must be 16-byte aligned");
-  img2tok_attn_kernel<<<dim3(IMG_TOK / 32, n_prompts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  img2tok_attn_kernel<<<dim3(IMG_TOK / I2T_TOK, n_prompts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(q), ldq, q_batch_stride, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v),
       ldv, static_cast<bf16*>(out), ldo);
   AMG_LAUNCHED();
@@ -575,6 +948,24 @@ extern "C" int llmseg_mask_logits(const void* up2, const void* hyper, int n_prom
   LLMSEG_REQUIRE(up2 && hyper && low_res && n_prompts > 0, LLMSEG_EARG, "llmseg_mask_logits: bad arguments");
   mask_logits_kernel<<<dim3(64, n_prompts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(up2), static_cast<const bf16*>(hyper), low_res);
+  AMG_LAUNCHED();
+}
+
+extern "C" int llmseg_upscale_logits(const void* up1, const void* gamma, const void* beta, float eps, const void* w2,
+                                     const void* b2, const void* hyper, int n_prompts, float* low_res, void* stream) {
+  if (int e = check_arch()) return e;
+  LLMSEG_REQUIRE(up1 && gamma && beta && w2 && b2 && hyper && low_res && n_prompts > 0, LLMSEG_EARG,
+                 "llmseg_upscale_logits: bad arguments");
+  LLMSEG_REQUIRE(((reinterpret_cast<uintptr_t>(up1) | reinterpret_cast<uintptr_t>(w2)) & 15) == 0, LLMSEG_EALIGN,
+                 "llmseg_upscale_logits: up1 / w2 must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LLMSEG_CUDA(cudaFuncSetAttribute(upscale_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPF_SMEM));
+    attr_set = true;
+  }
+  upscale_logits_kernel<<<dim3(64, n_prompts), 256, UPF_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(up1), static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), eps,
+      static_cast<const bf16*>(w2), static_cast<const bf16*>(b2), static_cast<const bf16*>(hyper), low_res);
   AMG_LAUNCHED();
 }
 

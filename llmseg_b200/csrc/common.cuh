@@ -446,6 +446,30 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+
+// Exact-erf GELU (nn.GELU(), reference image_encoder.py:170 / common.py MLPBlock) on two values:
+// erf(z) = z * P(z^2) on |z| <= 3, clamped beyond (1 - erf(3) = 2.2e-5); P is the degree-8 least-squares
+// fit on Chebyshev nodes, |erf error| < 2.7e-5, |GELU error| < 5.6e-5 absolute — below the bf16 rounding
+// that follows for every |GELU| > 0.015.  Pure FMA-pipe work (13 packed instructions per pair): the
+// A&S 7.1.26 form it replaces spent 2 MUFU per element and made the SAM MLP GEMM epilogue-bound
+// (profiles/r01h_gemm_epilogue_costs.md).
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  const float2 z = fmul2(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 zc = make_float2(fminf(fmaxf(z.x, -3.0f), 3.0f), fminf(fmaxf(z.y, -3.0f), 3.0f));
+  const float2 u = fmul2(zc, zc);
+  float2 q = make_float2(4.071986126e-08f, 4.071986126e-08f);
+  q = ffma2(q, u, make_float2(-1.945750910e-06f, -1.945750910e-06f));
+  q = ffma2(q, u, make_float2(4.110950977e-05f, 4.110950977e-05f));
+  q = ffma2(q, u, make_float2(-5.118074478e-04f, -5.118074478e-04f));
+  q = ffma2(q, u, make_float2(4.241328686e-03f, 4.241328686e-03f));
+  q = ffma2(q, u, make_float2(-2.512698807e-02f, -2.512698807e-02f));
+  q = ffma2(q, u, make_float2(1.111308783e-01f, 1.111308783e-01f));
+  q = ffma2(q, u, make_float2(-3.753655851e-01f, -3.753655851e-01f));
+  q = ffma2(q, u, make_float2(1.128284454e+00f, 1.128284454e+00f));
+  const float2 e = fmul2(zc, q);
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, e, hx);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

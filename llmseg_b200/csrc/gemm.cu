@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#include <climits>
 #include "common.cuh"
 
 namespace llmseg {
@@ -99,29 +100,7 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Exact-erf GELU (nn.GELU(), reference image_encoder.py:170 / common.py MLPBlock) on two values:
-// erf(z) = z * P(z^2) on |z| <= 3, clamped beyond (1 - erf(3) = 2.2e-5); P is the degree-8 least-squares
-// fit on Chebyshev nodes, |erf error| < 2.7e-5, |GELU error| < 5.6e-5 absolute — below the bf16 rounding
-// that follows for every |GELU| > 0.015.  Pure FMA-pipe work (13 packed instructions per pair): the
-// A&S 7.1.26 form it replaces spent 2 MUFU per element and made the SAM MLP GEMM epilogue-bound
-// (profiles/r01h_gemm_epilogue_costs.md).
-__device__ __forceinline__ float2 gelu2(float2 x) {
-  const float2 z = fmul2(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
-  const float2 zc = make_float2(fminf(fmaxf(z.x, -3.0f), 3.0f), fminf(fmaxf(z.y, -3.0f), 3.0f));
-  const float2 u = fmul2(zc, zc);
-  float2 q = make_float2(4.071986126e-08f, 4.071986126e-08f);
-  q = ffma2(q, u, make_float2(-1.945750910e-06f, -1.945750910e-06f));
-  q = ffma2(q, u, make_float2(4.110950977e-05f, 4.110950977e-05f));
-  q = ffma2(q, u, make_float2(-5.118074478e-04f, -5.118074478e-04f));
-  q = ffma2(q, u, make_float2(4.241328686e-03f, 4.241328686e-03f));
-  q = ffma2(q, u, make_float2(-2.512698807e-02f, -2.512698807e-02f));
-  q = ffma2(q, u, make_float2(1.111308783e-01f, 1.111308783e-01f));
-  q = ffma2(q, u, make_float2(-3.753655851e-01f, -3.753655851e-01f));
-  q = ffma2(q, u, make_float2(1.128284454e+00f, 1.128284454e+00f));
-  const float2 e = fmul2(zc, q);
-  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
-  return ffma2(hx, e, hx);
-}
+// gelu2 (packed-FMA exact-erf GELU) lives in common.cuh: the proposal kernels (amg.cu) use it too
 __device__ __forceinline__ float fast_sigmoid(float x) {
   return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x));
 }
@@ -567,6 +546,13 @@ __device__ __forceinline__ void stats_finish(const GemmDev& p, int m_blk, int wa
   }
 }
 
+// first residual row of an epilogue warp's 32-row block (res_mod: the residual is a res_mod-row table that
+// repeats down the output; the launcher admits tma_res only when res_mod % 32 == 0, so a block never wraps)
+__device__ __forceinline__ int res_row0(const GemmDev& p, int m_blk, int quarter) {
+  const int r = m_blk * BM + quarter * 32;
+  return p.res_mod > 0 ? r % p.res_mod : r;
+}
+
 // tma_res: start the loads of a tile's first two residual blocks of this warp (called BEFORE the wait for the
 // tile's accumulators; the landing buffers are free since the previous tile's last reads).
 template <int BN, int NP>
@@ -579,7 +565,7 @@ __device__ __forceinline__ void res_prefetch_first(const GemmDev& p, uint8_t* re
       const int n0b = n_blk * BN + (chalf * (BN / 32 / NP) + b) * 32;
       if (n0b < p.N) {
         mbar_expect_tx(&res_bar[b], 2048);
-        tma_load_2d(res_stage + b * 2048, tmR, &res_bar[b], n0b, m_blk * BM + quarter * 32);
+        tma_load_2d(res_stage + b * 2048, tmR, &res_bar[b], n0b, res_row0(p, m_blk, quarter));
       }
     }
   }
@@ -594,10 +580,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
                                               const SkOwner sk = SkOwner{0, 0, 0}, uint8_t* epi_stage = nullptr,
                                               const CUtensorMap* tmC = nullptr, uint8_t* res_stage = nullptr,
                                               uint64_t* res_bar = nullptr, const CUtensorMap* tmR = nullptr,
-                                              uint32_t* res_ph = nullptr) {
+                                              uint32_t* res_ph = nullptr, int out_row_pre = INT_MIN) {
   const int row = m_blk * BM + quarter * 32 + lane;
   int out_row = row;
-  if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
+  if (out_row_pre != INT_MIN)
+    out_row = out_row_pre;         // the caller fetched the row map before it waited for the accumulators
+  else if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && row < p.M)
     out_row = p.out_row_map[row];  // QKV: position of this token in the (sequence, slot) index space
   const bool live = row < p.M && out_row >= 0;
   const bool fold = MODE != MODE_RELPOS && p.row_stats != nullptr;
@@ -687,7 +675,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
         const int n0n = n0 + 64;
         if (lane == 0 && ci + 2 < C_FIRST_STRIDE && n0n < p.N) {
           mbar_expect_tx(&res_bar[ci & 1], 2048);
-          tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, m_blk * BM + quarter * 32);
+          tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, res_row0(p, m_blk, quarter));
         }
       }
       if (staged && (c & 1) == 1) {
@@ -714,14 +702,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
 //   1  bias + GELU, folded norm, staged TMA store                      SAM / DINOv2 MLP lin1
 //   2  bias + TMA residual + row statistics, staged TMA store          SAM / DINOv2 proj and lin2 (folded norms next)
 //   3  TMA residual, no bias, staged TMA store                         LLaMA o_proj / down_proj, CLIP-less text branch
+//   4  bias + TMA residual, staged TMA store                           SAM mask-decoder projections (proposal generation)
 //   0  generic (every option a runtime test) — everything else
 // The variants also read TMEM one chunk ahead (the next 32 columns are in flight while this chunk is worked on).
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
 struct EpiX {
-  static constexpr bool bias = EPI == 1 || EPI == 2;
+  static constexpr bool bias = EPI == 1 || EPI == 2 || EPI == 4;
   static constexpr bool gelu = EPI == 1;
-  static constexpr bool res = EPI == 2 || EPI == 3;
+  static constexpr bool res = EPI == 2 || EPI == 3 || EPI == 4;
   static constexpr bool stats = EPI == 2;
 };
 
@@ -769,7 +758,7 @@ __device__ __forceinline__ void epi_plain_x(const uint32_t* r, float rs, const u
   }
 }
 
-// one epilogue warp's share (32 rows x BN/2 columns) of a finished tile, variants 1-3 (pair kernel, BN = 256,
+// one epilogue warp's share (32 rows x BN/2 columns) of a finished tile, variants 1-4 (pair kernel, BN = 256,
 // N % 64 == 0, rows not scattered, C through staged TMA stores, residual through the TMA landing buffers)
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_plain_fast(const GemmDev& p, uint32_t taddr, int m_blk, int n_blk, int quarter,
@@ -814,7 +803,7 @@ __device__ __forceinline__ void epilogue_plain_fast(const GemmDev& p, uint32_t t
       const int n0n = n0 + 64;
       if (lane == 0 && ci + 2 < NC && n0n < p.N) {
         mbar_expect_tx(&res_bar[ci & 1], 2048);
-        tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, m_blk * BM + quarter * 32);
+        tma_load_2d(res_stage + (ci & 1) * 2048, tmR, &res_bar[ci & 1], n0n, res_row0(p, m_blk, quarter));
       }
     }
     if ((c & 1) == 1) {
@@ -1253,6 +1242,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         res_prefetch_first<BN, G2_EPI_WARPS / 4>(p, smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2, &tmR,
                                                  m_blk, n_blk, quarter, chalf, lane);
       const float rs = partial ? 1.f : row_rstd(p, m_blk * BM + quarter * 32 + lane);
+      // row map entry of this lane's row, in flight under the wait (ncu r2n: the QKV epilogue sat ~4 % of the kernel's
+      // samples on this load at the top of every tile)
+      int out_row_pre = m_blk * BM + quarter * 32 + lane;
+      if ((MODE == LLMSEG_GEMM_PLAIN || MODE == LLMSEG_GEMM_QKV) && p.out_row_map != nullptr && out_row_pre < p.M)
+        out_row_pre = __ldg(p.out_row_map + out_row_pre);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -1288,7 +1282,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           epilogue_tile<BN, MODE, ROPE, G2_EPI_WARPS / 4>(p, nullptr, taddr, m_blk, n_blk, quarter, chalf, lane, rs, own,
                                                           smem + C::OFF_EPI + (warp - 4) * C::EPI_TILE_BYTES, &tmC,
                                                           smem + C::OFF_RES + (warp - 4) * 4096, res_bar + (warp - 4) * 2,
-                                                          &tmR, &res_ph);
+                                                          &tmR, &res_ph, out_row_pre);
         if (own.n_peers > 0) {
           asm volatile("bar.sync 1, %0;" ::"n"(G2_EPI_WARPS * 32) : "memory");  // every reader of the partials is done
           if (warp == 4 && lane == 0)
@@ -1423,6 +1417,11 @@ bool tma_store_enabled() {
   return mode != 0;
 }
 // LLMSEG_GEMM_TMA_RES=0: residual tiles are read with per-lane global loads again (and the ring keeps all stages)
+int streamk_min_kb() {
+  const char* e = getenv("LLMSEG_GEMM_SK_MIN_KB");  // read per call (A/B runs)
+  return e == nullptr ? 32 : atoi(e);
+}
+
 bool tma_res_enabled() {
   const char* e = getenv("LLMSEG_GEMM_TMA_RES");  // read per call: scripts/gpu_gemm_ab.py flips it between launches
   return e == nullptr || atoi(e) != 0;
@@ -1589,7 +1588,10 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
       // at most ~4 segments per tile: every extra partial is another 128 KB round trip for the owner
       int w = (rem * kb + n_pairs - 1) / n_pairs;
       if (w < (kb + 3) / 4) w = (kb + 3) / 4;
-      if (rem > 0 && kb >= 32 && kb - w >= 16) {
+      // (round 2 tried the tail for K = 1280 too — LLMSEG_GEMM_SK_MIN_KB=16: at batch 1 the SAM GEMMs run 1.08 / 3.2 / 4.3
+      //  waves — and measured no gain, 14.97 vs 15.23 ms per step: the text branch's kernels on the second stream already
+      //  fill the idle SMs of those tail waves.  The floor stays at 32 k-blocks.)
+      if (rem > 0 && kb >= streamk_min_kb() && kb - w >= 12 && w >= 4) {
         d.sk_w = w;
         d.sk_flags = static_cast<int*>(p->workspace);
         d.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(p->workspace) + SK_FLAG_BYTES);
@@ -1613,8 +1615,8 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
     // residual through TMA landing buffers (LLMSEG_GEMM_TMA_RES=0: per-lane loads again): same tiling as C
     CUtensorMap tmR = tmA;
     d.tma_res = 0;
-    if (d.tma_store && bn == 256 && p->residual != nullptr && p->res_mod == 0 && tma_res_enabled()) {
-      uint64_t rdims[2] = {(uint64_t)p->N, (uint64_t)p->M};
+    if (d.tma_store && bn == 256 && p->residual != nullptr && p->res_mod % 32 == 0 && tma_res_enabled()) {
+      uint64_t rdims[2] = {(uint64_t)p->N, (uint64_t)(p->res_mod > 0 ? p->res_mod : p->M)};
       uint64_t rstr[1] = {(uint64_t)p->ldr * 2};
       uint32_t rbox[2] = {32, 32};
       if (int e = make_tmap_bf16(&tmR, p->residual, 2, rdims, rstr, rbox, 64)) return e;
@@ -1639,6 +1641,9 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
       if (p->act == LLMSEG_ACT_NONE && res && d.tma_res && p->stats_out == nullptr && p->bias == nullptr &&
           p->row_stats == nullptr)
         return launch2<256, LLMSEG_GEMM_PLAIN, false, 3>(tmA, tmB, tmC, tmR, d, pgrid, stream);
+      if (p->act == LLMSEG_ACT_NONE && res && d.tma_res && p->stats_out == nullptr && p->bias != nullptr &&
+          p->row_stats == nullptr)
+        return launch2<256, LLMSEG_GEMM_PLAIN, false, 4>(tmA, tmB, tmC, tmR, d, pgrid, stream);
     }
     if (bn == 256) {
       LLMSEG_GEMM2_DISPATCH(256)

@@ -548,6 +548,21 @@ def mask_logits(up2: torch.Tensor, hyper: torch.Tensor, n_prompts: int, out: Opt
     return out
 
 
+def upscale_logits(up1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                   hyper: torch.Tensor, n_prompts: int, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused LayerNorm2d(64)+GELU -> ConvTranspose #2 (+bias, GELU) -> hyper-network product: up1 bf16 [P*4096, 256],
+    w2 bf16 [128,64], b2 bf16 [128], hyper bf16 [P,4,32] -> low-res logits fp32 [P,3,256,256]."""
+    _req_bf16(up1, gamma, beta, w2, b2, hyper)
+    assert up1.is_contiguous() and up1.shape == (n_prompts * 4096, 256) and w2.is_contiguous() and w2.shape == (128, 64)
+    assert hyper.is_contiguous() and hyper.shape == (n_prompts, 4, 32) and b2.numel() == 128 and gamma.numel() == 64
+    if out is None:
+        out = torch.empty((n_prompts, 3, 256, 256), dtype=torch.float32, device=up1.device)
+    check(_lib.lib().llmseg_upscale_logits(up1.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), w2.data_ptr(),
+                                           b2.data_ptr(), hyper.data_ptr(), n_prompts, out.data_ptr(), _stream()),
+          "upscale_logits")
+    return out
+
+
 def mask_stats(low_res: torch.Tensor, cand: Optional[torch.Tensor] = None, threshold: float = 0.0,
                offset: float = 1.0) -> torch.Tensor:
     """low_res fp32 [n,256,256] -> int32 [n,8] = {area, #(>t+o), #(>t-o), 1023-x0, 1023-y0, x1, y1, 0}."""

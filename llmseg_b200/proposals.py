@@ -29,8 +29,14 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+import os
+
 from . import ops
 from .encoders import BF16, _dev
+
+# LLMSEG_AMG_FUSED_UPSCALE=0: LayerNorm2d+GELU, ConvTranspose #2 and the hyper-network product as three launches
+# (ln64_gelu + gemm + mask_logits) instead of `upscale_logits` — A/B runs and the parity test of the fused kernel
+FUSED_UPSCALE = os.environ.get("LLMSEG_AMG_FUSED_UPSCALE", "1") != "0"
 
 Tensor = torch.Tensor
 
@@ -174,9 +180,10 @@ class SamProposalGenerator:
         del kv
         # up-scaling (mask_decoder.py:56-64,141-142): two 2 x 2 transposed convolutions as GEMMs on un-shuffled rows
         u1 = ops.gemm(keys, self.w_up1, self.b_up1)                                             # [P*4096, 4 x 64]
-        ops.ln64_gelu(u1, self.ln_up[0], self.ln_up[1], 1e-6)
-        u2 = ops.gemm(u1.view(P * 16384, 64), self.w_up2, self.b_up2, act="gelu")               # [P*16384, 4 x 32]
-        del u1
+        if not FUSED_UPSCALE:
+            ops.ln64_gelu(u1, self.ln_up[0], self.ln_up[1], 1e-6)
+            u2 = ops.gemm(u1.view(P * 16384, 64), self.w_up2, self.b_up2, act="gelu")           # [P*16384, 4 x 32]
+            del u1
         # hyper-networks on the 4 mask tokens, IoU head on the IoU token (mask_decoder.py:143-162)
         hs7 = hs.view(P, 7 * 256)
         hyper = torch.empty((P, 4, 32), dtype=BF16, device=self.device)
@@ -188,7 +195,10 @@ class SamProposalGenerator:
         for i in range(4):
             mlp3(hs7[:, (1 + i) * 256:(2 + i) * 256], self.hyper[i], out=hyper[:, i, :])
         iou = mlp3(hs7[:, 0:256], self.iou_head)
-        low = ops.mask_logits(u2, hyper, P, out=low_out)
+        if FUSED_UPSCALE:   # LayerNorm2d + GELU, ConvTranspose #2 + GELU and the hyper-network product in one kernel
+            low = ops.upscale_logits(u1, self.ln_up[0], self.ln_up[1], self.w_up2, self.b_up2, hyper, P, 1e-6, out=low_out)
+        else:
+            low = ops.mask_logits(u2, hyper, P, out=low_out)
         return low, iou[:, 1:4].float()
 
     # ---- automatic mask generator ----------------------------------------------------------------------------

@@ -91,10 +91,49 @@ def test_gemm_streamk_tail(cuda_lib, M, N, K, mode):
         assert (sk - ref).abs().max().item() <= _ulp_tol(ref)
 
 
-@pytest.mark.parametrize("variant", ["gelu", "res_stats", "res"])
+@pytest.mark.parametrize("N,mode", [(1280, "res_stats"), (5120, "gelu"), (3840, "qkv")])
+def test_gemm_streamk_tail_short_k(cuda_lib, N, mode, monkeypatch):
+    """Batch-1 SAM shapes (M = 4096, K = 1280: 20 k-blocks, 1.08 / 4.3 / 3.2 waves of pair tiles) with the stream-K tail
+    admitted for short K (LLMSEG_GEMM_SK_MIN_KB=16; the default floor of 32 k-blocks keeps whole tiles — measured no gain
+    inside the two-stream step).  Against the default: same result up to fp32 summation order, row statistics included,
+    and deterministic."""
+    from llmseg_b200 import ops
+    M, K = 4096, 1280
+    g = torch.Generator(device=DEV).manual_seed(N)
+    a = _bf(torch.randn(M, K, generator=g, device=DEV))
+    w = _bf(torch.randn(N, K, generator=g, device=DEV) / K ** 0.5)
+    b = _bf(torch.randn(N, generator=g, device=DEV))
+    x0 = _bf(torch.randn(M, N, generator=g, device=DEV)) if mode == "res_stats" else None
+
+    def run():
+        if mode == "qkv":
+            H, hd, S = 16, 80, 512
+            q = torch.zeros(M // S * H, S, hd, device=DEV, dtype=torch.bfloat16)
+            k, vt = torch.zeros_like(q), torch.zeros(M // S * H, hd, S, device=DEV, dtype=torch.bfloat16)
+            ops.gemm_qkv(a, w, b, q, k, vt, heads=H, head_dim=hd, seq_in=S, seq_pad=S, row_stats=ops.norm_stats(a, 1e-6))
+            return torch.cat([q.flatten(), k.flatten(), vt.flatten()]).float(), None
+        if mode == "gelu":
+            return ops.gemm(a, w, b, act="gelu", row_stats=ops.norm_stats(a, 1e-6)).float(), None
+        x = x0.clone()
+        so = ops.gemm_stats_buffer(M, N, M, 1e-6)
+        ops.gemm(a, w, b, residual=x, out=x, stats_out=so)
+        return x.float(), so.final.clone()
+    y0, s0 = run()
+    monkeypatch.setenv("LLMSEG_GEMM_SK_MIN_KB", "16")
+    y1, s1 = run()
+    y2, s2 = run()
+    assert torch.equal(y1, y2)
+    d = (y0 - y1).abs()
+    assert d.max().item() <= _ulp_tol(y0) and d.mean().item() <= 1e-4
+    if s0 is not None:
+        assert torch.equal(s1, s2)
+        assert (s0 - s1).abs().max().item() <= 2e-3 * float(s0.abs().max())
+
+
+@pytest.mark.parametrize("variant", ["gelu", "res_stats", "res", "bias_res_mod"])
 def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
-    """The straight-line epilogue variants of the CTA-pair kernel (csrc/gemm.cu EpiX 1-3: bias + GELU (+ folded norm),
-    bias + TMA residual + row statistics, TMA residual alone) against the generic epilogue on the same problem —
+    """The straight-line epilogue variants of the CTA-pair kernel (csrc/gemm.cu EpiX 1-4: bias + GELU (+ folded norm),
+    bias + TMA residual + row statistics, TMA residual alone, bias + TMA residual from a repeating row table) against the generic epilogue on the same problem —
     bit-equal outputs and statistics (same arithmetic, only the control flow is resolved at compile time) — and
     against torch within the usual GEMM bound.  M x N = 2100 x 1280: 17 row tiles, a ragged last one."""
     from llmseg_b200 import ops
@@ -109,6 +148,8 @@ def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
         if variant == "gelu":
             st = ops.norm_stats(a, 1e-6)
             return ops.gemm(a, w, b, act="gelu", row_stats=st), None
+        if variant == "bias_res_mod":   # variant 4: bias + a 256-row residual table repeated down the output (TMA landing)
+            return ops.gemm(a, w, b, residual=x0[:256], res_mod=256), None
         x = x0.clone()
         if variant == "res_stats":
             so = ops.gemm_stats_buffer(M, N, M, 1e-6)
@@ -129,6 +170,12 @@ def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
         ref = torch.nn.functional.gelu((af * torch.rsqrt(var + 1e-6)) @ wf.T + b.float())
     elif variant == "res_stats":
         ref = af @ wf.T + b.float() + x0.float()
+    elif variant == "bias_res_mod":
+        ref = af @ wf.T + b.float() + x0[:256].float().repeat(9, 1)[:M]
+        monkeypatch.setenv("LLMSEG_GEMM_TMA_RES", "0")   # per-lane residual loads: same values, same arithmetic
+        y2, _ = run()
+        monkeypatch.delenv("LLMSEG_GEMM_TMA_RES")
+        assert torch.equal(y1, y2)
     else:
         ref = af @ wf.T + x0.float()
     assert (y1.float() - ref).abs().max().item() <= 2 ** -7 * float(ref.abs().max()) + 2e-2

@@ -29,6 +29,86 @@ def _blobs(n, seed):
     return (out + 0.3 * torch.randn(n, 256, 256, generator=g, device=DEV)).contiguous()
 
 
+def _mha_ref(q, k, v):
+    """fp32 softmax attention over 8 heads of 16 (reference/model/segment_anything/modeling/transformer.py:222-236)."""
+    P = q.shape[0]
+    qh, kh, vh = (t.float().view(P, -1, 8, 16).transpose(1, 2) for t in (q, k, v))
+    a = torch.softmax(qh @ kh.transpose(-1, -2) * 0.25, -1)
+    return (a @ vh).transpose(1, 2).reshape(P, -1, 128)
+
+
+@pytest.mark.parametrize("kernel", ["mma", "v1"])
+@pytest.mark.parametrize("shared_kv", [True, False])
+def test_tok2img_attention_vs_torch(cuda_lib, kernel, shared_kv, monkeypatch):
+    """7 prompt tokens x 4096 image keys, 8 heads of 16: the tensor-core kernel (mma.sync, warp per head, cp.async ring)
+    and the CUDA-core one it replaced (LLMSEG_T2I_V1=1), K / V shared by all prompts (layer 0) or per prompt, read as column
+    views of a wider buffer like the decoder does.  Scores get a few large entries so the online max moves."""
+    from llmseg_b200 import ops
+    P = 5
+    g = torch.Generator(device=DEV).manual_seed(3 + shared_kv)
+    q = (torch.randn(P * 7, 128, generator=g, device=DEV) * 2).bfloat16()
+    nk = 4096 if shared_kv else P * 4096
+    kv = torch.randn(nk, 384, generator=g, device=DEV).bfloat16()
+    kv[torch.randint(0, nk, (64,), generator=g, device=DEV), :128] *= 4
+    k, v = kv[:, :128], kv[:, 256:]
+    if kernel == "v1":
+        monkeypatch.setenv("LLMSEG_T2I_V1", "1")
+    out = ops.tok2img_attention(q, k, v, P, shared_kv)
+    kk = (k if not shared_kv else k.unsqueeze(0).expand(P, -1, -1)).reshape(P, 4096, 128)
+    vv = (v if not shared_kv else v.unsqueeze(0).expand(P, -1, -1)).reshape(P, 4096, 128)
+    ref = _mha_ref(q.view(P, 7, 128), kk, vv).reshape(P * 7, 128)
+    d = (out.float() - ref).abs()
+    # P is rounded to bf16 for the second MMA (2^-9 relative on each of ~tens of effective terms) and the output is bf16
+    assert d.max().item() <= 2 ** -7 * float(ref.abs().max()) and d.mean().item() <= 2e-3 * float(ref.abs().mean()) + 1e-4
+
+
+@pytest.mark.parametrize("shared_q", [True, False])
+def test_img2tok_attention_vs_torch(cuda_lib, shared_q):
+    """4096 image queries x 7 token keys per prompt (warp per head, K / V broadcast from shared memory)."""
+    from llmseg_b200 import ops
+    P = 3
+    g = torch.Generator(device=DEV).manual_seed(11 + shared_q)
+    nq = 4096 if shared_q else P * 4096
+    qb = (torch.randn(nq, 256, generator=g, device=DEV) * 2).bfloat16()
+    q = qb[:, 128:]
+    k = torch.randn(P * 7, 128, generator=g, device=DEV).bfloat16()
+    v = torch.randn(P * 7, 128, generator=g, device=DEV).bfloat16()
+    out = ops.img2tok_attention(q, k, v, P, shared_q)
+    qq = (q if not shared_q else q.unsqueeze(0).expand(P, -1, -1)).reshape(P, 4096, 128)
+    ref = _mha_ref(qq, k.view(P, 7, 128), v.view(P, 7, 128)).reshape(P * 4096, 128)
+    assert (out.float() - ref).abs().max().item() <= 2 ** -8 * float(ref.abs().max()) + 1e-3
+
+
+def test_upscale_logits_fused_vs_unfused_and_fp32(cuda_lib):
+    """`upscale_logits` (LayerNorm2d(64)+GELU -> ConvTranspose #2 + GELU -> hyper-network product, one kernel, ConvTranspose
+    #2 activations kept in fp32) against the three launches it replaces (ln64_gelu + gemm + mask_logits, which round them
+    to bf16) and against the same arithmetic in fp32 torch (mask_decoder.py:56-64,139-157 on un-shuffled rows): the fused
+    kernel must not be further from fp32 than the un-fused path."""
+    from llmseg_b200 import ops
+    P = 3
+    g = torch.Generator(device=DEV).manual_seed(5)
+    rnd = lambda *sh: torch.randn(*sh, generator=g, device=DEV)
+    u1 = (rnd(P * 4096, 256) * 1.5 + 0.2).bfloat16()
+    gamma, beta = (1 + 0.2 * rnd(64)).bfloat16(), (0.1 * rnd(64)).bfloat16()
+    w2, b2 = (rnd(128, 64) / 8).bfloat16(), (0.1 * rnd(32)).repeat(4).bfloat16().contiguous()
+    hyper = rnd(P, 4, 32).bfloat16()
+    fused = ops.upscale_logits(u1, gamma, beta, w2, b2, hyper, P, 1e-6)
+    x = u1.clone()
+    ops.ln64_gelu(x, gamma, beta, 1e-6)
+    unfused = ops.mask_logits(ops.gemm(x.view(P * 16384, 64), w2, b2, act="gelu"), hyper, P)
+    xf = torch.nn.functional.layer_norm(u1.float().view(-1, 64), (64,), gamma.float(), beta.float(), 1e-6)
+    u2 = torch.nn.functional.gelu(torch.nn.functional.gelu(xf) @ w2.float().T + b2.float())          # [P*16384, 128]
+    # rows (p, ty, tx, dy, dx), cols (dy2, dx2, c)  ->  pixel (4 ty + 2 dy + dy2, 4 tx + 2 dx + dx2)
+    u2 = u2.view(P, 64, 64, 2, 2, 2, 2, 32)
+    ref = torch.einsum("pyxabcdk,pmk->pmyacxbd", u2, hyper.float()[:, 1:4]).reshape(P, 3, 256, 256)
+    scale = float(ref.abs().max())
+    e_f, e_u = (fused - ref).abs(), (unfused - ref).abs()
+    print(f"upscale_logits: |ref| max {scale:.2f}; fused-fp32 max {e_f.max():.2e} mean {e_f.mean():.2e}; "
+          f"unfused-fp32 max {e_u.max():.2e} mean {e_u.mean():.2e}")
+    assert e_f.mean().item() <= 1.05 * e_u.mean().item() + 1e-6
+    assert e_f.max().item() <= 2 ** -7 * scale
+
+
 def test_mask_stats_boxes_soft_binarize_vs_oracle(cuda_lib):
     from llmseg_b200 import ops
     from oracle import sam_amg
