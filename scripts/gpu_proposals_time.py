@@ -33,7 +33,7 @@ def wrap(name, fn):
 
 
 for name in ("gemm", "layernorm", "add_rows_bcast", "small_attention", "point_tokens", "tok2img_attention", "img2tok_attention",
-             "ln64_gelu", "mask_logits", "mask_stats", "box_nms", "mask_soft", "mask_binarize"):
+             "ln64_gelu", "mask_logits", "upscale_logits", "mask_stats", "box_nms", "mask_soft", "mask_binarize"):
     setattr(ops, name, wrap(name, getattr(ops, name)))
 kw = dict(points_per_batch=ppb, pred_iou_thresh=-10.0, stability_score_thresh=0.5, box_nms_thresh=0.7)
 with torch.no_grad():
