@@ -685,45 +685,56 @@ mask_stats_kernel(const float* __restrict__ low, const int* __restrict__ cand, i
 #pragma unroll
   for (int j = 0; j < 4; ++j) tx[j] = tap_of(x0 + j);
   const float thr_hi = thr + off, thr_lo = thr - off;
-  int cur0 = -1, cur1 = -1;
   unsigned colany = 0;
-  float h0[4], h1[4];
-  for (int r = 0; r < ROWS; ++r) {
-    const int y = chunk * ROWS + r;
-    const Tap ty = tap_of(y);
-    if (ty.i0 != cur0) {   // block-uniform branches: the row taps depend on y only
-      if (ty.i0 == cur1) {
+  // Hi-res rows 4k+2 .. 4k+5 blend low-res rows k and min(k+1, 255) with weights l1 = 1/8, 3/8, 5/8, 7/8 (exact in fp32;
+  // rows 0, 1 clamp to l1 = 0 on row 0 = "group -1").  The 128 rows of a chunk are 33 groups, the first and the last
+  // one half inside the chunk; hA / hB are the horizontally interpolated low-res rows (the expression of up_at).
+  auto hrow = [&](int lr, float* h) {
+    const float* rr = tile[lr - lr0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h0[j] = h1[j];
-      } else {
-        const float* r0 = tile[ty.i0 - lr0];
+    for (int j = 0; j < 4; ++j) h[j] = tx[j].l0 * rr[tx[j].i0] + tx[j].l1 * rr[tx[j].i1];
+  };
+  auto rows = [&](const float* hA, const float* hB, int k, int i_lo, int i_hi) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h0[j] = tx[j].l0 * r0[tx[j].i0] + tx[j].l1 * r0[tx[j].i1];
+    for (int i = 0; i < 4; ++i) {
+      if (i < i_lo || i >= i_hi) continue;
+      const float l1 = k < 0 ? 0.f : 0.125f + 0.25f * (float)i, l0 = 1.f - l1;
+      const int y = 4 * k + 2 + i;
+      bool rowany = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = l0 * hA[j] + l1 * hB[j];
+        hi_c += v > thr_hi;
+        lo_c += v > thr_lo;
+        const bool in = v > thr;
+        area += in;
+        colany |= (unsigned)in << j;
+        rowany |= in;
       }
-      cur0 = ty.i0;
+      if (rowany) {
+        mny = max(mny, HI - 1 - y);
+        mxy = max(mxy, y);
+      }
     }
-    if (ty.i1 != cur1) {
-      const float* r1 = tile[ty.i1 - lr0];
+  };
+  float hA[4], hB[4];
+  int k = chunk * (ROWS / 4) - 1;
+  hrow(max(k, 0), hA);
+  hrow(min(k + 1, LOW - 1), hB);
+  rows(hA, hB, k, 2, 4);
+#pragma unroll 1
+  for (int g = 1; g < ROWS / 4; ++g) {
+    ++k;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h1[j] = tx[j].l0 * r1[tx[j].i0] + tx[j].l1 * r1[tx[j].i1];
-      cur1 = ty.i1;
-    }
-    bool rowany = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float v = ty.l0 * h0[j] + ty.l1 * h1[j];
-      hi_c += v > thr_hi;
-      lo_c += v > thr_lo;
-      const bool in = v > thr;
-      area += in;
-      colany |= (unsigned)in << j;
-      rowany |= in;
-    }
-    if (rowany) {
-      mny = max(mny, HI - 1 - y);
-      mxy = max(mxy, y);
-    }
+    for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+    hrow(min(k + 1, LOW - 1), hB);
+    rows(hA, hB, k, 0, 4);
   }
+  ++k;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hA[j] = hB[j];
+  hrow(min(k + 1, LOW - 1), hB);
+  rows(hA, hB, k, 0, 2);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if ((colany >> j) & 1u) {
