@@ -820,329 +820,6 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ C
 }
 
 // =============================================================================================
-// v5: v3's schedule (64-key tiles double-buffered in TMEM, MMA warp one tile ahead) with v1's warp count — 8 softmax
-// warps per CTA, 16 per SM — for the SAM global rows, where v3's 2 softmax warps per scheduler could not cover the
-// MUFU / TMEM latencies (profiles/round2_attn.md).  Two threads share a query row WITHOUT a per-tile barrier; see the
-// softmax section for how they agree on the reference maximum.  P of each half stays over that half's own score
-// columns, so the PV MMAs take their A operand from columns {0, 8, 32, 40} of the tile's buffer.
-// =============================================================================================
-template <int HD, int EXT>
-__global__ void __launch_bounds__(320, 2)
-attn5_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
-             const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
-             const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQx,
-             const __grid_constant__ CUtensorMap tmE, const AttnDev p) {
-  using C = A3Cfg<HD, EXT>;
-  constexpr int ST = C::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* bar_q = bars + 0;
-  uint64_t* k_full = bars + 1;          // [ST]
-  uint64_t* k_empty = bars + 1 + ST;    // [ST]
-  uint64_t* v_full = bars + 1 + 2 * ST; // [ST]
-  uint64_t* v_empty = bars + 1 + 3 * ST;
-  uint64_t* bar_s = bars + 1 + 4 * ST;  // [2] score buffer (j & 1) holds S(j)
-  uint64_t* bar_p = bar_s + 2;          // [2] P(j) written over it (4 elected arrivals)
-  uint64_t* bar_pv = bar_p + 2;         // PV(j) complete (one completion per tile)
-  uint64_t* bar_done = bar_pv + 1;      // every PV complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_done + 1);
-  // [4 slots][128 rows][2 halves] tagged maxima, one untagged scratch slot (tile 0), the row-sum exchange
-  uint32_t* xch = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 256);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM;
-  const int bh = blockIdx.y;
-  const int b = bh / p.heads;
-
-  pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQa);
-    tma_prefetch_desc(&tmKa);
-    tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 1 + 4 * ST + 2; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bar_p[0], 8);
-    mbar_init(&bar_p[1], 8);
-    mbar_init(bar_pv, 1);
-    mbar_init(bar_done, 1);
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < 4 * 128 * 2; i += 320) xch[i] = 3u;   // generation tag 3: never expected before tile 12
-  if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();  // prologue done; everything below may read what the previous kernel wrote
-
-  int kv_limit = p.seq;
-  if (p.kv_len) kv_limit = min(kv_limit, max(p.kv_len[b], 1));
-  int kv_hi = kv_limit;
-  if (p.causal) kv_hi = min(kv_hi, q0 + BM);
-  const int n_tiles = (kv_hi + BN3 - 1) / BN3;
-
-  if (warp == 0) {
-    // ================================ TMA producer ================================
-    const bool issuer = elect_one();
-    if (issuer) {
-      mbar_expect_tx(bar_q, C::Q_TX);
-      tma_load_3d(smem + C::OFF_Q0, &tmQa, bar_q, 0, q0, bh);
-      if (HD == 80) tma_load_3d(smem + C::OFF_Q1, &tmQb, bar_q, 64, q0, bh);
-      if (HD == 128) tma_load_3d(smem + C::OFF_Q1, &tmQa, bar_q, 64, q0, bh);
-      if (EXT) {
-        tma_load_3d(smem + C::OFF_QX, &tmQx, bar_q, 0, q0, bh);
-        tma_load_2d(smem + C::OFF_E, &tmE, bar_q, 0, 0);
-      }
-    }
-    __syncwarp();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int key0 = j * BN3;
-      uint8_t* st = smem + C::OFF_ST + s * C::STAGE_BYTES;
-      mbar_wait(&k_empty[s], ph ^ 1);
-      if (issuer) {
-        mbar_expect_tx(&k_full[s], C::K_TX);
-        tma_load_3d(st, &tmKa, &k_full[s], 0, key0, bh);
-        if (HD == 80) tma_load_3d(st + C::K0_BYTES, &tmKb, &k_full[s], 64, key0, bh);
-        if (HD == 128) tma_load_3d(st + C::K0_BYTES, &tmKa, &k_full[s], 64, key0, bh);
-      }
-      __syncwarp();
-      mbar_wait(&v_empty[s], ph ^ 1);
-      if (issuer) {
-        mbar_expect_tx(&v_full[s], C::V_TX);
-        tma_load_3d(st + C::K0_BYTES + C::K1_BYTES, &tmV, &v_full[s], key0, 0, bh);
-      }
-      __syncwarp();
-      if (++s == ST) {
-        s = 0;
-        ph ^= 1;
-      }
-    }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN3);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(BM, HD);
-    const bool issuer = elect_one();
-    const uint32_t sQ0 = smem_u32(smem + C::OFF_Q0), sQ1 = smem_u32(smem + C::OFF_Q1);
-    const uint32_t sQX = smem_u32(smem + C::OFF_QX), sE = smem_u32(smem + C::OFF_E);
-    const uint32_t sSt = smem_u32(smem + C::OFF_ST);
-    const uint32_t tO = tmem_base + C::O_COL;
-    const uint64_t dQ0 = umma_smem_desc(sQ0, 1024, UMMA_SW128);
-    const uint64_t dQ1s = umma_smem_desc(sQ1, 256, UMMA_SW32);
-    const uint64_t dQ1 = umma_smem_desc(sQ1, 1024, UMMA_SW128);
-    const uint64_t dQXw = umma_smem_desc(sQX, 512, UMMA_SW64), dEw = umma_smem_desc(sE, 512, UMMA_SW64);
-    const uint64_t dQXg = umma_smem_desc(sQX, 1024, UMMA_SW128), dEg = umma_smem_desc(sE, 1024, UMMA_SW128);
-    int ks = 0, vs = 0;          // ring positions of the next K / V tile to consume
-    uint32_t kph = 0, vph = 0;
-    auto issue_s = [&](int j) {
-      const uint32_t sk = sSt + ks * C::STAGE_BYTES;
-      const uint32_t tS = tmem_base + (j & 1) * BN3;
-      mbar_wait(&k_full[ks], kph);
-      tc_fence_after();
-      if (issuer) {
-        const uint64_t dK0 = umma_smem_desc(sk, 1024, UMMA_SW128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tS, dQ0 + 2 * k, dK0 + 2 * k, idesc_s, k != 0);
-        if (HD == 80) umma_ss(tS, dQ1s, umma_smem_desc(sk + C::K0_BYTES, 256, UMMA_SW32), idesc_s, 1);
-        if (HD == 128) {
-          const uint64_t dK1 = umma_smem_desc(sk + C::K0_BYTES, 1024, UMMA_SW128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, dQ1 + 2 * k, dK1 + 2 * k, idesc_s, 1);
-        }
-        if (EXT == 1) {  // kext rows [64j, 64j+64) of the [256 x 32] one-hot table: 64 rows x 64 B = 4096 B per tile
-#pragma unroll
-          for (int k = 0; k < 2; ++k) umma_ss(tS, dQXw + 2 * k, dEw + (uint64_t)(j * 256 + 2 * k), idesc_s, 1);
-        }
-        if (EXT == 2) {  // a 64-key tile is one grid row: the same 64 x 64 identity for every tile
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tS, dQXg + 2 * k, dEg + 2 * k, idesc_s, 1);
-        }
-        umma_commit(&k_empty[ks]);
-        umma_commit(&bar_s[j & 1]);
-      }
-      __syncwarp();
-      if (++ks == ST) {
-        ks = 0;
-        kph ^= 1;
-      }
-    };
-    auto issue_pv = [&](int j) {
-      const uint32_t sv = sSt + vs * C::STAGE_BYTES + C::K0_BYTES + C::K1_BYTES;
-      const uint32_t tP = tmem_base + (j & 1) * BN3;
-      mbar_wait(&bar_p[j & 1], (uint32_t)((j >> 1) & 1));
-      mbar_wait(&v_full[vs], vph);
-      tc_fence_after();
-      if (issuer) {
-        const uint64_t dV = umma_smem_desc(sv, 1024, UMMA_SW128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ts(tO, tP + (k >> 1) * 32 + (k & 1) * 8, dV + 2 * k, idesc_o, (j | k) != 0);
-        umma_commit(&v_empty[vs]);
-        umma_commit(bar_pv);
-      }
-      __syncwarp();
-      if (++vs == ST) {
-        vs = 0;
-        vph ^= 1;
-      }
-    };
-    mbar_wait(bar_q, 0);
-    issue_s(0);
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_s(j + 1);
-      issue_pv(j);
-    }
-    if (issuer) umma_commit(bar_done);
-    __syncwarp();
-  } else {
-    // ================================ softmax / correction / epilogue ================================
-    // warps 2..9: two warps per TMEM lane quarter (warp & 3), each on 32 of a tile's 64 keys.  The two threads of a
-    // row share ONE reference maximum m without meeting at a barrier: P(j) is taken against an m that only ever
-    // moves to the joint maximum of tiles <= j-2, which both threads read from the tagged exchange slots (a thread
-    // at tile j is past tile j-2's publication of its partner: S(j) completes after PV(j-2) was issued, and PV(j-2)
-    // needed both arrivals on bar_p — the tag makes the reader robust against a late write regardless).  m is a
-    // reference point, not the exact maximum: exp2(t - m) may exceed 1 by the growth of the scores over 128 keys.
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row_in_tile = quarter * 32 + lane;
-    const int q_row = q0 + row_in_tile;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t tO = t_row + C::O_COL;
-    const int lim = p.causal ? min(kv_limit, q_row + 1) : kv_limit;  // key valid iff key < lim
-    const bf16* rb = nullptr;
-    if (EXT == 2) rb = p.row_bias + ((size_t)bh * p.seq_pad + min(q_row, p.seq_pad - 1)) * 64;
-    const float c1 = p.c1;
-    float m = -INFINITY, l = 0.f, m_lag = -INFINITY;
-    float add_next = 0.f;
-    if (EXT == 2) add_next = __bfloat162float(rb[0]) * LOG2E;
-    // own maximum of tile j (log2 domain, absolute) into slot j & 3, its two low mantissa bits replaced by the slot's
-    // generation (j >> 2) & 3 — m is a reference point, the 2^-21 relative perturbation is immaterial
-    auto publish = [&](int j, float v) {
-      xch[((j & 3) * 128 + row_in_tile) * 2 + half] = (__float_as_uint(v) & ~3u) | (uint32_t)((j >> 2) & 3);
-    };
-    auto fetch = [&](int j, int h) -> float {
-      volatile uint32_t* src = xch + ((j & 3) * 128 + row_in_tile) * 2 + h;
-      uint32_t bits = *src;
-      while ((bits & 3u) != (uint32_t)((j >> 2) & 3)) bits = *src;
-      return __uint_as_float(bits & ~3u);
-    };
-    uint32_t ra[32];
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const int key0 = j * BN3 + half * 32;
-      const uint32_t tS = t_row + sb * BN3 + half * 32;
-      const float add = add_next;
-      if (EXT == 2 && j + 1 < n_tiles) add_next = __bfloat162float(rb[j + 1]) * LOG2E;
-      const bool need_mask = (j * BN3 + BN3 > kv_limit) || (p.causal && j * BN3 + BN3 - 1 > q0);
-      float lsum = 0.f;
-      mbar_wait(&bar_s[sb], ph);
-      tc_fence_after();
-      tmem_ld32(tS, ra);
-      if (j == 0) {
-        // the first tile fixes m exactly: the one place where the pair meets (named barrier of 64 threads)
-        tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float t = fmaf(__uint_as_float(ra[e]), c1, add);
-          mx = fmaxf(mx, (!need_mask || key0 + e < lim) ? t : -INFINITY);
-        }
-        xch[(4 * 128 + row_in_tile) * 2 + half] = __float_as_uint(mx);   // untagged scratch slot behind the four
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        m = fmaxf(mx, __uint_as_float(xch[(4 * 128 + row_in_tile) * 2 + (half ^ 1)]));
-        publish(0, mx);
-      } else {
-        if (j >= 2) {
-          m_lag = fmaxf(m_lag, fmaxf(fetch(j - 2, 0), fetch(j - 2, 1)));
-          const bool grow = (m == -INFINITY) ? (m_lag > -INFINITY) : (m_lag > m + 8.0f);
-          if (__any_sync(0xffffffffu, grow)) {
-            // rescale O (half 0, after PV(j-1)) and l (both) to the new reference; rows that did not grow keep f = 1
-            const float m_new = grow ? m_lag : m;
-            const float f = (grow && m != -INFINITY) ? ex2(m - m_new) : 1.f;
-            if (half == 0) {
-              mbar_wait(bar_pv, (uint32_t)((j - 1) & 1));
-              tc_fence_after();
-#pragma unroll 1
-              for (int c = 0; c < HD / 16; ++c) {
-                uint32_t r[16];
-                tmem_ld16(tO + c * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * f);
-                tmem_st16(tO + c * 16, r);
-              }
-            }
-            l *= f;
-            m = m_new;
-          }
-        }
-        tmem_ld_wait();
-      }
-      // P = exp2(t - m) over this thread's 32 keys, written over its own first 16 score columns
-      {
-        const float addm = add - ((m == -INFINITY) ? 0.f : m);
-        uint32_t pk[16];
-        float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-        if (need_mask) softmax_exp_chunk<true>(ra, c1, addm, key0, lim, mx0, mx1, l0, l1, pk);
-        else softmax_exp_chunk<false>(ra, c1, addm, key0, lim, mx0, mx1, l0, l1, pk);
-        lsum = l0 + l1;
-        tmem_st16(tS, pk);
-        if (j > 0) publish(j, fmaxf(mx0, mx1) + ((m == -INFINITY) ? 0.f : m));
-      }
-      l += lsum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[sb]);
-    }
-
-    // ---- epilogue: the pair adds its row sums, then O / l → bf16 → out[b*seq + q_row, h*HD + d] (chunks split) ----
-    float* lx = reinterpret_cast<float*>(xch + 5 * 128 * 2);
-    lx[row_in_tile * 2 + half] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    l += lx[row_in_tile * 2 + (half ^ 1)];
-    mbar_wait(bar_done, 0);
-    tc_fence_after();
-    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
-    const int h = bh - b * p.heads;
-    long long out_r = (long long)b * p.seq + q_row;
-    if (p.out_row_map != nullptr) out_r = q_row < p.seq ? p.out_row_map[out_r] : -1;
-    bf16* orow = p.out + (size_t)(out_r < 0 ? 0 : out_r) * p.ldo + h * HD;
-    constexpr int NCH = HD / 16, C_SPLIT = (NCH + 1) / 2;
-#pragma unroll 1
-    for (int c = half ? C_SPLIT : 0; c < (half ? NCH : C_SPLIT); ++c) {
-      uint32_t r[16];
-      tmem_ld16(tO + c * 16, r);
-      tmem_ld_wait();
-      if (q_row < p.seq && out_r >= 0) {
-        uint4 o0, o1;
-        o0.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
-        o0.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
-        o0.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
-        o0.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
-        o1.x = pack_bf16(__uint_as_float(r[8]) * inv_l, __uint_as_float(r[9]) * inv_l);
-        o1.y = pack_bf16(__uint_as_float(r[10]) * inv_l, __uint_as_float(r[11]) * inv_l);
-        o1.z = pack_bf16(__uint_as_float(r[12]) * inv_l, __uint_as_float(r[13]) * inv_l);
-        o1.w = pack_bf16(__uint_as_float(r[14]) * inv_l, __uint_as_float(r[15]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + c * 16) = o0;
-        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// =============================================================================================
 // Window kernel: SAM 14x14 windowed attention (196 keys, hd 80, 32 rel-pos extension columns).
 //
 // The generic kernel spends most of a window CTA's life in its prologue (6400 two-tile CTAs per
@@ -1666,14 +1343,10 @@ int launch_attn(const llmseg_attn_params* p, cudaStream_t stream) {
   return 0;
 }
 
-constexpr bool ATTN_V5_DEFAULT = false;
-constexpr int A5_XCH_BYTES = 6 * 128 * 2 * 4;   // v5: exchange slots behind the barriers
-
-template <int HD, int EXT, bool V5 = false>
+template <int HD, int EXT>
 int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
   using C = A3Cfg<HD, EXT>;
-  constexpr int SMEM = C::SMEM_BYTES + (V5 ? A5_XCH_BYTES : 0);
-  static_assert(2 * (SMEM + 1024) <= 227 * 1024, "two CTAs per SM");
+  constexpr int SMEM = C::SMEM_BYTES;
   const int BH = p->batch * p->heads;
   CUtensorMap tmQa, tmQb, tmKa, tmKb, tmV, tmQx, tmE;
   {
@@ -1722,16 +1395,13 @@ int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
   d.out_row_map = p->out_row_map;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((p->seq + BM - 1) / BM, BH);
-  cfg.blockDim = dim3(V5 ? 320 : 192);
+  cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   cfg.attrs = attr;
   cfg.numAttrs = pdl_attr(attr, 0);
-  auto kern = [] {
-    if constexpr (V5) return attn5_kernel<HD, EXT>;
-    else return attn3_kernel<HD, EXT>;
-  }();
+  auto kern = attn3_kernel<HD, EXT>;
   static bool attr_done = false;
   if (!attr_done) {
     LLMSEG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1747,15 +1417,13 @@ int launch_attn3(const llmseg_attn_params* p, cudaStream_t stream) {
 // DINOv2 4097 tokens 880 -> 825 us); the SAM global layers (rel-pos extension columns: 13 instead of 9 score MMAs
 // per 128 keys, and twice the softmax warps per SM to hide their latencies) stay 8-10 % faster on the 128-key kernel.
 // LLMSEG_ATTN_V1 = 1 / 0 forces one of them (read per call: A/B runs flip it between launches).
-// LLMSEG_ATTN_V5 = 1 / 0: the rel-pos global heads (EXT == 2) on v3's schedule with 8 softmax warps (attn5_kernel).
+// (Round 2 also measured v3's schedule with v1's warp count — two softmax threads per row sharing a reference maximum two
+// tiles late, no per-tile barrier: correct, 967-1052 us against v1's 803-895 and v3's 894-964 on the SAM global shape.
+// Halving the keys a thread handles per visit costs more than the added warps hide; profiles/round2_attn.md.)
 template <int HD, int EXT>
 int launch_attn_any(const llmseg_attn_params* p, cudaStream_t stream) {
   const char* e = getenv("LLMSEG_ATTN_V1");
   const bool v1 = e != nullptr ? atoi(e) == 1 : EXT != 0;
-  if constexpr (EXT == 2) {
-    const char* e5 = getenv("LLMSEG_ATTN_V5");
-    if (e5 != nullptr ? atoi(e5) != 0 : ATTN_V5_DEFAULT) return launch_attn3<HD, EXT, true>(p, stream);
-  }
   return v1 ? launch_attn<HD, EXT>(p, stream) : launch_attn3<HD, EXT>(p, stream);
 }
 

@@ -21,18 +21,16 @@ ops.relpos_prep(q, rel, bh=B * H, seq=S, seq_pad=S, head_dim=hd, grid=64, inv_sc
 out = torch.empty(B * S, H * hd, device=dev, dtype=torch.bfloat16); kext = ops.make_kext(64, dev)
 fl = 4 * B * H * S * S * hd
 outs = {}
-def variant(v):   # v1: single 128-key score buffer, 8 softmax warps; v3: two 64-key buffers, 4 softmax warps; v5: 8
+def variant(v):   # v1: single 128-key score buffer, 8 softmax warps; v3: two 64-key buffers, 4 softmax warps
     os.environ["LLMSEG_ATTN_V1"] = "1" if v == "v1" else "0"
-    os.environ["LLMSEG_ATTN_V5"] = "1" if v == "v5" else "0"
-for v in ("v1", "v3", "v5", "v1", "v3", "v5", "v5", "v1"):      # interleaved
+for v in ("v1", "v3", "v1", "v3"):      # interleaved
     variant(v)
     o = torch.empty_like(out)
     us = t(lambda: ops.attention(q, k, vt, o, batch=B, heads=H, head_dim=hd, seq=S, seq_pad=S, scale=scale, qext=qext, kext=kext, row_bias=rb, ext_cols=64))
     outs[v] = o
     print(f"global attention B={B} {v}: {us:8.1f} us  {fl / us / 1e6:6.0f} TF/s", flush=True)
-print(f"global attention max|d| v3-v1 {(outs['v3'].float() - outs['v1'].float()).abs().max().item():.5f}  "
-      f"v5-v1 {(outs['v5'].float() - outs['v1'].float()).abs().max().item():.5f}", flush=True)
-os.environ.pop("LLMSEG_ATTN_V1"); os.environ["LLMSEG_ATTN_V5"] = "0"
+print(f"global attention max|d| v3-v1 {(outs['v3'].float() - outs['v1'].float()).abs().max().item():.5f}", flush=True)
+os.environ.pop("LLMSEG_ATTN_V1")
 if len(sys.argv) > 1 and sys.argv[1] == "global":
     sys.exit(0)
 # LLaMA causal (T=319, hd 128), CLIP (257, hd 64), DINOv2 (4097, hd 64) through both kernels
