@@ -124,6 +124,79 @@ norm_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Narrow rows (dim <= 256: one 16-byte vector per lane), many of them (the 1 M x 256 token stream of the SAM mask
+// decoder, the 256-channel neck): a warp takes R consecutive rows at once, so R loads per lane are in flight instead
+// of one — the one-row kernel above keeps 40 warps x 512 B = 20 KB per SM in flight and measured 3.8 TB/s on
+// LayerNorm(1 M x 256).  Same arithmetic as norm_kernel (two-pass variance from registers).
+// ---------------------------------------------------------------------------------------------
+template <bool RMS, int R>
+__global__ void __launch_bounds__(256)
+norm_narrow_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out,
+                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, int rows, int dim, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row0 = warp * R;
+  if (row0 >= rows) return;
+  const int nvec = dim >> 3;
+  const bool on = lane < nvec;
+  uint4 v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    v[r] = make_uint4(0, 0, 0, 0);
+    if (on && row0 + r < rows) v[r] = ld_stream16(reinterpret_cast<const uint4*>(in + (size_t)(row0 + r) * ld_in) + lane);
+  }
+  uint4 g = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+  if (on) {
+    g = __ldg(reinterpret_cast<const uint4*>(gamma) + lane);
+    if (!RMS && beta) b = __ldg(reinterpret_cast<const uint4*>(beta) + lane);
+  }
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  const float inv_n = 1.0f / (float)dim;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= rows) break;   // warp-uniform
+    const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+    float f[8], s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16(w[e]);
+      f[2 * e] = t.x;
+      f[2 * e + 1] = t.y;
+      s += t.x + t.y;
+      ss += t.x * t.x + t.y * t.y;
+    }
+    float mean = 0.f, rstd;
+    if (RMS) {
+      rstd = rsqrtf(warp_sum(ss) * inv_n + eps);
+    } else {
+      mean = warp_sum(s) * inv_n;
+      float sq = 0.f;
+      if (on) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // pairwise like norm_kernel: bit-equal statistics
+          const float a = f[2 * e] - mean, c = f[2 * e + 1] - mean;
+          sq += a * a + c * c;
+        }
+      }
+      rstd = rsqrtf(warp_sum(sq) * inv_n + eps);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 gg = unpack_bf16(gw[e]);
+      if (RMS) {
+        const float a = bf16_round(f[2 * e] * rstd), c = bf16_round(f[2 * e + 1] * rstd);
+        o[e] = pack_bf16(a * gg.x, c * gg.y);
+      } else {
+        const float2 bb = unpack_bf16(bw[e]);
+        o[e] = pack_bf16((f[2 * e] - mean) * rstd * gg.x + bb.x, (f[2 * e + 1] - mean) * rstd * gg.y + bb.y);
+      }
+    }
+    if (on) reinterpret_cast<uint4*>(out + (size_t)(row0 + r) * ld_out)[lane] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Streaming variant for large problems (>= 1 MB of rows): persistent, one CTA per SM, every warp owns a ring of
 // row buffers in shared memory that `cp.async.bulk` (the TMA engine's 1-D copy) keeps full — up to 24 KB per warp,
 // 192 KB per SM in flight with no register cost, and loads stay in flight while the warp normalises and stores
@@ -326,8 +399,18 @@ int launch_norm(const void* in, int ld_in, void* out, int ld_out, const void* ga
     return 0;
   }
   const int warps_per_block = 8;
-  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
   const int per_lane = (dim / 8 + 31) / 32;
+  if (per_lane <= 1 && rows >= 8192 && src_map == nullptr && stats == nullptr && out != nullptr) {
+    constexpr int R = 4;
+    const int nb = ((rows + R - 1) / R + warps_per_block - 1) / warps_per_block;
+    norm_narrow_kernel<RMS, R><<<nb, warps_per_block * 32, 0, stream>>>(
+        static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out, static_cast<const bf16*>(gamma),
+        static_cast<const bf16*>(beta), rows, dim, eps);
+    LLMSEG_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
 #define LLMSEG_NORM_LAUNCH(NV_)                                                              \
   norm_kernel<RMS, NV_><<<blocks, warps_per_block * 32, 0, stream>>>(                        \
       static_cast<const bf16*>(in), ld_in, static_cast<bf16*>(out), ld_out,                  \

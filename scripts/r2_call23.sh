@@ -1,0 +1,11 @@
+set -x
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 > gpurun_out/r2q_pytest_gpu.log; cat gpurun_out/r2q_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 900 python bench.py 2>gpurun_out/r2q_bench.err | tail -1 > gpurun_out/r2q_bench_b8.json; python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r2q_bench_b8.json"))
+for k in ("value", "ms_per_step", "e2e", "clocks", "gpu_launches", "batch1", "configs3", "configs4", "proposals", "eager_gpu_baseline", "cpu_baseline"):
+    print(k, json.dumps(d.get(k))[:400])
+print(d["roofline"]["frac"], d["roofline_attn"]["frac"], d["roofline_all_gemms"]["frac"])
+PY
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r2q_reference_arm.json; cut -c1-600 gpurun_out/r2q_reference_arm.json

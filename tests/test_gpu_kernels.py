@@ -216,6 +216,29 @@ def test_norms(cuda_lib, rows, dim, eps):
     assert (y.float() - ref4).abs().max().item() <= _ulp_tol(ref4)
 
 
+@pytest.mark.parametrize("rows,dim", [(8192 + 3, 256), (20001, 64), (9000, 200)])
+def test_narrow_row_norm(cuda_lib, rows, dim):
+    """Rows of <= 256 values, >= 8192 of them (the mask decoder's token stream, the neck): the kernel that takes four
+    rows per warp (csrc/norm.cu norm_narrow_kernel) — bit-equal to the one-row kernel (same arithmetic), against torch,
+    with a row count that is no multiple of 4, a strided input, and in place."""
+    from llmseg_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    xs = _bf(torch.randn(rows, dim + 8, generator=g) * 2 + 0.5)
+    x = xs[:, :dim]
+    gm, bt = _bf(1 + 0.1 * torch.randn(dim, generator=g)), _bf(0.1 * torch.randn(dim, generator=g))
+    y = ops.layernorm(x, gm, bt, 1e-6)
+    ref = torch.nn.functional.layer_norm(x.float(), (dim,), gm.float(), bt.float(), 1e-6)
+    assert (y.float() - ref).abs().max().item() <= _ulp_tol(ref)
+    one_row = torch.cat([ops.layernorm(x[i:i + 4096], gm, bt, 1e-6) for i in range(0, rows, 4096)])   # < 8192 rows per call
+    assert torch.equal(y, one_row)
+    yr = ops.rmsnorm(x, gm, 1e-6)
+    xf = x.float()
+    refr = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().float() * gm.float()
+    assert (yr.float() - refr).abs().max().item() <= _ulp_tol(refr)
+    xc = x.contiguous()
+    assert torch.equal(ops.layernorm(xc, gm, bt, 1e-6, out=xc), y)
+
+
 @pytest.mark.parametrize("rows,dim,rms", [(6000, 1280, False), (2100, 4096, True), (3000, 1024, False)])
 def test_streaming_norm_with_row_gather(cuda_lib, rows, dim, rms):
     """The bulk-copy-staged kernel (>= 1 MB, rows >= 2 KB) with a gather map that repeats rows and contains
