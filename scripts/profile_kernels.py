@@ -60,7 +60,7 @@ elif which == "gemm_qkv_sam":    # SAM windowed layer's QKV projection as the en
     for _ in range(iters):
         ops.gemm_qkv(x, w, bias, q, k, vt, heads=H, head_dim=hd, seq_in=sw, seq_pad=sw_pad, row_map=tok2win, row_stats=st)
 elif which.startswith("gemm"):
-    shapes = {"gemm_qkv": (4096 * B, 3840, 1280), "gemm_mlp1": (4096 * B, 5120, 1280), "gemm_mlp2": (4096 * B, 1280, 5120),
+    shapes = {"gemm_up1": (1048576, 256, 256), "gemm_qkv": (4096 * B, 3840, 1280), "gemm_mlp1": (4096 * B, 5120, 1280), "gemm_mlp2": (4096 * B, 1280, 5120),
               "gemm_llama_gu": (319 * B, 22016, 4096), "gemm_llama_down": (319 * B, 4096, 11008),
               "gemm_proj": (4096 * B, 1280, 1280)}
     M, N, K = shapes[which]
@@ -74,6 +74,19 @@ elif which.startswith("gemm"):
                 x = torch.randn(M, N, device=dev).bfloat16(); st = ops.gemm_stats_buffer(M, N, M, 1e-6)
             ops.gemm(a, w, bias, residual=x, out=x, stats_out=st)
         else: ops.gemm(a, w, bias)
+elif which == "amg_tok2img":     # mask decoder token->image attention, 256 prompts, per-prompt K / V as column views
+    P = 256
+    q = torch.randn(P * 7, 128, device=dev).bfloat16(); kv = torch.randn(P * 4096, 256, device=dev).bfloat16()
+    for _ in range(iters): ops.tok2img_attention(q, kv[:, :128], kv[:, 128:], P, False)
+elif which == "amg_img2tok":
+    P = 256
+    qb = torch.randn(P * 4096, 384, device=dev).bfloat16(); k = torch.randn(P * 7, 128, device=dev).bfloat16(); v = torch.randn_like(k)
+    for _ in range(iters): ops.img2tok_attention(qb[:, 256:384], k, v, P, False)
+elif which == "amg_upscale":     # fused LayerNorm2d+GELU -> ConvTranspose #2 -> hyper-network product, 256 prompts
+    P = 256
+    u1 = torch.randn(P * 4096, 256, device=dev).bfloat16(); gm = torch.ones(64, device=dev).bfloat16(); bt = torch.zeros(64, device=dev).bfloat16()
+    w2 = (torch.randn(128, 64, device=dev) / 8).bfloat16(); b2 = torch.zeros(128, device=dev).bfloat16(); hy = torch.randn(P, 4, 32, device=dev).bfloat16()
+    for _ in range(iters): ops.upscale_logits(u1, gm, bt, w2, b2, hy, P)
 elif which == "maskpool":
     K = 64
     segs = torch.rand(B * K, 256, 256, device=dev).bfloat16(); emb = torch.randn(B, 4096, 256, device=dev).bfloat16()
