@@ -703,12 +703,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
 //   2  bias + TMA residual + row statistics, staged TMA store          SAM / DINOv2 proj and lin2 (folded norms next)
 //   3  TMA residual, no bias, staged TMA store                         LLaMA o_proj / down_proj, CLIP-less text branch
 //   4  bias + TMA residual, staged TMA store                           SAM mask-decoder projections (proposal generation)
+//   5  bias alone, staged TMA store                                    mask-decoder ConvTranspose #1 as a GEMM
 //   0  generic (every option a runtime test) — everything else
 // The variants also read TMEM one chunk ahead (the next 32 columns are in flight while this chunk is worked on).
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
 struct EpiX {
-  static constexpr bool bias = EPI == 1 || EPI == 2 || EPI == 4;
+  static constexpr bool bias = EPI == 1 || EPI == 2 || EPI == 4 || EPI == 5;
   static constexpr bool gelu = EPI == 1;
   static constexpr bool res = EPI == 2 || EPI == 3 || EPI == 4;
   static constexpr bool stats = EPI == 2;
@@ -758,7 +759,7 @@ __device__ __forceinline__ void epi_plain_x(const uint32_t* r, float rs, const u
   }
 }
 
-// one epilogue warp's share (32 rows x BN/2 columns) of a finished tile, variants 1-4 (pair kernel, BN = 256,
+// one epilogue warp's share (32 rows x BN/2 columns) of a finished tile, variants 1-5 (pair kernel, BN = 256,
 // N % 64 == 0, rows not scattered, C through staged TMA stores, residual through the TMA landing buffers)
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_plain_fast(const GemmDev& p, uint32_t taddr, int m_blk, int n_blk, int quarter,
@@ -1644,6 +1645,8 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
       if (p->act == LLMSEG_ACT_NONE && res && d.tma_res && p->stats_out == nullptr && p->bias != nullptr &&
           p->row_stats == nullptr)
         return launch2<256, LLMSEG_GEMM_PLAIN, false, 4>(tmA, tmB, tmC, tmR, d, pgrid, stream);
+      if (p->act == LLMSEG_ACT_NONE && !res && p->stats_out == nullptr && p->bias != nullptr && p->row_stats == nullptr)
+        return launch2<256, LLMSEG_GEMM_PLAIN, false, 5>(tmA, tmB, tmC, tmR, d, pgrid, stream);
     }
     if (bn == 256) {
       LLMSEG_GEMM2_DISPATCH(256)

@@ -224,19 +224,28 @@ class SamProposalGenerator:
                 iou_parts.append(iou)
             iou_preds = torch.cat(iou_parts, dim=0)
         cand_logits = low_res.reshape(P * 3, 256, 256)
-        stats = ops.mask_stats(cand_logits, None, 0.0, stability_score_offset).cpu().numpy()          # sync 1
-        iou_np = iou_preds.reshape(-1).float().cpu().numpy()
-        # ---- host: <= 3 * P records (reference automatic_mask_generator.py:288-304)
+        empty = {"segs": torch.zeros((0, 256, 256), dtype=BF16, device=dev), "boxes": torch.zeros((0, 4), dtype=torch.int64),
+                 "iou_preds": torch.zeros(0), "stability": torch.zeros(0), "areas": torch.zeros(0, dtype=torch.int64),
+                 "points": torch.zeros((0, 2)), "n_masks": 0, "candidates": torch.zeros(0, dtype=torch.int64)}
+        # ---- host: <= 3 * P records (reference automatic_mask_generator.py:288-304).  The predicted-IoU filter comes
+        # first, as upstream, so the up-sampled statistics are only evaluated for the candidates that pass it
+        iou_np = iou_preds.reshape(-1).float().cpu().numpy()                                           # sync 1
         idx = np.arange(P * 3)
         keep = iou_np > pred_iou_thresh if pred_iou_thresh > 0.0 else np.ones(P * 3, dtype=bool)
+        pre = idx[keep]
+        if pre.size == 0:
+            return empty
+        if pre.size == P * 3:
+            stats = ops.mask_stats(cand_logits, None, 0.0, stability_score_offset).cpu().numpy()      # sync 2
+        else:
+            stats = np.zeros((P * 3, 8), dtype=np.int32)
+            stats[pre] = ops.mask_stats(cand_logits, torch.from_numpy(pre.astype(np.int32)).to(dev), 0.0,
+                                        stability_score_offset).cpu().numpy()
         with np.errstate(divide="ignore", invalid="ignore"):
             stab = stats[:, 1].astype(np.float32) / stats[:, 2].astype(np.float32)
         if stability_score_thresh > 0.0:
             keep &= stab >= np.float32(stability_score_thresh)
         idx = idx[keep]
-        empty = {"segs": torch.zeros((0, 256, 256), dtype=BF16, device=dev), "boxes": torch.zeros((0, 4), dtype=torch.int64),
-                 "iou_preds": torch.zeros(0), "stability": torch.zeros(0), "areas": torch.zeros(0, dtype=torch.int64),
-                 "points": torch.zeros((0, 2)), "n_masks": 0, "candidates": torch.zeros(0, dtype=torch.int64)}
         if idx.size == 0:
             return empty
         boxes = np.stack([1023 - stats[:, 3], 1023 - stats[:, 4], stats[:, 5], stats[:, 6]], axis=1)
@@ -244,7 +253,7 @@ class SamProposalGenerator:
         order = idx[np.argsort(-iou_np[idx], kind="stable")]                                           # score order
         if order.size > 4096:
             raise ValueError(f"{order.size} candidates after filtering; box NMS handles at most 4096")
-        keep_nms = ops.box_nms(torch.from_numpy(boxes[order].astype(np.float32)).to(dev), box_nms_thresh).cpu().numpy()  # sync 2
+        keep_nms = ops.box_nms(torch.from_numpy(boxes[order].astype(np.float32)).to(dev), box_nms_thresh).cpu().numpy()  # sync 3
         kept = order[keep_nms.astype(bool)]
         areas = stats[kept, 0].astype(np.int64)
         top = kept[np.argsort(-areas, kind="stable")[:top_k]]                                          # largest first

@@ -130,7 +130,7 @@ def test_gemm_streamk_tail_short_k(cuda_lib, N, mode, monkeypatch):
         assert (s0 - s1).abs().max().item() <= 2e-3 * float(s0.abs().max())
 
 
-@pytest.mark.parametrize("variant", ["gelu", "res_stats", "res", "bias_res_mod"])
+@pytest.mark.parametrize("variant", ["gelu", "res_stats", "res", "bias_res_mod", "bias"])
 def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
     """The straight-line epilogue variants of the CTA-pair kernel (csrc/gemm.cu EpiX 1-4: bias + GELU (+ folded norm),
     bias + TMA residual + row statistics, TMA residual alone, bias + TMA residual from a repeating row table) against the generic epilogue on the same problem —
@@ -148,6 +148,8 @@ def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
         if variant == "gelu":
             st = ops.norm_stats(a, 1e-6)
             return ops.gemm(a, w, b, act="gelu", row_stats=st), None
+        if variant == "bias":           # variant 5: bias alone
+            return ops.gemm(a, w, b), None
         if variant == "bias_res_mod":   # variant 4: bias + a 256-row residual table repeated down the output (TMA landing)
             return ops.gemm(a, w, b, residual=x0[:256], res_mod=256), None
         x = x0.clone()
@@ -170,6 +172,8 @@ def test_gemm_epilogue_variants_equal_generic(cuda_lib, variant, monkeypatch):
         ref = torch.nn.functional.gelu((af * torch.rsqrt(var + 1e-6)) @ wf.T + b.float())
     elif variant == "res_stats":
         ref = af @ wf.T + b.float() + x0.float()
+    elif variant == "bias":
+        ref = af @ wf.T + b.float()
     elif variant == "bias_res_mod":
         ref = af @ wf.T + b.float() + x0[:256].float().repeat(9, 1)[:M]
         monkeypatch.setenv("LLMSEG_GEMM_TMA_RES", "0")   # per-lane residual loads: same values, same arithmetic
