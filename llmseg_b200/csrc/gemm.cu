@@ -218,7 +218,10 @@ __device__ __forceinline__ void epi_swiglu(const GemmDev& p, const uint32_t* r, 
 }
 
 // ---- QKV split (no RoPE): 8-column groups never straddle a head (head_dim % 8 == 0) ----------
-__device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int row, int n0,
+// acc * rs + bias on packed pairs (rs: folded-norm row scale, 1 without; pf.bias is zero without a bias): the epilogue
+// of the K = 1280 QKV projection paces its mainloop (ncu r2n: 2207 instructions per warp and tile), so the scale, the
+// bias and the conversion are one FFMA2 + one pack per pair, and the transposed V stores share one packed conversion.
+__device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, float rs, int row, int n0,
                                         const EpiPrefetch& pf) {
   const int b = row / p.seq_in;
   const int s = row - b * p.seq_in;
@@ -230,36 +233,32 @@ __device__ __forceinline__ void epi_qkv(const GemmDev& p, const uint32_t* r, int
   const int rem0 = n0 - which * hw;
   int h = rem0 / hd;
   int d = rem0 - h * hd;
+  const float2 rs2 = make_float2(rs, rs);
+  const uint32_t sp = (uint32_t)p.seq_pad;
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int col = n0 + j;
     if (col >= p.N) break;
-    float v[8];
+    const uint4 bb = pf.bias[j >> 3];
+    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+    uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
-    if (p.bias) {
-      const uint4 bb = pf.bias[j >> 3];
-      const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = unpack_bf16(bw[e]);
-        v[2 * e] += f.x;
-        v[2 * e + 1] += f.y;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 v = ffma2(make_float2(__uint_as_float(r[j + 2 * e]), __uint_as_float(r[j + 2 * e + 1])), rs2,
+                             unpack_bf16(bw[e]));
+      o[e] = pack_bf16(v.x, v.y);
     }
     const size_t bh = (size_t)b * p.heads + h;
     if (which < 2) {
       bf16* dst = (which == 0 ? p.q : p.k) + (bh * p.seq_pad + s) * hd + d;
-      uint4 o;
-      o.x = pack_bf16(v[0], v[1]);
-      o.y = pack_bf16(v[2], v[3]);
-      o.z = pack_bf16(v[4], v[5]);
-      o.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(dst) = o;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
     } else {
-      bf16* dst = p.vt + (bh * hd + d) * p.seq_pad + s;
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.vt) + (bh * hd + d) * p.seq_pad + s;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dst[(size_t)e * p.seq_pad] = __float2bfloat16_rn(v[e]);
+      for (int e = 0; e < 4; ++e) {
+        dst[(2 * e) * sp] = (uint16_t)(o[e] & 0xffffu);
+        dst[(2 * e + 1) * sp] = (uint16_t)(o[e] >> 16);
+      }
     }
     d += 8;   // 8-column groups never straddle a head (head_dim % 8 == 0)
     if (d >= hd) {
@@ -629,10 +628,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       tmem_ld_wait();
       if (ci + 1 < NC) tmem_ld32(taddr + (c + 1) * 32, r[(ci + 1) & 1]);
       if (sk.n_peers > 0) sk_accumulate(p, BN, r[ci & 1], c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
-      if (fold) row_scale(r[ci & 1], rs);
+      if (fold && MODE == LLMSEG_GEMM_SWIGLU) row_scale(r[ci & 1], rs);   // QKV folds the scale into its bias FFMA2
       if (live && n0 < p.N) {
         if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r[ci & 1], out_row, n0);
-        else epi_qkv(p, r[ci & 1], out_row, n0, pf);
+        else epi_qkv(p, r[ci & 1], fold ? rs : 1.f, out_row, n0, pf);
       }
     }
   } else {
@@ -651,7 +650,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
       if (MODE != LLMSEG_GEMM_SWIGLU) epi_prefetch(p, pf, MODE == LLMSEG_GEMM_PLAIN ? out_row : 0, n0, live);
       tmem_ld_wait();
       if (sk.n_peers > 0) sk_accumulate(p, BN, r, c * 32, quarter * 32 + lane, sk.pair, sk.cta_rank, sk.n_peers);
-      if (fold && MODE != LLMSEG_GEMM_PLAIN) row_scale(r, rs);  // PLAIN folds the scale into its bias FFMA2
+      if (fold && MODE == LLMSEG_GEMM_SWIGLU) row_scale(r, rs);  // PLAIN / QKV fold the scale into their bias FFMA2
       const bool staged = MODE == LLMSEG_GEMM_PLAIN && epi_stage != nullptr && p.tma_store;
       if (tres && n0 < p.N) {
         mbar_wait(&res_bar[ci & 1], (*res_ph >> (ci & 1)) & 1u);
@@ -667,7 +666,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmDev& p, float* rp_stage,
           epi_plain(p, r, fold ? rs : 1.f, out_row, n0, pf, st_s, st_ss, staged ? epi_stage + lane * 128 : nullptr, (c & 1) * 4,
                     lane & 7, tres ? res_stage + (ci & 1) * 2048 + lane * 64 : nullptr, (lane >> 1) & 3);
         else if (MODE == LLMSEG_GEMM_SWIGLU) epi_swiglu(p, r, out_row, n0);
-        else epi_qkv(p, r, out_row, n0, pf);
+        else epi_qkv(p, r, fold ? rs : 1.f, out_row, n0, pf);
       }
       if (tres) {
         // every lane has consumed its row of this landing buffer: refill it with the block two steps ahead
