@@ -1549,6 +1549,8 @@ extern "C" int llmseg_gemm(const llmseg_gemm_params* p, void* stream_) {
   const int sms = num_sms();
   int bn = 256;
   if (p->N < 256 || m_tiles * ((p->N + 255) / 256) < sms) bn = 128;
+  // (N = 384 — the mask decoder's image-side projection, a full and a half-empty 256-wide tile per row block — measured
+  //  407 us with 256-wide tiles, 736 us with 128-wide ones, 470 us as a 256 + 128 pair of GEMMs: the wide tile stays)
   // (tried: 128-wide pair tiles when 256-wide ones quantise badly, e.g. LLaMA o_proj/down at batch 8 with
   //  2.16 waves — slower: a 256x128 pair tile needs twice the L2->SM bytes per flop and becomes L2-bound.)
   d.num_m_tiles = m_tiles;
