@@ -635,22 +635,43 @@ upscale_logits_kernel(const bf16* __restrict__ u1, const bf16* __restrict__ gamm
       }
     }
     // lane holds, per (mt, row half rh, n-tile nt): columns nh*64 + nt*8 + qc, +1  ->  sub-sub-pixel s = nh*2 + nt/4,
-    // channels (nt & 3)*8 + qc, +1
+    // channels (nt & 3)*8 + qc, +1.  Channel group t outermost: the six hyper-network weights of a lane's two
+    // channels are read once per t and serve all eight (mt, rh, pl) dot products.
+    float d[2][2][2][3];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) d[mt][rh][pl][0] = d[mt][rh][pl][1] = d[mt][rh][pl][2] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = t * 8 + qc;
+      const float2 h0 = *reinterpret_cast<const float2*>(hy + c), h1 = *reinterpret_cast<const float2*>(hy + 32 + c),
+                   h2 = *reinterpret_cast<const float2*>(hy + 64 + c);
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const int nt = pl * 4 + t;
+        const float2 bb = *reinterpret_cast<const float2*>(bias2 + nh * 64 + nt * 8 + qc);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const float2 g = gelu2(make_float2(acc[mt][nt][rh * 2] + bb.x, acc[mt][nt][rh * 2 + 1] + bb.y));
+            float* dd = d[mt][rh][pl];
+            dd[0] = fmaf(g.x, h0.x, dd[0]); dd[0] = fmaf(g.y, h0.y, dd[0]);
+            dd[1] = fmaf(g.x, h1.x, dd[1]); dd[1] = fmaf(g.y, h1.y, dd[1]);
+            dd[2] = fmaf(g.x, h2.x, dd[2]); dd[2] = fmaf(g.y, h2.y, dd[2]);
+          }
+      }
+    }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
-          float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int nt = pl * 4 + t, col = nh * 64 + nt * 8 + qc, c = t * 8 + qc;
-            const float2 g = gelu2(make_float2(acc[mt][nt][rh * 2] + bias2[col], acc[mt][nt][rh * 2 + 1] + bias2[col + 1]));
-            d0 = fmaf(g.x, hy[c], d0); d0 = fmaf(g.y, hy[c + 1], d0);
-            d1 = fmaf(g.x, hy[32 + c], d1); d1 = fmaf(g.y, hy[32 + c + 1], d1);
-            d2 = fmaf(g.x, hy[64 + c], d2); d2 = fmaf(g.y, hy[64 + c + 1], d2);
-          }
+          float d0 = d[mt][rh][pl][0], d1 = d[mt][rh][pl][1], d2 = d[mt][rh][pl][2];
 #pragma unroll
           for (int o = 1; o < 4; o <<= 1) {
             d0 += __shfl_xor_sync(0xffffffffu, d0, o);
