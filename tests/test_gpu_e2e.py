@@ -395,6 +395,28 @@ def test_plan_buckets_survive_varying_shapes(cuda_lib):
     assert all(len(eng._plans[s]) <= eng.max_plans for s in ("image", "text", "sel"))
 
 
+def test_plan_cache_eviction_bounds_memory(cuda_lib):
+    """More prompt-length buckets than `max_plans` (6 > 4), visited round-robin so that every call evicts the least
+    recently used text plan (static buffers + captured graph + its private pool) and re-captures: device memory after
+    the third and fourth sweep equals the second's — nothing a plan owned survives its eviction."""
+    from llmseg_b200 import synthetic
+    model, sd, inp, ocfg = _setup((2, (1,), 2, 1), 2, 8, 16)
+    eng = model.engine
+    after = []
+    for sweep in range(4):
+        for tt in (20, 50, 80, 110, 140, 170):
+            x = synthetic.make_inputs(model.cfg, 2, 8, tt, seed=tt, device=DEV)
+            with torch.no_grad():
+                for _ in range(2):                     # second use of a plan captures its graph
+                    out = model.forward(**x)
+            assert out["pred_similarity"][0].shape == (1, 8)
+        torch.cuda.synchronize()
+        after.append(torch.cuda.memory_allocated())
+        assert len(eng._plans["text"]) <= eng.max_plans
+    print("allocated after each sweep (MB):", [round(a / 2 ** 20, 1) for a in after])
+    assert after[2] <= after[1] + (1 << 20) and after[3] <= after[1] + (1 << 20)
+
+
 def test_reference_shaped_constructor(cuda_lib):
     """`LISAForCausalLM(config, **kwargs)` + `load_state_dict` + `.eval()` + `.state_dict()` (reference
     model/LISA.py:144-170): an nn.Module built the way the reference's scripts build theirs gives the same outputs
