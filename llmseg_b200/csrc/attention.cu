@@ -1169,6 +1169,9 @@ attn_win_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant_
           }
         }
       }
+      // (fetching this thread's out_row_map entry at the top of the item instead of right before its use measured
+      //  SLOWER too — 94.0 vs 86.2 us, same box, two library builds, scripts/gpu_attn_win_time.py: the kernel's two query
+      //  tiles run half a period apart and anything that shifts one warp group's timing moves them into each other)
       // (releasing the columns right after the TMEM read, before the row stores, measured SLOWER twice — 134-141 us
       //  against 118 with the two-pass softmax, 98 against 93.6 with the single pass: the stores are part of what
       //  keeps the two tiles half a period apart)
