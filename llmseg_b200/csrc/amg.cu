@@ -3,9 +3,14 @@
 //
 //   point_tokens     prompt encoder for one foreground point per prompt + output tokens
 //                    (reference segment_anything/modeling/prompt_encoder.py:73-90,186-195; mask_decoder.py:123-131)
-//   tok2img_attn     7 tokens x 4096 image keys, 8 heads x 16 (reference modeling/transformer.py:222-242 as called at
-//                    :169-172 and :101-103): one block per (prompt, head), keys streamed once, fp32 softmax
-//   img2tok_attn     4096 image queries x 7 token keys (transformer.py:179-182): thread per (image token, head)
+//   tok2img_attn_mma 7 tokens x 4096 image keys, 8 heads x 16 (reference modeling/transformer.py:222-242 as called at
+//                    :169-172 and :101-103): block per prompt, warp per head, K / V through a warp-private cp.async ring,
+//                    both products on mma.sync, online softmax (tok2img_attn: the CUDA-core kernel it replaced, kept
+//                    behind LLMSEG_T2I_V1 and compared with it in the tests)
+//   img2tok_attn     4096 image queries x 7 token keys (transformer.py:179-182): warp per head, token per lane, K / V as
+//                    warp-uniform shared-memory broadcasts, query / output tiles staged with whole-row copies
+//   upscale_logits   LayerNorm2d(64) + GELU -> second ConvTranspose (mma.sync) + GELU -> hyper-network product in one
+//                    kernel (mask_decoder.py:56-64,139-157); the three un-fused steps stay as the comparison path:
 //   ln64_gelu        LayerNorm2d(64) + GELU of the first up-scaling step on the un-shuffled ConvTranspose output
 //                    (mask_decoder.py:56-62): every group of 64 columns is one output pixel
 //   mask_logits      hyper-network product on the un-shuffled second ConvTranspose output -> low-res mask logits
@@ -17,8 +22,8 @@
 //                    again straight from the low-res logits: the 1024 x 1024 masks never exist unless asked for
 //   mask_binarize    the 1024 x 1024 binary masks themselves (what `origin_segs_list` holds), on request
 //
-// All of these are HBM / latency bound integer-and-compare work; the dense algebra of the decoder (projections, MLPs,
-// ConvTranspose-as-GEMM) runs on llmseg_gemm.
+// Most of these are HBM / latency bound integer-and-compare work; the dense algebra of the decoder (projections, MLPs,
+// the first ConvTranspose as a GEMM) runs on llmseg_gemm.
 #include <atomic>
 
 #include "common.cuh"

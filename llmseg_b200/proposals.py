@@ -7,8 +7,9 @@ Per image, with the class defaults of the reference (32 x 32 point grid, one cro
 
   1. prompt encoder: one foreground point + the padding point per prompt -> 7 decoder tokens      (llmseg_point_tokens)
   2. mask decoder: two-way transformer (2 blocks + final attention), 4x up-scaling, hyper-network product, IoU head
-     — every linear / ConvTranspose on llmseg_gemm, the 7-token attentions on llmseg_small_attention /
-     llmseg_tok2img_attention / llmseg_img2tok_attention                                           -> low-res logits [P,3,256,256]
+     — every linear and the first ConvTranspose on llmseg_gemm, the 7-token attentions on llmseg_small_attention /
+     llmseg_tok2img_attention / llmseg_img2tok_attention, the rest of the up-scaling in llmseg_upscale_logits
+                                                                                                   -> low-res logits [P,3,256,256]
   3. per candidate, on the 4x up-sampled logits evaluated on the fly: area, stability counts, box  (llmseg_mask_stats)
   4. predicted-IoU / stability filters, score sort (host, <= 3072 records), box NMS                (llmseg_box_nms)
   5. the `top_k` largest survivors -> antialiased 256 x 256 soft masks                            (llmseg_mask_soft)
